@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE CODE (build container only).
+
+TEST INFRASTRUCTURE.  Imports the unmodified reference modules from
+/root/reference with the three shims of SURVEY.md §8c (typeguard no-op, no
+pretrained weights, offline tokenizer built from the reference's own
+``whisper/assets/multilingual.tiktoken``) and stores small input/output
+vectors.  /root/reference does not exist on the GPU box, so the committed
+fixtures are what travels.  Run:  python oracle/make_golden.py
+"""
+import base64
+import json
+import os
+import pickle
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+sys.path[:0] = [f"{REF}/espnet", f"{REF}/espnet/whisper"]
+import typeguard  # noqa: E402
+
+typeguard.check_argument_types = lambda *a, **k: True
+typeguard.check_return_type = lambda *a, **k: True
+
+import torch  # noqa: E402
+import whisper  # noqa: E402
+from whisper.model import MultiHeadAttention  # noqa: E402
+from espnet2.asr.encoder.whisper_encoder import OpenAIWhisperEncoder  # noqa: E402
+from espnet2.asr.espnet_model import ESPnetASRModel  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import aga_oracle as O  # noqa: E402
+
+OUT = os.path.join(HERE, "..", "tests", "golden")
+PKG_DATA = os.path.join(HERE, "..", "attention-guided-adaptation-for-code-switching-speech-recognition_b200", "data")
+os.makedirs(OUT, exist_ok=True)
+os.makedirs(PKG_DATA, exist_ok=True)
+torch.set_num_threads(4)
+
+
+# ----------------------------------------------------------------------------- tokenizer shim
+def load_tiktoken_ranks(path):
+    ranks = {}
+    with open(path) as f:
+        for line in f:
+            if not line.strip():
+                continue
+            tok, rank = line.split()
+            ranks[int(rank)] = base64.b64decode(tok)
+    return ranks
+
+
+class OfflineTokenizer:
+    """convert_ids_to_tokens in HF style from the reference's own BPE asset."""
+
+    def __init__(self):
+        self.ranks = load_tiktoken_ranks(f"{REF}/espnet/whisper/whisper/assets/multilingual.tiktoken")
+        self.b2u = O.bytes_to_unicode()
+        self.n_base = len(self.ranks)
+        assert self.n_base == 50257, self.n_base
+
+    def token_string(self, i):
+        i = int(i)
+        if i < self.n_base:
+            return "".join(self.b2u[b] for b in self.ranks[i])
+        if i == 50257:
+            return "<|endoftext|>"
+        return f"<|special_{i}|>"
+
+    def convert_ids_to_tokens(self, ids):
+        return [self.token_string(i) for i in (ids.tolist() if hasattr(ids, "tolist") else ids)]
+
+
+TOK = OfflineTokenizer()
+
+
+def make_lid_table(vocab=51865):
+    tab = np.zeros(vocab, dtype=np.uint8)
+    for i in range(vocab):
+        tab[i] = O.lid_class_of_token_string(TOK.token_string(i))
+    return tab
+
+
+# ----------------------------------------------------------------------------- model shims
+def bare_asr_model():
+    m = object.__new__(ESPnetASRModel)
+    torch.nn.Module.__init__(m)
+    m.tokenizer = TOK
+    m.attention_count = {l: {h: 0 for h in range(1, 13)} for l in range(1, 13)}
+    return m
+
+
+def fake_encoder_self():
+    s = types.SimpleNamespace()
+    s.n_fft, s.win_length, s.hop_length, s.n_mels = 400, 400, 160, 80
+    s.mel_filters = whisper.audio.mel_filters
+    return s
+
+
+def synth_audio(B, N, seed, kind):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "noise":
+        return (0.1 * torch.randn(B, N, generator=g)).clamp(-1, 1)
+    t = torch.arange(N, dtype=torch.float64) / 16000.0
+    out = []
+    for b in range(B):
+        x = 0.0
+        for (f0, f1, a) in [(200.0, 3000.0, 0.5), (7000.0, 500.0, 0.2), (50.0, 120.0, 0.3)]:
+            ph = 2 * np.pi * (f0 * t + 0.5 * (f1 - f0) * t * t / (N / 16000.0) * (1 + 0.1 * b))
+            x = x + a * torch.sin(ph)
+        x = x.float() + 1e-3 * torch.randn(N, generator=g)
+        out.append(x)
+    x = torch.stack(out).clamp(-1, 1)
+    if kind == "chirp_padded":
+        x[-1, N // 2:] = 0.0  # ESPnet zero-pads shorter utterances
+    return x
+
+
+def main():
+    meta = {}
+    # ---- a2 mel filters
+    mel80 = whisper.audio.mel_filters("cpu", 80).numpy()
+    np.save(os.path.join(OUT, "mel_80_ref.npy"), mel80)
+
+    # ---- LID table (product data + fixture of sample strings)
+    lid = make_lid_table()
+    lid.tofile(os.path.join(PKG_DATA, "lid_table_multilingual.u8"))
+    sample_ids = list(range(0, 50257, 997)) + [220, 50256, 50257, 50258, 50259, 50260, 50359, 50363, 51864]
+    meta["lid_samples"] = [[i, TOK.token_string(i), int(lid[i])] for i in sample_ids]
+    meta["lid_hist"] = np.bincount(lid, minlength=4).tolist()
+
+    # ---- a1 log-mel
+    enc_self = fake_encoder_self()
+    lm = {}
+    for name, (B, N, seed, kind) in {
+        "noise": (2, 16000, 2022, "noise"),
+        "chirp": (2, 12800, 7, "chirp"),
+        "chirp_padded": (3, 8000, 11, "chirp_padded"),
+        "short": (1, 480, 3, "noise"),
+    }.items():
+        x = synth_audio(B, N, seed, kind)
+        ilens = torch.full((B,), N, dtype=torch.long)
+        if kind == "chirp_padded":
+            ilens[-1] = N // 2
+        y, ol = OpenAIWhisperEncoder.log_mel_spectrogram(enc_self, x, ilens)
+        lm[f"{name}_audio"] = x.numpy()
+        lm[f"{name}_ilens"] = ilens.numpy()
+        lm[f"{name}_logmel"] = y.numpy()
+        lm[f"{name}_olens"] = ol.numpy()
+        # fp64 run of the same reference code (torch.stft in double): accuracy yardstick
+        enc64 = fake_encoder_self()
+        enc64.mel_filters = lambda dev, n: whisper.audio.mel_filters(dev, n).double()
+        y64, _ = _logmel64(x)
+        lm[f"{name}_logmel_f64"] = y64.numpy()
+    np.savez_compressed(os.path.join(OUT, "logmel.npz"), **lm)
+
+    # ---- a3 attention fwd + bwd (fp32 reference autograd)
+    at = {}
+    for name, (B, H, Tq, Tk, causal, seed, amp) in {
+        "self_causal": (2, 2, 37, 37, True, 1, 1.0),
+        "cross": (2, 3, 5, 50, False, 2, 1.0),
+        "enc_self": (1, 2, 70, 70, False, 3, 3.0),
+    }.items():
+        d = 64
+        D = H * d
+        g = torch.Generator().manual_seed(seed)
+        q = (amp * torch.randn(B, Tq, D, generator=g)).requires_grad_()
+        k = (amp * torch.randn(B, Tk, D, generator=g)).requires_grad_()
+        v = torch.randn(B, Tk, D, generator=g).requires_grad_()
+        mha = MultiHeadAttention(D, H)
+        mask = torch.empty(Tk, Tk).fill_(-np.inf).triu_(1) if causal else None
+        out, qk = mha.qkv_attention(q, k, v, mask)
+        dout = torch.randn(B, Tq, D, generator=g)
+        dqk = torch.zeros_like(qk)
+        dqk[..., 1:3] = torch.randn(B, H, Tq, 2, generator=g)
+        fin = torch.isfinite(qk)
+        loss = (out * dout).sum() + (torch.where(fin, qk, torch.zeros_like(qk)) * dqk).sum()
+        loss.backward()
+        for nm, t in dict(q=q, k=k, v=v, out=out, qk=qk, dout=dout, dqk=dqk, dq=q.grad, dk=k.grad, dv=v.grad).items():
+            at[f"{name}_{nm}"] = t.detach().numpy()
+        at[f"{name}_cfg"] = np.array([B, H, Tq, Tk, int(causal)])
+    np.savez_compressed(os.path.join(OUT, "attention.npz"), **at)
+
+    # ---- a9 head mask
+    with open(f"{REF}/espnet/egs2/seame/asr1/attention_count_whispernoft_new.pkl", "rb") as f:
+        counts = pickle.load(f)
+    meta["attention_count"] = {str(l): {str(h): int(c) for h, c in d.items()} for l, d in counts.items()}
+
+    # ---- a11/a12 pattern + cs loss, a10 head selection
+    m = bare_asr_model()
+    cs = {}
+    L, B, H, T = 12, 3, 12, 20
+    g = torch.Generator().manual_seed(5)
+    toks = []
+    lens = [T, 14, 9]
+    # a few real vocabulary ids: english words, chinese bytes, space, digits
+    eng = [i for i in range(1000, 50257) if lid[i] == O.LID_ENGLISH][:200]
+    oth = [i for i in range(1000, 50257) if lid[i] == O.LID_OTHER][:200]
+    both = [i for i in range(0, 50257) if lid[i] == O.LID_BOTH]
+    meta["lid_both_ids"] = both[:10]
+    for b in range(B):
+        n_words = lens[b] - 6
+        pool = eng + oth + both
+        idx = torch.randint(0, len(pool), (n_words,), generator=g).tolist()
+        body = [pool[i] for i in idx]
+        seq = [50258, 50260, 50259, 50359, 50363] + body + [50257]
+        seq = seq + [50257] * (T - len(seq))
+        toks.append(seq[:T])
+    toks = torch.tensor(toks, dtype=torch.long)
+    maps = torch.randn(L, B, H, T, T, generator=g)
+    cmask = torch.empty(T, T).fill_(-np.inf).triu_(1)
+    maps = (maps + cmask).requires_grad_()
+    pats = torch.stack([m.create_attention_pattern(t, 0.6).detach() for t in toks])
+    loss = m.calculate_cs_loss(maps * 1.0, toks, 0.6)
+    loss.backward()
+    cs["tokens"] = toks.numpy()
+    cs["maps"] = maps.detach().numpy()
+    cs["pattern"] = pats.numpy()
+    cs["loss"] = np.array(loss.item(), dtype=np.float64)
+    cs["dmaps"] = maps.grad.numpy()
+    # probabilities for head selection
+    probs = torch.softmax(maps.detach() * 2.0, dim=-1)
+    m.new_check_attention_language(probs)
+    cnt = np.array([[m.attention_count[l + 1][h + 1] for h in range(12)] for l in range(12)], dtype=np.int64)
+    cs["probs"] = probs.numpy()
+    cs["vote_counts"] = cnt
+    np.savez_compressed(os.path.join(OUT, "cs_loss.npz"), **cs)
+
+    with open(os.path.join(OUT, "meta.json"), "w") as f:
+        json.dump(meta, f, ensure_ascii=True, indent=0)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+def _logmel64(x):
+    """The reference recipe (whisper_encoder.py:105-135) evaluated in float64 by torch."""
+    x = x.double()
+    window = torch.hann_window(400, dtype=torch.float64)
+    stft = torch.stft(x, 400, 160, window=window, return_complex=True)
+    mag = stft[..., :-1].abs() ** 2
+    filt = whisper.audio.mel_filters("cpu", 80).double()
+    mel = filt @ mag
+    ls = torch.clamp(mel, min=1e-10).log10()
+    ls = torch.maximum(ls, ls.view(x.size(0), -1).max(dim=-1)[0][:, None, None] - 8.0)
+    return (ls + 4.0) / 4.0, None
+
+
+if __name__ == "__main__":
+    main()
