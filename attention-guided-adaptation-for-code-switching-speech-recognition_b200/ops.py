@@ -1,0 +1,323 @@
+"""torch-facing operators of the hot path; each one is a thin call into the C ABI (``_lib``).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only.  Tensors must live on a CUDA
+device: there is no CPU implementation in this package (the CPU restatement lives in ``oracle/`` and is
+test infrastructure).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+HOP_LENGTH = 160
+N_FFT = 400
+N_FREQ = 201
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise L.AgaError(f"{name} must be a CUDA tensor: aga_b200 has no CPU path")
+
+
+# ------------------------------------------------------------------------------------------------
+# a2. mel filterbank  (reference: whisper/audio.py:92-107 loads librosa.filters.mel from an npz)
+# ------------------------------------------------------------------------------------------------
+def _hz_to_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    logstep = np.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_hz / f_sp + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep, f / f_sp)
+
+
+def _mel_to_hz(m):
+    m = np.asarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filterbank_numpy(n_mels: int = 80, sr: int = 16000, n_fft: int = N_FFT) -> np.ndarray:
+    """Slaney-scale, area-normalised triangular filterbank == librosa.filters.mel(sr, n_fft, n_mels)."""
+    n_freq = n_fft // 2 + 1
+    fftfreqs = np.linspace(0.0, sr / 2.0, n_freq)
+    mel_f = _mel_to_hz(np.linspace(_hz_to_mel(0.0), _hz_to_mel(sr / 2.0), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    lower = -ramps[:-2] / fdiff[:-1, None]
+    upper = ramps[2:] / fdiff[1:, None]
+    w = np.maximum(0.0, np.minimum(lower, upper))
+    w *= (2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels]))[:, None]
+    return w.astype(np.float32)
+
+
+_FILTER_CACHE = {}
+_PACKED_CACHE = {}
+
+
+def mel_filters(device, n_mels: int = 80) -> torch.Tensor:
+    """Drop-in for whisper.audio.mel_filters(device, n_mels) (cached per device); also serves 128 bins."""
+    key = (str(torch.device(device)), int(n_mels))
+    if key not in _FILTER_CACHE:
+        _FILTER_CACHE[key] = torch.from_numpy(mel_filterbank_numpy(n_mels)).to(device)
+    return _FILTER_CACHE[key]
+
+
+def _packed_filters(filters: torch.Tensor) -> torch.Tensor:
+    key = (filters.data_ptr(), filters._version, tuple(filters.shape), str(filters.device))
+    hit = _PACKED_CACHE.get(key)
+    if hit is not None:
+        return hit
+    lib = L.lib()
+    n_mels = filters.shape[0]
+    nbytes = C.c_size_t()
+    L.check(lib.aga_logmel_packed_filter_bytes(n_mels, C.byref(nbytes)), "aga_logmel_packed_filter_bytes")
+    packed = torch.empty(nbytes.value, dtype=torch.uint8, device=filters.device)
+    L.check(lib.aga_logmel_pack_filters(_ptr(filters), n_mels, _ptr(packed), nbytes.value,
+                                        _stream_ptr(filters.device)), "aga_logmel_pack_filters")
+    if len(_PACKED_CACHE) > 16:
+        _PACKED_CACHE.clear()
+    _PACKED_CACHE[key] = packed
+    packed._aga_keepalive = filters
+    return packed
+
+
+# ------------------------------------------------------------------------------------------------
+# a1. log-mel
+# ------------------------------------------------------------------------------------------------
+def log_mel_spectrogram(audio: torch.Tensor, ilens: Optional[torch.Tensor] = None, n_mels: int = 80,
+                        filters: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """(B, N) fp32 -> ((B, n_mels, N//160) fp32, ilens // 160).
+
+    Same contract as OpenAIWhisperEncoder.log_mel_spectrogram (espnet2/asr/encoder/whisper_encoder.py:105-135).
+    """
+    _require_cuda(audio, "audio")
+    if audio.dim() != 2:
+        raise L.AgaError("audio must be (B, N)")
+    if audio.dtype != torch.float32:
+        audio = audio.float()
+    if audio.stride(1) != 1:
+        audio = audio.contiguous()
+    B, N = audio.shape
+    if N <= N_FFT // 2:
+        raise L.AgaError("log_mel_spectrogram needs N > 200 samples (reflect padding)")
+    if filters is None:
+        filters = mel_filters(audio.device, n_mels)
+    else:
+        filters = filters.to(device=audio.device, dtype=torch.float32).contiguous()
+        n_mels = filters.shape[0]
+    if filters.shape != (n_mels, N_FREQ):
+        raise L.AgaError(f"filters must be ({n_mels}, {N_FREQ})")
+    lib = L.lib()
+    packed = _packed_filters(filters)
+    F = N // HOP_LENGTH
+    out = torch.empty((B, n_mels, F), dtype=torch.float32, device=audio.device)
+    nbytes = C.c_size_t()
+    L.check(lib.aga_logmel_workspace_bytes(B, N, n_mels, C.byref(nbytes)), "aga_logmel_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=audio.device)
+    L.check(lib.aga_logmel_fwd(_ptr(audio), B, N, audio.stride(0), _ptr(packed), n_mels, _ptr(out), _ptr(ws),
+                               nbytes.value, _stream_ptr(audio.device)), "aga_logmel_fwd")
+    olens = None if ilens is None else ilens // HOP_LENGTH
+    return out, olens
+
+
+# ------------------------------------------------------------------------------------------------
+# a3. attention core
+# ------------------------------------------------------------------------------------------------
+_DTYPES = {torch.float32: L.AGA_F32, torch.bfloat16: L.AGA_BF16}
+_IMPLS = {"auto": L.ATTN_AUTO, "simt": L.ATTN_SIMT, "tcgen05": L.ATTN_TCGEN05}
+_KINDS = {None: L.EXPORT_NONE, "none": L.EXPORT_NONE, "logits": L.EXPORT_LOGITS, "probs": L.EXPORT_PROBS}
+
+
+def _prep(t: torch.Tensor) -> torch.Tensor:
+    vec = 8 if t.dtype == torch.bfloat16 else 4
+    ok = t.stride(2) == 1 and t.stride(0) % vec == 0 and t.stride(1) % vec == 0 and t.data_ptr() % 16 == 0
+    return t if ok else t.contiguous()
+
+
+def _fill_params(p: L.AttnParams, q, k, v, out, lse, n_head, causal, kind, cols, head_sel, export_buf, impl):
+    B, Tq, D = q.shape
+    p.dtype = _DTYPES[q.dtype]
+    p.impl = impl
+    p.B, p.H, p.Tq, p.Tk = B, n_head, Tq, k.shape[1]
+    p.causal = 1 if causal else 0
+    p.export_kind = kind
+    p.export_lo, p.export_hi = (cols if kind != L.EXPORT_NONE else (0, 0))
+    p.q_stride_b, p.q_stride_t = q.stride(0), q.stride(1)
+    p.k_stride_b, p.k_stride_t = k.stride(0), k.stride(1)
+    p.v_stride_b, p.v_stride_t = v.stride(0), v.stride(1)
+    p.o_stride_b, p.o_stride_t = out.stride(0), out.stride(1)
+    p.q, p.k, p.v, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    p.lse = lse.data_ptr()
+    p.head_sel = 0 if head_sel is None else head_sel.data_ptr()
+    p.export_buf = 0 if export_buf is None else export_buf.data_ptr()
+
+
+class _AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, n_head, causal, kind, cols, head_sel, impl):
+        for name, t in (("q", q), ("k", k), ("v", v)):
+            _require_cuda(t, name)
+        if q.dtype not in _DTYPES:
+            raise L.AgaError(f"attention supports fp32 and bf16, got {q.dtype}")
+        k = k.to(q.dtype)
+        v = v.to(q.dtype)
+        q, k, v = _prep(q), _prep(k), _prep(v)
+        B, Tq, D = q.shape
+        if D != n_head * 64:
+            raise L.AgaError("head dim must be 64 (every Whisper size)")
+        lib = L.lib()
+        out = torch.empty((B, Tq, D), dtype=q.dtype, device=q.device)
+        lse = torch.empty((B, n_head, Tq), dtype=torch.float32, device=q.device)
+        export_buf = None
+        if kind != L.EXPORT_NONE:
+            lo, hi = cols
+            # rows of unselected heads are never written by the kernel: define them as zero
+            alloc = torch.zeros if head_sel is not None else torch.empty
+            export_buf = alloc((B, n_head, Tq, hi - lo), dtype=torch.float32, device=q.device)
+        p = L.AttnParams()
+        _fill_params(p, q, k, v, out, lse, n_head, causal, kind, cols, head_sel, export_buf, impl)
+        nbytes = C.c_size_t()
+        L.check(lib.aga_attn_fwd_workspace_bytes(C.byref(p), C.byref(nbytes)), "aga_attn_fwd_workspace_bytes")
+        ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
+        L.check(lib.aga_attn_fwd(C.byref(p), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_fwd")
+        ctx.save_for_backward(q, k, v, out, lse, head_sel if head_sel is not None else torch.empty(0),
+                              export_buf if (export_buf is not None and kind == L.EXPORT_PROBS) else torch.empty(0))
+        ctx.cfg = (n_head, causal, kind, cols, impl, head_sel is not None)
+        if export_buf is None:
+            ctx.mark_non_differentiable(lse)
+            return out, lse, None
+        ctx.mark_non_differentiable(lse)
+        return out, lse, export_buf
+
+    @staticmethod
+    def backward(ctx, dout, _dlse, dexport):
+        q, k, v, out, lse, head_sel, probs = ctx.saved_tensors
+        n_head, causal, kind, cols, impl, has_sel = ctx.cfg
+        lib = L.lib()
+        if dout is None:
+            dout = torch.zeros_like(out)
+        dout = dout.to(out.dtype)
+        if dout.stride() != out.stride():
+            dout = dout.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        bp = L.AttnBwdParams()
+        export_buf = probs if probs.numel() else None
+        if dexport is not None:
+            dexport = dexport.float().contiguous()
+        _fill_params(bp.fwd, q, k, v, out, lse, n_head, causal, kind if dexport is not None else L.EXPORT_NONE, cols,
+                     head_sel if has_sel else None, export_buf, impl)
+        if dexport is not None and kind == L.EXPORT_LOGITS:
+            bp.fwd.export_buf = dexport.data_ptr()  # logits export: only the gradient is needed (non-null marker)
+        bp.dout = dout.data_ptr()
+        bp.d_export = 0 if dexport is None else dexport.data_ptr()
+        bp.dq, bp.dk, bp.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+        # dq/dk/dv must share the strides of q/k/v
+        assert dq.stride() == q.stride() and dk.stride() == k.stride() and dv.stride() == v.stride()
+        nbytes = C.c_size_t()
+        L.check(lib.aga_attn_bwd_workspace_bytes(C.byref(bp), C.byref(nbytes)), "aga_attn_bwd_workspace_bytes")
+        ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
+        L.check(lib.aga_attn_bwd(C.byref(bp), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_bwd")
+        return dq, dk, dv, None, None, None, None, None, None
+
+
+def qkv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int, causal: bool = False,
+                  export: Optional[str] = None, export_cols: Optional[Tuple[int, int]] = None,
+                  head_sel: Optional[torch.Tensor] = None, impl: str = "auto"):
+    """Fused MultiHeadAttention.qkv_attention (whisper/model.py:93-109).
+
+    q (B,Tq,D), k,v (B,Tk,D), D = n_head*64.  Returns (out (B,Tq,D), lse (B,H,Tq), exported) where
+    ``exported`` is None or the fp32 (B,H,Tq,hi-lo) side buffer holding key columns [lo,hi) of the
+    scaled, masked logits (``export="logits"``, what the reference returns at HEAD) or of the softmax
+    (``export="probs"``).  Differentiable in q, k, v through ``out`` and through ``exported``.
+    """
+    kind = _KINDS[export]
+    if kind != L.EXPORT_NONE and export_cols is None:
+        export_cols = (0, k.shape[1])
+    if head_sel is not None:
+        head_sel = head_sel.to(device=q.device, dtype=torch.uint8).contiguous()
+    empty_cols = export_cols if export_cols is not None else (0, 0)
+    return _AttnFn.apply(q, k, v, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl])
+
+
+# ------------------------------------------------------------------------------------------------
+# a11 / a12 / a10
+# ------------------------------------------------------------------------------------------------
+def attention_pattern(tokens: torch.Tensor, lid_table: torch.Tensor, c: float = 0.6) -> torch.Tensor:
+    """(B,T) int64 ys_in_pad -> (B,T,2) fp32 pattern (+inf on pad rows); espnet_model.py:236-275."""
+    _require_cuda(tokens, "tokens")
+    tokens = tokens.to(torch.int64).contiguous()
+    B, T = tokens.shape
+    lid_table = lid_table.to(device=tokens.device, dtype=torch.uint8).contiguous()
+    out = torch.empty((B, T, 2), dtype=torch.float32, device=tokens.device)
+    L.check(L.lib().aga_attention_pattern(_ptr(tokens), _ptr(lid_table), lid_table.numel(), B, T, float(c), _ptr(out),
+                                          _stream_ptr(tokens.device)), "aga_attention_pattern")
+    return out
+
+
+class _GuidedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, slab, pattern, head_mask, n_early):
+        _require_cuda(slab, "slab")
+        if slab.dtype != torch.float32 or slab.dim() != 5 or slab.shape[-1] != 2 or slab.stride(-1) != 1:
+            raise L.AgaError("slab must be fp32 (L,B,H,T,2) with unit last stride")
+        Lyr, B, H, T, _ = slab.shape
+        pattern = pattern.to(device=slab.device, dtype=torch.float32).contiguous()
+        head_mask = head_mask.to(device=slab.device, dtype=torch.float32).contiguous()
+        if pattern.shape != (B, T, 2) or head_mask.shape != (Lyr, H):
+            raise L.AgaError("pattern must be (B,T,2) and head_mask (L,H)")
+        lib = L.lib()
+        loss = torch.empty((), dtype=torch.float32, device=slab.device)
+        need_grad = ctx.needs_input_grad[0]
+        # a strided view (columns 1:3 of full maps) is gathered once: the slab is only L*B*H*T*2 floats,
+        # and autograd scatters the dense gradient back through the view
+        src = slab.contiguous()
+        d_slab = torch.empty_like(src) if need_grad else None
+        nbytes = C.c_size_t()
+        L.check(lib.aga_guided_loss_workspace_bytes(Lyr, B, H, C.byref(nbytes)), "aga_guided_loss_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=slab.device)
+        L.check(lib.aga_guided_loss_fwd_bwd(_ptr(src), src.stride(0), src.stride(1), src.stride(2), src.stride(3),
+                                            _ptr(pattern), _ptr(head_mask), Lyr, B, H, T, int(n_early), _ptr(loss),
+                                            _ptr(d_slab), _ptr(ws), nbytes.value, _stream_ptr(slab.device)),
+                "aga_guided_loss_fwd_bwd")
+        ctx.d_slab = d_slab
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.d_slab
+        return (None if d is None else d * g), None, None, None
+
+
+def guided_loss(slab: torch.Tensor, pattern: torch.Tensor, head_mask: torch.Tensor, n_early: int = 2) -> torch.Tensor:
+    """Attention-guided loss on exported columns 1:3 — ESPnetASRModel.calculate_cs_loss (espnet_model.py:463-530)."""
+    return _GuidedLossFn.apply(slab, pattern, head_mask, n_early)
+
+
+def head_vote(probs: torch.Tensor, counts: Optional[torch.Tensor] = None):
+    """probs (L,B,H,T,T) fp32 -> (decisions (L,B,H) uint8, counts (L,H) int32); espnet_model.py:285-310."""
+    _require_cuda(probs, "probs")
+    probs = probs.float().contiguous()
+    Lyr, B, H, T, T2 = probs.shape
+    assert T == T2
+    dec = torch.empty((Lyr, B, H), dtype=torch.uint8, device=probs.device)
+    if counts is None:
+        counts = torch.zeros((Lyr, H), dtype=torch.int32, device=probs.device)
+    L.check(L.lib().aga_head_vote(_ptr(probs), Lyr, B, H, T, _ptr(dec), _ptr(counts), _stream_ptr(probs.device)),
+            "aga_head_vote")
+    return dec, counts

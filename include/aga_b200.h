@@ -1,0 +1,164 @@
+/*
+ * aga_b200.h — C ABI of the B200-native hot path for Attention-Guided Adaptation
+ * (Whisper attention fwd/bwd with selected-head map export, guided "cs" loss,
+ * Whisper log-mel frontend).
+ *
+ * Drop-in boundary.  Every entry point names the reference
+ * interface it replaces; paths are relative to /root/reference/espnet, with
+ *   W/  = whisper/whisper/   and   E2/ = espnet2/ .
+ *
+ * Contract shared by all functions
+ *   - plain pointers and sizes only; all device buffers are owned by the caller
+ *     (PyTorch's caching allocator in the reference integration);
+ *   - the library never allocates or frees device memory, never synchronises
+ *     the device and enqueues work only on the stream passed in
+ *     (a cudaStream_t, passed as void*);
+ *   - scratch space is caller-provided: query the size, pass the buffer;
+ *   - return value: AGA_OK (0) or a negative aga_status; no C++ exceptions
+ *     cross the ABI; aga_status_str() names the code;
+ *   - re-entrant: no mutable global state beyond immutable per-device tables;
+ *   - there is no CPU fallback and no other backend: the kernels are sm_100a.
+ */
+#ifndef AGA_B200_H_
+#define AGA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGA_B200_VERSION 100
+
+#if defined(__GNUC__)
+#define AGA_API __attribute__((visibility("default")))
+#else
+#define AGA_API
+#endif
+
+typedef enum aga_status {
+  AGA_OK = 0,
+  AGA_ERR_INVALID_ARGUMENT = -1,
+  AGA_ERR_UNSUPPORTED = -2,
+  AGA_ERR_CUDA = -3,
+  AGA_ERR_WORKSPACE_TOO_SMALL = -4,
+  AGA_ERR_NO_SM100 = -5
+} aga_status;
+
+typedef enum aga_dtype { AGA_F32 = 0, AGA_BF16 = 1 } aga_dtype;
+
+/* What the attention kernel writes to the side buffer (W/model.py:108-109):
+ * LOGITS = the scaled, causally masked pre-softmax scores `qk` the reference
+ * returns at HEAD; PROBS = softmax `w`, the "#modify here qk to w" variant that
+ * head selection and plotting need (code_util/head_selection.md:5-9). */
+typedef enum aga_export_kind { AGA_EXPORT_NONE = 0, AGA_EXPORT_LOGITS = 1, AGA_EXPORT_PROBS = 2 } aga_export_kind;
+
+/* Which implementation ran (for tests / gpu_launches accounting). */
+typedef enum aga_attn_impl { AGA_ATTN_AUTO = 0, AGA_ATTN_SIMT = 1, AGA_ATTN_TCGEN05 = 2 } aga_attn_impl;
+
+AGA_API int aga_version(void);
+AGA_API const char* aga_status_str(int status);
+/* cudaError_t of the last failing CUDA call made by this library on the calling thread (0 if none). */
+AGA_API int aga_last_cuda_error(void);
+/* Number of kernels this library has launched in this process (all threads). */
+AGA_API uint64_t aga_launch_count(void);
+/* AGA_OK when device `dev` is compute capability 10.x (tcgen05/TMEM/TMA path usable). */
+AGA_API int aga_device_is_sm100(int dev);
+
+/* ------------------------------------------------------------------------------------------
+ * Log-mel frontend.
+ * Replaces OpenAIWhisperEncoder.log_mel_spectrogram (E2/asr/encoder/whisper_encoder.py:105-135),
+ * its twin WhisperFrontend.log_mel_spectrogram (E2/asr/frontend/whisper.py:54-83) and
+ * whisper.audio.log_mel_spectrogram (W/audio.py:110-157): reflect-pad 200, periodic Hann(400),
+ * 400-point real DFT at hop 160, drop last frame, |.|^2, mel projection, log10(clamp 1e-10),
+ * max(x, per-utterance max - 8), (x + 4) / 4.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Bytes for the packed (banded) form of an (n_mels x 201) filterbank. */
+AGA_API int aga_logmel_packed_filter_bytes(int n_mels, size_t* bytes);
+/* Pack a dense device filterbank `melfb` (n_mels x 201 fp32, row-major — the tensor
+ * whisper.audio.mel_filters returns, W/audio.py:92-107) into `packed`. Done once per device. */
+AGA_API int aga_logmel_pack_filters(const float* melfb, int n_mels, void* packed, size_t packed_bytes, void* stream);
+/* Scratch bytes for aga_logmel_fwd. */
+AGA_API int aga_logmel_workspace_bytes(int64_t B, int64_t N, int n_mels, size_t* bytes);
+/* audio: (B, N) fp32, row stride `ld` elements (16-byte aligned rows give 128-bit loads).
+ * out:   (B, n_mels, N / 160) fp32 contiguous.  Requires N > 200 (torch.stft reflect pad). */
+AGA_API int aga_logmel_fwd(const float* audio, int64_t B, int64_t N, int64_t ld, const void* packed_filters, int n_mels,
+                   float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-head attention core, head dim 64 (every Whisper size).
+ * Replaces MultiHeadAttention.qkv_attention (W/model.py:93-109) and what autograd replays for it.
+ *   S = (q d^-1/4)(k d^-1/4)^T (+ causal -inf mask, W/model.py:322), P = softmax_fp32(S), out = P v.
+ * Tensors are addressed as x[b, t, h*64 + c] = base + b*stride_b + t*stride_t + h*64 + c (elements),
+ * i.e. the (B, T, D) activations of the q/k/v Linear layers with heads interleaved along D.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct aga_attn_params {
+  int32_t dtype;  /* aga_dtype of q, k, v, out, dout, dq, dk, dv */
+  int32_t impl;   /* aga_attn_impl; AUTO = tcgen05 for bf16, SIMT for fp32 */
+  int32_t B, H, Tq, Tk;
+  int32_t causal; /* 1: key j visible to query i iff j <= i (requires Tq == Tk) */
+  int32_t export_kind;           /* aga_export_kind */
+  int32_t export_lo, export_hi;  /* exported key columns [lo, hi) */
+  int64_t q_stride_b, q_stride_t;
+  int64_t k_stride_b, k_stride_t;
+  int64_t v_stride_b, v_stride_t;
+  int64_t o_stride_b, o_stride_t;  /* out and dout */
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;                /* (B, Tq, H*64) */
+  float* lse;               /* (B, H, Tq) fp32 natural-log row log-sum-exp of S (needed by backward) */
+  const uint8_t* head_sel;  /* (H) 0/1: heads whose columns are exported; NULL = all heads */
+  float* export_buf;        /* (B, H, Tq, hi-lo) fp32; rows of unselected heads are left untouched */
+} aga_attn_params;
+
+AGA_API int aga_attn_fwd_workspace_bytes(const aga_attn_params* p, size_t* bytes);
+AGA_API int aga_attn_fwd(const aga_attn_params* p, void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct aga_attn_bwd_params {
+  aga_attn_params fwd;      /* same problem as forward; fwd.out / fwd.lse / fwd.export_buf are inputs here */
+  const void* dout;         /* (B, Tq, H*64), strides o_stride_* */
+  const float* d_export;    /* gradient w.r.t. export_buf, same layout, or NULL */
+  void* dq;                 /* strides as q */
+  void* dk;                 /* strides as k */
+  void* dv;                 /* strides as v */
+} aga_attn_bwd_params;
+
+AGA_API int aga_attn_bwd_workspace_bytes(const aga_attn_bwd_params* p, size_t* bytes);
+AGA_API int aga_attn_bwd(const aga_attn_bwd_params* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention-guided ("cs") loss on the exported columns.
+ * Replaces ESPnetASRModel.calculate_cs_loss (E2/asr/espnet_model.py:463-530): MSE between the
+ * decoder self-attention columns 1:3 (<|zh|>, <|en|> prompt tokens) and the per-token language
+ * pattern, mean over non-zero rows, masked by the selected-head matrix, mean over the batch.
+ *   slab element (l,b,h,t,j), j in {0,1}  = slab[l*stride_l + b*stride_b + h*stride_h + t*stride_t + j]
+ *   (compact (L,B,H,T,2) export, or a view of columns 1:3 of full (L,B,H,T,T) maps)
+ *   pattern (B,T,2) fp32 from aga_attention_pattern; +inf marks pad rows
+ *   head_mask (L,H) fp32; layers [0,n_early) use the all-zero "early" target and keep pad rows
+ * loss: 1 fp32 on device.  d_slab (may be NULL): d loss / d slab, same strides as slab.
+ * ------------------------------------------------------------------------------------------ */
+AGA_API int aga_guided_loss_workspace_bytes(int L, int B, int H, size_t* bytes);
+AGA_API int aga_guided_loss_fwd_bwd(const float* slab, int64_t stride_l, int64_t stride_b, int64_t stride_h, int64_t stride_t,
+                            const float* pattern, const float* head_mask, int L, int B, int H, int T, int n_early,
+                            float* loss, float* d_slab, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces ESPnetASRModel.create_attention_pattern (E2/asr/espnet_model.py:236-275), with the
+ * per-step HF-tokenizer string loop turned into a (vocab) uint8 lookup:
+ * lid_table[id]: 0 other/Mandarin, 1 ASCII-letters-only (English), 2 space-only, 3 end-of-text.
+ * tokens (B,T) int64 = ys_in_pad; pattern (B,T,2) fp32. */
+AGA_API int aga_attention_pattern(const int64_t* tokens, const uint8_t* lid_table, int vocab, int B, int T, float c,
+                          float* pattern, void* stream);
+
+/* Replaces ESPnetASRModel.new_check_attention_language (E2/asr/espnet_model.py:285-310).
+ * probs: full maps (L,B,H,T,T) fp32 contiguous.  decisions (L,B,H) uint8 (sum_1 > sum_2);
+ * counts (L,H) int32, incremented per selected (utterance, layer, head). Sums are accumulated in
+ * fp32 in the reference's order so near-ties decide identically. */
+AGA_API int aga_head_vote(const float* probs, int L, int B, int H, int T, uint8_t* decisions, int32_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGA_B200_H_ */
