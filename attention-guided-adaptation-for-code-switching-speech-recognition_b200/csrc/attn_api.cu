@@ -48,6 +48,11 @@ bool use_tc(const aga_attn_params& p) {
   if (p.dtype != AGA_BF16) return false;
   return attn_tc_supported(p);
 }
+bool use_tc_bwd(const aga_attn_params& p) {
+  if (p.impl == AGA_ATTN_SIMT) return false;
+  if (p.dtype != AGA_BF16) return false;
+  return attn_tc_bwd_supported(p);
+}
 
 }  // namespace
 }  // namespace aga
@@ -87,8 +92,8 @@ extern "C" int aga_attn_bwd_workspace_bytes(const aga_attn_bwd_params* p, size_t
   const void* ptrs[] = {p->dout, p->dq, p->dk, p->dv};
   for (const void* x : ptrs)
     if (reinterpret_cast<uintptr_t>(x) & 15) return AGA_ERR_UNSUPPORTED;
-  if (p->fwd.impl == AGA_ATTN_TCGEN05 && !use_tc(p->fwd)) return AGA_ERR_UNSUPPORTED;
-  *bytes = use_tc(p->fwd) ? attn_tc_bwd_workspace(p->fwd) : attn_simt_bwd_workspace(p->fwd);
+  if (p->fwd.impl == AGA_ATTN_TCGEN05 && !use_tc_bwd(p->fwd)) return AGA_ERR_UNSUPPORTED;
+  *bytes = use_tc_bwd(p->fwd) ? attn_tc_bwd_workspace(p->fwd) : attn_simt_bwd_workspace(p->fwd);
   return AGA_OK;
 }
 
@@ -98,5 +103,5 @@ extern "C" int aga_attn_bwd(const aga_attn_bwd_params* p, void* workspace, size_
   if (st != AGA_OK) return st;
   if (!workspace || workspace_bytes < need) return AGA_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return use_tc(p->fwd) ? attn_tc_bwd(*p, workspace, s) : attn_simt_bwd(*p, workspace, s);
+  return use_tc_bwd(p->fwd) ? attn_tc_bwd(*p, workspace, s) : attn_simt_bwd(*p, workspace, s);
 }

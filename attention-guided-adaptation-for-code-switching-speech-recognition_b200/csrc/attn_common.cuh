@@ -13,6 +13,7 @@ int attn_simt_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s);
 bool attn_tc_supported(const aga_attn_params& p);
 size_t attn_tc_fwd_workspace(const aga_attn_params& p);
 int attn_tc_fwd(const aga_attn_params& p, void* ws, cudaStream_t s);
+bool attn_tc_bwd_supported(const aga_attn_params& p);
 size_t attn_tc_bwd_workspace(const aga_attn_params& p);
 int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s);
 
