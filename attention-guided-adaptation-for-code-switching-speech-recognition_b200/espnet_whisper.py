@@ -1,0 +1,199 @@
+"""Drop-in mirrors of the reference's ESPnet2 plugin modules for the Whisper path:
+
+  OpenAIWhisperEncoder  <- espnet2/asr/encoder/whisper_encoder.py:12-243
+  OpenAIWhisperDecoder  <- espnet2/asr/decoder/whisper_decoder.py:12-273
+
+Same constructor keywords, same forward signatures and return conventions, same ``state_dict`` keys
+(``encoders.*`` / ``decoders.*``); log-mel and attention run in the aga_b200 CUDA library.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any, List, Optional, Tuple, Union
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from . import whisper_model as W
+from .specaug import SpecAug
+
+N_SAMPLES = 480000  # whisper/audio.py:18
+
+
+class OpenAIWhisperEncoder(torch.nn.Module):
+    def __init__(self, input_size: int = 1, dropout_rate: float = 0.0, whisper_model: str = "small",
+                 download_dir: Optional[str] = None, use_specaug: bool = False,
+                 specaug_conf: Union[dict, None] = None, do_pad_trim: bool = False, pe_whisper: bool = False,
+                 adapter: bool = False, side_network: bool = False, side_network_conf=None, seed: int = 0):
+        super().__init__()
+        self.n_fft, self.win_length, self.hop_length = ops.N_FFT, ops.N_FFT, ops.HOP_LENGTH
+        self.mel_filters = ops.mel_filters
+        self.dropout = torch.nn.Dropout(dropout_rate)
+        if whisper_model not in W.available_models():
+            import os
+            assert os.path.isfile(whisper_model), f"unknown whisper model {whisper_model}"
+        _model = W.load_model(whisper_model, adapter, pe_whisper, side_network, side_network_conf,
+                              download_root=download_dir, seed=seed)
+        self.sidenetwork = side_network
+        self.encoders = copy.deepcopy(_model.encoder)
+        self.n_mels = _model.dims.n_mels
+        self.encoders.train()
+        del _model
+        self.specaug = SpecAug(**specaug_conf) if use_specaug else None
+        self.do_pad_trim = do_pad_trim
+        self.pad_samples = N_SAMPLES
+        self.interctc_use_conditioning = False
+
+    def output_size(self) -> int:
+        return self.encoders.ln_post.normalized_shape[-1]
+
+    def pad_or_trim(self, array: torch.Tensor, length: int, axis: int = -1) -> torch.Tensor:
+        """Zero-pad or cut to ``length`` samples (whisper_encoder.py:84-103)."""
+        n = array.shape[axis]
+        if n > length:
+            array = array.narrow(axis, 0, length)
+        elif n < length:
+            pad = [0, 0] * array.ndim
+            pad[2 * (array.ndim - 1 - (axis % array.ndim)) + 1] = length - n
+            array = F.pad(array, pad)
+        return array
+
+    def log_mel_spectrogram(self, audio: torch.Tensor, ilens: torch.Tensor = None):
+        """whisper_encoder.py:105-135 -> one fused CUDA pass (csrc/logmel.cu)."""
+        return ops.log_mel_spectrogram(audio, ilens, n_mels=self.n_mels)
+
+    def whisper_encode(self, input: torch.Tensor, ilens: torch.Tensor = None):
+        """whisper_encoder.py:137-222 (no side network)."""
+        enc = self.encoders
+        x = F.gelu(enc.conv1(input))
+        x = F.gelu(enc.conv2(x)).permute(0, 2, 1)
+        n_frames, max_pos = x.size(1), enc.positional_embedding.size(0)
+        if n_frames <= max_pos:
+            x = (x + enc.positional_embedding[:n_frames, :]).to(x.dtype)
+        else:  # audio > 30 s: truncated to the positional table (:163-165)
+            x = x[:, :max_pos, :] + enc.positional_embedding
+        x = self.dropout(x)
+        last = len(enc.blocks) - 1
+        for layer, block in enumerate(enc.blocks):
+            x, _ = block(x)
+            if layer < last:
+                x = self.dropout(x)
+        x = enc.ln_post(x)
+        if ilens is not None:
+            olens = 1 + (ilens - enc.conv2.kernel_size[0] + 2 * enc.conv2.padding[0]) // enc.conv2.stride[0]
+            olens = torch.clamp(olens, max=max_pos)
+        else:
+            olens = None
+        return x, olens
+
+    def forward(self, xs_pad: torch.Tensor, ilens: torch.Tensor, prev_states: torch.Tensor = None
+                ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        if self.do_pad_trim:
+            xs_pad = self.pad_or_trim(xs_pad, self.pad_samples)
+        feats, feats_lens = self.log_mel_spectrogram(xs_pad, ilens)
+        if self.specaug is not None and self.encoders.training:
+            feats, feats_lens = self.specaug(feats, feats_lens)
+        xs_pad, olens = self.whisper_encode(feats, feats_lens)
+        return xs_pad, olens, None
+
+
+class OpenAIWhisperDecoder(torch.nn.Module):
+    """``forward`` returns ``(logits, att_maps)`` like the reference.  ``att_maps`` holds, per decoder layer
+    ``>= src_layer-1``, the SELF-attention map the block returns (whisper/model.py:232,248):
+
+      export_mode="full"    (B,H,T,T) per layer, stacked to (L_sel,B,H,T,T) — the reference's tensor, fp32 logits
+                            with -inf above the diagonal (or probabilities with ``export_kind="probs"``)
+      export_mode="compact" only key columns 1:3 (the <|zh|>, <|en|> prompt tokens, the only ones the guided loss
+                            reads, espnet_model.py:506): (L_sel,B,H,T,2)
+    """
+
+    def __init__(self, vocab_size: int, encoder_output_size: int, dropout_rate: float = 0.0,
+                 whisper_model: str = "small", download_dir: Optional[str] = None, src_layer: int = 12,
+                 whisper_cs: bool = False, pe_whisper: bool = False, adapter: bool = False, side_network: bool = False,
+                 side_network_conf=None, c_val_attention: float = 0.6, estimate_c: bool = False,
+                 export_mode: str = "full", export_kind: str = "logits", seed: int = 0):
+        super().__init__()
+        _model = W.load_model(whisper_model, adapter, pe_whisper, side_network, side_network_conf,
+                              download_root=download_dir, seed=seed)
+        self.sidenetwork = side_network
+        self.decoders = copy.deepcopy(_model.decoder)
+        self.decoders.train()
+        del _model
+        attention_dim = self.decoders.token_embedding.embedding_dim
+        self.dropout = torch.nn.Dropout(dropout_rate)
+        if vocab_size != self.decoders.token_embedding.num_embeddings:  # whisper_decoder.py:66-79
+            std, mean = torch.std_mean(self.decoders.token_embedding.weight)
+            self.decoders.token_embedding = torch.nn.Embedding(vocab_size, attention_dim)
+            torch.nn.init.normal_(self.decoders.token_embedding.weight, mean.item(), std.item())
+        self.whisper_cs = whisper_cs
+        self.src_layer = src_layer - 1
+        self.att_map = None
+        self.estimate_c = estimate_c
+        self.c_val_attention = c_val_attention
+        if estimate_c:
+            self.decoders.estimated_c_val = torch.nn.Parameter(torch.Tensor([c_val_attention]))
+        assert export_mode in ("full", "compact") and export_kind in ("logits", "probs")
+        self.export_mode, self.export_kind = export_mode, export_kind
+
+    def _set_export(self, enabled: bool, mode: Optional[str] = None) -> None:
+        mode = mode or self.export_mode
+        for layer, block in enumerate(self.decoders.blocks):
+            on = enabled and layer >= self.src_layer
+            block.attn.export = (self.export_kind, (1, 3) if mode == "compact" else None) if on else None
+
+    def forward(self, hs_pad: torch.Tensor, hlens: torch.Tensor, ys_in_pad: torch.Tensor, ys_in_lens: torch.Tensor,
+                side_encoder_output: torch.Tensor = None) -> Tuple[torch.Tensor, Any]:
+        """whisper_decoder.py:89-170.  hlens / ys_in_lens are ignored exactly as in the reference (no key padding)."""
+        dec = self.decoders
+        tgt = dec.token_embedding(ys_in_pad) + dec.positional_embedding[: ys_in_pad.size(1)]
+        x = self.dropout(tgt).to(hs_pad.dtype)
+        self._set_export(self.whisper_cs)
+        attention_scores: List[torch.Tensor] = []
+        last = len(dec.blocks) - 1
+        for layer, block in enumerate(dec.blocks):
+            x, attention_map = block(x, hs_pad, mask=dec.mask)
+            if layer < last:
+                x = self.dropout(x)
+            if self.whisper_cs and layer >= self.src_layer:
+                attention_scores.append(attention_map)
+        x = dec.ln(x)
+        logits = (x @ dec.token_embedding.weight.to(x.dtype).t()).float()
+        if self.whisper_cs:
+            return logits, torch.stack(attention_scores)
+        return logits, attention_scores
+
+    def forward_one_step(self, tgt: torch.Tensor, tgt_mask: torch.Tensor, memory: torch.Tensor,
+                         cache: List[torch.Tensor] = None, side_encoder_output: torch.Tensor = None,
+                         return_maps: bool = False):
+        """whisper_decoder.py:172-244: whole-prefix recompute, last position -> log_softmax.
+
+        The reference dumps every layer's map to the CPU each step (:230); here maps stay on the device and are
+        only produced when ``return_maps`` is set (then stored in ``self.att_map`` as a list of (n,H,t,t))."""
+        dec = self.decoders
+        if tgt.size(1) > 448:
+            tgt = tgt[:, :448]
+        x = dec.token_embedding(tgt) + dec.positional_embedding[: tgt.size(1)]
+        x = self.dropout(x).to(memory.dtype)
+        self._set_export(return_maps, mode="full")
+        maps = []
+        last = len(dec.blocks) - 1
+        for layer, block in enumerate(dec.blocks):
+            x, att_map = block(x, memory, mask=dec.mask)
+            if return_maps:
+                maps.append(att_map)
+            if layer < last:
+                x = self.dropout(x)
+        if return_maps:
+            self.att_map = maps
+        x = dec.ln(x)
+        y = (x[:, -1] @ dec.token_embedding.weight.to(x.dtype).t()).float()
+        return torch.log_softmax(y, dim=-1), None
+
+    def score(self, ys, state, x):
+        logp, state = self.forward_one_step(ys.unsqueeze(0), torch.empty(0), x.unsqueeze(0), cache=state)
+        return logp.squeeze(0), state
+
+    def batch_score(self, ys: torch.Tensor, states: List[Any], xs: torch.Tensor, x_enc: torch.Tensor = None):
+        logp, _ = self.forward_one_step(ys, torch.empty(0), xs, cache=None, side_encoder_output=x_enc)
+        return logp, None

@@ -1,0 +1,305 @@
+"""Host-side mirror of the reference's Whisper nn modules (whisper/whisper/model.py), with the attention
+core replaced by the aga_b200 CUDA kernels.
+
+Only the module tree that the shipped SEAME recipes instantiate is mirrored (``pe_whisper: false``, no
+side network — SURVEY.md §2a #1); parameter names and shapes are identical to the reference so that
+``state_dict`` keys (``blocks.N.attn.query.weight``, ``blocks.N.adapter_attn.model.0.weight`` …) and therefore
+checkpoints are interchangeable.  Everything except ``MultiHeadAttention.qkv_attention`` stays plain PyTorch
+(cuBLAS GEMMs on frozen weights, LayerNorm, GELU): plumbing around the hot path, not the product.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import ops
+
+
+@dataclass
+class ModelDimensions:  # whisper/model.py:16-27
+    n_mels: int
+    n_audio_ctx: int
+    n_audio_state: int
+    n_audio_head: int
+    n_audio_layer: int
+    n_vocab: int
+    n_text_ctx: int
+    n_text_state: int
+    n_text_head: int
+    n_text_layer: int
+
+
+def _dims(state, heads, layers, n_mels=80, n_vocab=51865):
+    return ModelDimensions(n_mels, 1500, state, heads, layers, n_vocab, 448, state, heads, layers)
+
+
+# SURVEY.md Appendix A.1 (checkpoint `dims`; head dim is 64 for every size)
+MODEL_DIMS: Dict[str, ModelDimensions] = {
+    "tiny": _dims(384, 6, 4),
+    "base": _dims(512, 8, 6),
+    "small": _dims(768, 12, 12),
+    "medium": _dims(1024, 16, 24),
+    "large-v1": _dims(1280, 20, 32),
+    "large-v2": _dims(1280, 20, 32),
+    "large": _dims(1280, 20, 32),
+    # documented extrapolation (BASELINE.json config 4): large-v2 body with a 128-bin mel stem
+    "large-v2-mel128": _dims(1280, 20, 32, n_mels=128),
+}
+
+
+def available_models():
+    return list(MODEL_DIMS)
+
+
+class LayerNorm(nn.LayerNorm):
+    """fp32 statistics whatever the activation dtype (whisper/model.py:30-32)."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F.layer_norm(x.float(), self.normalized_shape, self.weight, self.bias, self.eps).to(x.dtype)
+
+
+class Linear(nn.Linear):
+    """Weights follow the activation dtype (whisper/model.py:35-41)."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        b = None if self.bias is None else self.bias.to(x.dtype)
+        return F.linear(x, self.weight.to(x.dtype), b)
+
+
+class Conv1d(nn.Conv1d):
+    def _conv_forward(self, x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+        return super()._conv_forward(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
+
+
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> Tensor:
+    """Fixed positional table of the audio encoder (whisper/model.py:53-59)."""
+    half = channels // 2
+    inv = torch.exp(-(math.log(max_timescale) / (half - 1)) * torch.arange(half))
+    ang = torch.arange(length)[:, None] * inv[None, :]
+    return torch.cat([ang.sin(), ang.cos()], dim=1)
+
+
+class MultiHeadAttention(nn.Module):
+    """whisper/model.py:62-109 with ``qkv_attention`` served by the CUDA library.
+
+    ``forward`` keeps the reference signature and its ``(out, second)`` return.  The reference always
+    materialises the full fp32 ``qk`` as ``second`` (and throws it away everywhere except the decoder
+    self-attention); here ``second`` is what the export policy asks for:
+
+      export = None                     -> second is None (encoder, cross attention)
+      export = ("logits" | "probs", None)      -> full (B,H,Tq,Tk) map, same values as the reference's qk / w
+      export = ("logits" | "probs", (lo, hi))  -> only key columns [lo,hi): (B,H,Tq,hi-lo)
+    """
+
+    def __init__(self, n_state: int, n_head: int):
+        super().__init__()
+        self.n_head = n_head
+        self.query = Linear(n_state, n_state)
+        self.key = Linear(n_state, n_state, bias=False)
+        self.value = Linear(n_state, n_state)
+        self.out = Linear(n_state, n_state)
+        self.export: Optional[Tuple[str, Optional[Tuple[int, int]]]] = None
+        self.head_sel: Optional[Tensor] = None
+        self.impl = "auto"
+
+    def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                kv_cache: Optional[dict] = None):
+        q = self.query(x)
+        if kv_cache is None or xa is None or self.key not in kv_cache:
+            src = x if xa is None else xa
+            k = self.key(src)
+            v = self.value(src)
+            if kv_cache is not None and xa is not None:
+                kv_cache[self.key], kv_cache[self.value] = k, v  # cross-attention K/V are computed once
+        else:
+            k, v = kv_cache[self.key], kv_cache[self.value]
+        wv, second = self.qkv_attention(q, k, v, mask)
+        return self.out(wv), second
+
+    def qkv_attention(self, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor] = None):
+        # The only mask the reference ever passes is TextDecoder.mask = triu(-inf) (whisper/model.py:322,103),
+        # i.e. "mask is not None" <=> causal over equal-length q/k.
+        causal = mask is not None and q.shape[1] == k.shape[1]
+        kind, cols = self.export if self.export is not None else (None, None)
+        out, _lse, second = ops.qkv_attention(q, k, v, self.n_head, causal=causal, export=kind, export_cols=cols,
+                                              head_sel=self.head_sel, impl=self.impl)
+        return out, second
+
+
+class Adapter(nn.Module):
+    """Bottleneck adapter x + W2 gelu(W1 x), bottleneck idim//4 (whisper/model.py:181-194)."""
+
+    def __init__(self, idim: int, bottleneck_dim: Optional[int] = None) -> None:
+        super().__init__()
+        bottleneck_dim = bottleneck_dim or idim // 4
+        self.model = nn.Sequential(nn.Linear(idim, bottleneck_dim), nn.GELU(), nn.Linear(bottleneck_dim, idim))
+
+    def forward(self, x: Tensor) -> Tensor:
+        return x + self.model(x)
+
+
+class ResidualAttentionBlock(nn.Module):
+    """whisper/model.py:195-248: returns (x, second output of the SELF attention)."""
+
+    def __init__(self, n_state: int, n_head: int, adapter: bool = False, pe_whisper: bool = False,
+                 cross_attention: bool = False):
+        super().__init__()
+        if pe_whisper:
+            raise NotImplementedError("pe_whisper (MultiHeadAttentionPE ablation) is outside the hot path")
+        self.adapter_flag = adapter
+        self.attn = MultiHeadAttention(n_state, n_head)
+        self.attn_ln = LayerNorm(n_state)
+        if adapter:
+            self.adapter_attn = Adapter(n_state)
+            self.adapter_attn_ln = LayerNorm(n_state)
+        self.cross_attn = MultiHeadAttention(n_state, n_head) if cross_attention else None
+        self.cross_attn_ln = LayerNorm(n_state) if cross_attention else None
+        self.mlp = nn.Sequential(Linear(n_state, 4 * n_state), nn.GELU(), Linear(4 * n_state, n_state))
+        self.mlp_ln = LayerNorm(n_state)
+        if adapter:
+            self.adapter_mlp = Adapter(n_state)
+            self.adapter_mlp_ln = LayerNorm(n_state)
+
+    def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                kv_cache: Optional[dict] = None):
+        a, second = self.attn(self.attn_ln(x), mask=mask, kv_cache=kv_cache)
+        x = x + a
+        if self.adapter_flag:
+            x = self.adapter_attn_ln(self.adapter_attn(x))  # post-LN replaces x (:234-236)
+        if self.cross_attn is not None:
+            x = x + self.cross_attn(self.cross_attn_ln(x), xa, kv_cache=kv_cache)[0]
+        x = x + self.mlp(self.mlp_ln(x))
+        if self.adapter_flag:
+            x = self.adapter_mlp_ln(self.adapter_mlp(x))
+        return x, second
+
+
+class AudioEncoder(nn.Module):
+    """whisper/model.py:251-290."""
+
+    def __init__(self, n_mels: int, n_ctx: int, n_state: int, n_head: int, n_layer: int, adapter: bool = False,
+                 pe_whisper: bool = False):
+        super().__init__()
+        self.conv1 = Conv1d(n_mels, n_state, kernel_size=3, padding=1)
+        self.conv2 = Conv1d(n_state, n_state, kernel_size=3, stride=2, padding=1)
+        self.register_buffer("positional_embedding", sinusoids(n_ctx, n_state))
+        self.blocks = nn.ModuleList(
+            [ResidualAttentionBlock(n_state, n_head, adapter=adapter, pe_whisper=pe_whisper) for _ in range(n_layer)])
+        self.ln_post = LayerNorm(n_state)
+        self.n_layer = n_layer
+
+    def forward(self, x: Tensor) -> Tensor:
+        x = F.gelu(self.conv1(x))
+        x = F.gelu(self.conv2(x)).permute(0, 2, 1)
+        assert x.shape[1:] == self.positional_embedding.shape, "incorrect audio shape"
+        x = (x + self.positional_embedding).to(x.dtype)
+        for block in self.blocks:
+            x, _ = block(x)
+        return self.ln_post(x)
+
+
+class TextDecoder(nn.Module):
+    """whisper/model.py:293-347 (the upstream forward is broken by the fork's tuple-returning blocks, :339-340;
+    this one unpacks the tuple)."""
+
+    def __init__(self, n_vocab: int, n_ctx: int, n_state: int, n_head: int, n_layer: int, pe_whisper: bool = False,
+                 adapter: bool = False):
+        super().__init__()
+        self.token_embedding = nn.Embedding(n_vocab, n_state)
+        self.positional_embedding = nn.Parameter(torch.empty(n_ctx, n_state))
+        self.blocks = nn.ModuleList(
+            [ResidualAttentionBlock(n_state, n_head, adapter=adapter, pe_whisper=pe_whisper, cross_attention=True)
+             for _ in range(n_layer)])
+        self.ln = LayerNorm(n_state)
+        mask = torch.empty(n_ctx, n_ctx).fill_(float("-inf")).triu_(1)
+        self.register_buffer("mask", mask, persistent=False)
+        self.n_layer = n_layer
+
+    def forward(self, x: Tensor, xa: Tensor, kv_cache: Optional[dict] = None) -> Tensor:
+        offset = next(iter(kv_cache.values())).shape[1] if kv_cache else 0
+        x = self.token_embedding(x) + self.positional_embedding[offset: offset + x.shape[-1]]
+        x = x.to(xa.dtype)
+        for block in self.blocks:
+            x, _ = block(x, xa, mask=self.mask, kv_cache=kv_cache)
+        x = self.ln(x)
+        return (x @ self.token_embedding.weight.to(x.dtype).t()).float()
+
+
+class Whisper(nn.Module):
+    """Container with the reference's constructor signature (whisper/model.py:485-506)."""
+
+    def __init__(self, dims: ModelDimensions, pe_whisper: bool = False, adapter: bool = False,
+                 side_network: bool = False, side_network_conf: Optional[dict] = None):
+        super().__init__()
+        if side_network:
+            raise NotImplementedError("side networks are an unused ablation of the reference (SURVEY.md §2a #1)")
+        self.dims = dims
+        self.encoder = AudioEncoder(dims.n_mels, dims.n_audio_ctx, dims.n_audio_state, dims.n_audio_head,
+                                    dims.n_audio_layer, adapter=adapter, pe_whisper=pe_whisper)
+        self.decoder = TextDecoder(dims.n_vocab, dims.n_text_ctx, dims.n_text_state, dims.n_text_head,
+                                   dims.n_text_layer, pe_whisper=pe_whisper, adapter=adapter)
+
+    @property
+    def is_multilingual(self) -> bool:
+        return self.dims.n_vocab == 51865
+
+
+def seeded_init_(module: nn.Module, seed: int = 0) -> nn.Module:
+    """Deterministic init that depends only on parameter NAMES and SHAPES (so the reference module tree and this
+    mirror, which share both, get identical weights): used where no checkpoint is available offline."""
+    for name, p in sorted(module.named_parameters(), key=lambda kv: kv[0]):
+        g = torch.Generator().manual_seed((hash_name(name) + seed) % (2 ** 31))
+        with torch.no_grad():
+            if p.dim() >= 2:
+                fan_in = p.shape[1] * (p.shape[2] if p.dim() > 2 else 1)
+                vals = torch.randn(p.shape, generator=g) / math.sqrt(max(1, fan_in))
+                if name.endswith("token_embedding.weight"):
+                    vals = vals * math.sqrt(fan_in) * 0.02
+            elif name.endswith("ln.weight") or name.endswith("ln_post.weight") or "_ln.weight" in name:
+                vals = 1.0 + 0.02 * torch.randn(p.shape, generator=g)
+            else:
+                vals = 0.02 * torch.randn(p.shape, generator=g)
+            p.copy_(vals.to(p.dtype))
+    return module
+
+
+def hash_name(name: str) -> int:
+    h = 2166136261
+    for ch in name.encode():
+        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+    return h
+
+
+def load_model(name: str, adapter: bool = False, pe_whisper: bool = False, side_network: bool = False,
+               side_network_conf: Optional[dict] = None, device=None, download_root: Optional[str] = None,
+               in_memory: bool = False, seed: int = 0) -> Whisper:
+    """Signature of the fork's whisper.load_model (whisper/__init__.py:182-268).
+
+    ``name`` is a model size or a path to an OpenAI-format checkpoint ({"dims", "model_state_dict"}); a size name
+    is looked up as ``<download_root>/<name>.pt``.  There is no network here: when no checkpoint file exists the
+    model is initialised deterministically from ``seed`` (adapter runs load with strict=False as the reference does).
+    """
+    import os
+
+    path = None
+    if os.path.isfile(name):
+        path = name
+    elif download_root is not None and os.path.isfile(os.path.join(download_root, f"{name}.pt")):
+        path = os.path.join(download_root, f"{name}.pt")
+    if path is not None:
+        ckpt = torch.load(path, map_location="cpu")
+        dims = ModelDimensions(**ckpt["dims"])
+        model = Whisper(dims, pe_whisper, adapter, side_network, side_network_conf)
+        seeded_init_(model, seed)  # adapter params are absent from stock checkpoints
+        model.load_state_dict(ckpt["model_state_dict"], strict=not adapter)
+    else:
+        if name not in MODEL_DIMS:
+            raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
+        model = Whisper(MODEL_DIMS[name], pe_whisper, adapter, side_network, side_network_conf)
+        seeded_init_(model, seed)
+    return model.to(device) if device is not None else model

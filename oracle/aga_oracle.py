@@ -425,6 +425,7 @@ def label_smoothing_loss(logits: np.ndarray, target: np.ndarray, smoothing: floa
     true[np.arange(len(tt)), tt] = 1.0 - smoothing
     lse = np.log(np.exp(x - x.max(1, keepdims=True)).sum(1, keepdims=True)) + x.max(1, keepdims=True)
     logp = x - lse
-    kl = true * (np.log(true) - logp)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        kl = np.where(true > 0, true * (np.log(true) - logp), 0.0)  # nn.KLDivLoss: 0 * log 0 = 0
     kl[ignore] = 0.0
     return float(kl.sum() / (total if normalize_length else B))

@@ -247,5 +247,91 @@ def _logmel64(x):
     return (ls + 4.0) / 4.0, None
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--e2e" not in sys.argv:
     main()
+
+
+# ----------------------------------------------------------------------------- end-to-end module golden
+def e2e_golden():
+    """Reference OpenAIWhisperEncoder + OpenAIWhisperDecoder + ESPnetASRModel.forward (fp32, CPU) on a 12x12-head
+    decoder (the guided loss hard-codes 12 layers x 12 heads) with weights from the name-seeded initialiser that the
+    product mirror shares (aga_b200.whisper_model.seeded_init_).  Stores inputs, losses and gradient summaries."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import aga_b200  # noqa: F401  (product package: only its deterministic initialiser is used here)
+    from aga_b200.whisper_model import seeded_init_
+    from whisper.model import ModelDimensions, Whisper
+    from espnet2.asr.decoder.whisper_decoder import OpenAIWhisperDecoder
+    from espnet.nets.pytorch_backend.transformer.label_smoothing_loss import LabelSmoothingLoss
+
+    dims = ModelDimensions(n_mels=80, n_audio_ctx=1500, n_audio_state=768, n_audio_head=12, n_audio_layer=2,
+                           n_vocab=51865, n_text_ctx=448, n_text_state=768, n_text_head=12, n_text_layer=12)
+
+    def fake_load_model(name, adapter=False, pe_whisper=False, side_network=False, side_network_conf=None, **kw):
+        m = Whisper(dims, pe_whisper, adapter, side_network, side_network_conf)
+        return seeded_init_(m, seed=0)
+
+    whisper.load_model = fake_load_model
+    whisper.available_models = lambda: ["small"]
+    enc = OpenAIWhisperEncoder(whisper_model="small", adapter=True)
+    dec = OpenAIWhisperDecoder(51865, 768, whisper_model="small", adapter=True, whisper_cs=True, src_layer=1)
+    keys = {k: list(v.shape) for k, v in list(enc.state_dict().items()) + list(dec.state_dict().items())}
+
+    m = bare_asr_model()
+    m.vocab_size, m.ignore_id, m.sos, m.eos = 51865, -1, 50258, 50257
+    m.ctc_weight, m.cs_weight, m.interctc_weight = 0.0, 0.01, 0.0
+    m.encoder, m.decoder = enc, dec
+    m.encoder.interctc_use_conditioning = False
+    m.use_transducer_decoder = False
+    m.frontend = m.specaug = m.normalize = m.preencoder = m.postencoder = None
+    m.error_calculator = None
+    m.criterion_att = LabelSmoothingLoss(size=51865, padding_idx=-1, smoothing=0.1, normalize_length=False)
+    m.is_encoder_whisper = True
+    m.c_val_attention = 0.6
+    m.lang_token_id = None
+    m.train()
+    for n, p in m.named_parameters():
+        p.requires_grad_("adapter" in n)
+
+    g = torch.Generator().manual_seed(2022)
+    B, N = 2, 32000
+    speech = (0.1 * torch.randn(B, N, generator=g)).clamp(-1, 1)
+    speech_lengths = torch.tensor([N, N - 4000])
+    speech[1, N - 4000:] = 0.0
+    lid = make_lid_table()
+    eng = [i for i in range(1000, 50257) if lid[i] == O.LID_ENGLISH][:300]
+    oth = [i for i in range(1000, 50257) if lid[i] == O.LID_OTHER][:300]
+    text = torch.full((B, 16), -1, dtype=torch.long)
+    tl = [16, 11]
+    for b in range(B):
+        pool = eng + oth
+        body = [pool[i] for i in torch.randint(0, len(pool), (tl[b] - 5,), generator=g).tolist()]
+        text[b, : tl[b]] = torch.tensor([50260, 50259, 50359, 50363] + body + [50257])
+    text_lengths = torch.tensor(tl)
+    loss, stats, weight = m(speech, speech_lengths, text.clone(), text_lengths)
+    loss.backward()
+    out = dict(speech=speech.numpy(), speech_lengths=speech_lengths.numpy(), text=text.numpy(),
+               text_lengths=text_lengths.numpy(), loss=np.float64(loss.item()),
+               loss_att=np.float64(stats["loss_att"].item()), loss_cs=np.float64(stats["loss_cs"].item()),
+               acc=np.float64(float(stats["acc"])))
+    with torch.no_grad():
+        eo, el, _ = enc(speech, speech_lengths)
+    out["encoder_out_slice"] = eo[:, :8, :16].numpy()
+    out["encoder_out_lens"] = el.numpy()
+    gnames, gnorms = [], []
+    for n, p in sorted(m.named_parameters()):
+        if p.grad is not None:
+            gnames.append(n)
+            gnorms.append(float(p.grad.double().norm()))
+    out["grad_norms"] = np.array(gnorms)
+    pick = "decoder.decoders.blocks.5.adapter_attn.model.2.bias"
+    out["grad_pick"] = dict(m.named_parameters())[pick].grad.numpy()
+    pick2 = "encoder.encoders.blocks.0.adapter_mlp.model.0.bias"
+    out["grad_pick2"] = dict(m.named_parameters())[pick2].grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "e2e_small.npz"), **out)
+    with open(os.path.join(OUT, "e2e_small_meta.json"), "w") as f:
+        json.dump({"state_dict": keys, "grad_names": gnames, "grad_pick": pick, "grad_pick2": pick2}, f, indent=0)
+    print("e2e golden: loss", loss.item(), {k: (float(v) if v is not None else None) for k, v in stats.items()})
+
+
+if __name__ == "__main__" and "--e2e" in sys.argv:
+    e2e_golden()
