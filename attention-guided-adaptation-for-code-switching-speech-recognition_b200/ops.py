@@ -19,6 +19,28 @@ N_FFT = 400
 N_FREQ = 201
 
 
+# Optional per-launch timing (bench.py): when set to a dict, C-ABI calls that launch the hot kernels are bracketed
+# with CUDA events on the launching stream and appended as (tag, flops_or_bytes, start_event, end_event).
+PROFILE = None
+
+
+class _Timed:
+    __slots__ = ("tag", "work", "e0", "e1")
+
+    def __init__(self, tag, work, device):
+        self.tag, self.work = tag, work
+        self.e0 = self.e1 = None
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(device))
+
+    def done(self, device):
+        if self.e0 is not None:
+            self.e1.record(torch.cuda.current_stream(device))
+            PROFILE.setdefault(self.tag, []).append((self.work, self.e0, self.e1))
+
+
 def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -130,8 +152,10 @@ def log_mel_spectrogram(audio: torch.Tensor, ilens: Optional[torch.Tensor] = Non
     nbytes = C.c_size_t()
     L.check(lib.aga_logmel_workspace_bytes(B, N, n_mels, C.byref(nbytes)), "aga_logmel_workspace_bytes")
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=audio.device)
+    tm = _Timed("logmel", float(B) * (N * 4 + n_mels * F * 4), audio.device)
     L.check(lib.aga_logmel_fwd(_ptr(audio), B, N, audio.stride(0), _ptr(packed), n_mels, _ptr(out), _ptr(ws),
                                nbytes.value, _stream_ptr(audio.device)), "aga_logmel_fwd")
+    tm.done(audio.device)
     olens = None if ilens is None else ilens // HOP_LENGTH
     return out, olens
 
@@ -142,6 +166,17 @@ def log_mel_spectrogram(audio: torch.Tensor, ilens: Optional[torch.Tensor] = Non
 _DTYPES = {torch.float32: L.AGA_F32, torch.bfloat16: L.AGA_BF16}
 _IMPLS = {"auto": L.ATTN_AUTO, "simt": L.ATTN_SIMT, "tcgen05": L.ATTN_TCGEN05}
 _KINDS = {None: L.EXPORT_NONE, "none": L.EXPORT_NONE, "logits": L.EXPORT_LOGITS, "probs": L.EXPORT_PROBS}
+
+
+TC_BWD_AVAILABLE = False  # flipped by the library probe below once the tcgen05 backward exists
+
+
+def _impl_name(q, causal, kind, impl, bwd=False) -> str:
+    """Which implementation the C ABI will pick (mirrors attn_api.cu::use_tc) — for profiling tags only."""
+    tc = impl != L.ATTN_SIMT and q.dtype == torch.bfloat16 and not causal and kind == L.EXPORT_NONE
+    if bwd:
+        tc = tc and TC_BWD_AVAILABLE
+    return "tc" if tc else "simt"
 
 
 def _prep(t: torch.Tensor) -> torch.Tensor:
@@ -195,7 +230,10 @@ class _AttnFn(torch.autograd.Function):
         nbytes = C.c_size_t()
         L.check(lib.aga_attn_fwd_workspace_bytes(C.byref(p), C.byref(nbytes)), "aga_attn_fwd_workspace_bytes")
         ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
+        flops = 4.0 * B * n_head * Tq * k.shape[1] * 64 * (0.5 if causal else 1.0)
+        tm = _Timed(f"attn_fwd_{_impl_name(q, causal, kind, impl)}_{Tq}x{k.shape[1]}", flops, q.device)
         L.check(lib.aga_attn_fwd(C.byref(p), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_fwd")
+        tm.done(q.device)
         ctx.save_for_backward(q, k, v, out, lse, head_sel if head_sel is not None else torch.empty(0),
                               export_buf if (export_buf is not None and kind == L.EXPORT_PROBS) else torch.empty(0))
         ctx.cfg = (n_head, causal, kind, cols, impl, head_sel is not None)
@@ -232,7 +270,10 @@ class _AttnFn(torch.autograd.Function):
         nbytes = C.c_size_t()
         L.check(lib.aga_attn_bwd_workspace_bytes(C.byref(bp), C.byref(nbytes)), "aga_attn_bwd_workspace_bytes")
         ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
+        flops = 10.0 * q.shape[0] * n_head * q.shape[1] * k.shape[1] * 64 * (0.5 if causal else 1.0)
+        tm = _Timed(f"attn_bwd_{_impl_name(q, causal, kind, impl, bwd=True)}_{q.shape[1]}x{k.shape[1]}", flops, q.device)
         L.check(lib.aga_attn_bwd(C.byref(bp), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_bwd")
+        tm.done(q.device)
         return dq, dk, dv, None, None, None, None, None, None
 
 
