@@ -316,8 +316,350 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
   return AGA_OK;
 }
 
-bool attn_tc_bwd_supported(const aga_attn_params&) { return false; }
-size_t attn_tc_bwd_workspace(const aga_attn_params&) { return 0; }
-int attn_tc_bwd(const aga_attn_bwd_params&, void*, cudaStream_t) { return AGA_ERR_UNSUPPORTED; }
+namespace {
+// =============================================================================================== backward
+// One CTA = one 128-key tile (K_j, V_j resident in smem) of one (batch, head); it walks the 128-row query tiles.
+// Five tcgen05 GEMMs per (i, j) pair, accumulators in TMEM (448 of 512 columns):
+//   S  = Q_i K_j^T          [  0,128)   SS, both K-major
+//   dP = dO_i V_j^T         [128,256)   SS, both K-major
+//   dV_j += P^T dO_i        [256,320)   A = P  (smem, MN-major: M = keys), B = dO_i (MN-major)
+//   dK_j += dS^T Q_i        [320,384)   A = dS (smem, MN-major),           B = Q_i  (MN-major)
+//   dQ_i  = dS K_j          [384,448)   A = dS (smem, K-major),            B = K_j  (MN-major)
+// The 8 softmax warps (two warpgroups, 64 key columns each) turn S, dP into P = exp2(S c - lse), dS = P (dP - delta)
+// (bf16, written to smem in the 128-byte-swizzled UMMA layout); 4 epilogue warps drain dQ_i with vector
+// red.global.add into an fp32 accumulator (converted to bf16 and scaled by a tiny kernel afterwards) and, at the
+// end, store dK_j, dV_j.  Rows/keys past the tensor ends are zero-filled by TMA, which makes their contributions
+// exactly zero — no masking is needed in the non-causal backward.
+constexpr int kBwdThreads = 448;
+constexpr int kBwdSoftmaxWarps = 8;
+constexpr int kBwdDqWarp0 = 8;
+constexpr int kBwdTmaWarp = 12;
+constexpr int kBwdMmaWarp = 13;
+constexpr uint32_t kColBS = 0, kColBdP = 128, kColBdV = 256, kColBdK = 320, kColBdQ = 384;
+constexpr int kPanelBytes = kBlockM * 128;  // 128 rows x 64 bf16
+
+struct BwdSmem {
+  uint64_t kv_full;
+  uint64_t qdo_full[2], qdo_empty[2];
+  uint64_t sdp_full, pds_ready, dq_full, dq_empty;
+  uint32_t tmem_base;
+};
+// K, V | 2 x (Q, dO) | P (2 panels) | dS (2 panels)
+constexpr size_t kBwdSmemBytes = 1024 + size_t(2 + 4) * kTileBytes + 4 * size_t(kPanelBytes) + sizeof(BwdSmem);
+
+struct BwdArgs {
+  int B, H, Tq, Tk;
+  int64_t k_sb, k_st, v_sb, v_st;
+  const float* lse;
+  const float* delta;
+  float* dq_accum;  // (B, Tq, H*64) fp32, zero-initialised
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+};
+
+// MN-major operand spanning two 64-element panels along M (P^T / dS^T as A): LBO = panel stride
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t(lbo_bytes >> 4) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                   const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kTileBytes;
+  uint8_t* sQ = sV + kTileBytes;        // 2 stages
+  uint8_t* sdO = sQ + 2 * kTileBytes;   // 2 stages
+  uint8_t* sP = sdO + 2 * kTileBytes;   // 2 panels
+  uint8_t* sdS = sP + 2 * kPanelBytes;  // 2 panels
+  BwdSmem* sb = reinterpret_cast<BwdSmem*>(sdS + 2 * kPanelBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int key0 = kt * kBlockN;
+  const int n_qt = (a.Tq + kBlockM - 1) / kBlockM;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sb->kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sb->qdo_full[s], 1);
+      mbar_init(&sb->qdo_empty[s], 1);
+    }
+    mbar_init(&sb->sdp_full, 1);
+    mbar_init(&sb->pds_ready, kBwdSoftmaxWarps);
+    mbar_init(&sb->dq_full, 1);
+    mbar_init(&sb->dq_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == kBwdMmaWarp) {
+    tmem_alloc(&sb->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == kBwdTmaWarp && lane == 0) {
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_k);
+    prefetch_tensormap(&map_v);
+    prefetch_tensormap(&map_do);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sb->tmem_base;
+
+  if (warp == kBwdTmaWarp) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sb->kv_full, 2 * kTileBytes);
+      tma_load_4d(sK, &map_k, &sb->kv_full, 0, h, key0, b);
+      tma_load_4d(sV, &map_v, &sb->kv_full, 0, h, key0, b);
+      for (int i = 0; i < n_qt; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&sb->qdo_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&sb->qdo_full[s], 2 * kTileBytes);
+        tma_load_4d(sQ + s * kTileBytes, &map_q, &sb->qdo_full[s], 0, h, i * kBlockM, b);
+        tma_load_4d(sdO + s * kTileBytes, &map_do, &sb->qdo_full[s], 0, h, i * kBlockM, b);
+      }
+    }
+  } else if (warp == kBwdMmaWarp) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_nt = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // S, dP
+      constexpr uint32_t idesc_tn = make_idesc_bf16(kBlockN, kHeadDim, 1, 1);  // dV, dK: A and B MN-major
+      constexpr uint32_t idesc_nn = make_idesc_bf16(kBlockM, kHeadDim, 0, 1);  // dQ: A K-major, B MN-major
+      const uint64_t dK_k = make_smem_desc_sw128(smem_u32(sK));
+      const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV));
+      const uint64_t dP_mn = make_smem_desc_sw128_mn(smem_u32(sP), kPanelBytes);
+      const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(sdS), kPanelBytes);
+      mbar_wait(&sb->kv_full, 0);
+      for (int i = 0; i < n_qt; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + s * kTileBytes));
+        const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + s * kTileBytes));
+        mbar_wait(&sb->qdo_full[s], ph);
+        tc_fence_after();
+        // S and dP TMEM regions are free: the softmax of tile i-1 finished reading them before pds_ready(i-1)
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk)
+          mma_ss(tmem + kColBS, dQ_s + uint64_t(kk * 2), dK_k + uint64_t(kk * 2), idesc_nt, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk)
+          mma_ss(tmem + kColBdP, ddO_s + uint64_t(kk * 2), dV_k + uint64_t(kk * 2), idesc_nt, kk > 0);
+        tc_commit(&sb->sdp_full);
+        mbar_wait(&sb->pds_ready, i & 1);
+        if (i > 0) mbar_wait(&sb->dq_empty, (i - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kBlockM / 16; ++kk) {  // contraction over the 128 query rows: 16 rows = 2048 bytes
+          mma_ss(tmem + kColBdV, dP_mn + uint64_t(kk * 128), ddO_s + uint64_t(kk * 128), idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < kBlockM / 16; ++kk) {
+          mma_ss(tmem + kColBdK, dS_mn + uint64_t(kk * 128), dQ_s + uint64_t(kk * 128), idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < kBlockN / 16; ++kk) {  // contraction over the 128 keys: panel kk/4, +32 bytes per step
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sdS + (kk >> 2) * kPanelBytes)) + uint64_t((kk & 3) * 2);
+          mma_ss(tmem + kColBdQ, a_desc, dK_k + uint64_t(kk * 128), idesc_nn, kk > 0);
+        }
+        tc_commit(&sb->dq_full);
+        tc_commit(&sb->qdo_empty[s]);
+      }
+    }
+  } else if (warp < kBwdSoftmaxWarps) {
+    // ============================== P / dS producers ==============================
+    const int g = warp >> 2;  // column half
+    const uint32_t lane_base = uint32_t((warp & 3) * 32);
+    const int r = int(lane_base) + lane;  // row inside the query tile
+    const uint32_t t_s = tmem + (lane_base << 16) + kColBS + g * 64;
+    const uint32_t t_dp = tmem + (lane_base << 16) + kColBdP + g * 64;
+    uint8_t* prow = sP + g * kPanelBytes + r * 128;
+    uint8_t* dsrow = sdS + g * kPanelBytes + r * 128;
+    for (int i = 0; i < n_qt; ++i) {
+      const int row = i * kBlockM + r;
+      float lse2 = 0.f, dl = 0.f;
+      if (row < a.Tq) {
+        const int64_t idx = (int64_t(b) * a.H + h) * a.Tq + row;
+        lse2 = a.lse[idx] * 1.4426950408889634f;
+        dl = a.delta[idx];
+      }
+      mbar_wait(&sb->sdp_full, i & 1);
+      if (i > 0) mbar_wait(&sb->dq_full, (i - 1) & 1);  // P / dS smem consumed by the MMAs of tile i-1
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(t_s + c * 32, sv);
+        tmem_ld32(t_dp + c * 32, dv);
+        tmem_wait_ld();
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = ex2(fmaf(__uint_as_float(sv[2 * e]), kScaleLog2, -lse2));
+          const float p1 = ex2(fmaf(__uint_as_float(sv[2 * e + 1]), kScaleLog2, -lse2));
+          const float d0 = p0 * (__uint_as_float(dv[2 * e]) - dl);
+          const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - dl);
+          __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1), hd = __floats2bfloat162_rn(d0, d1);
+          pp[e] = *reinterpret_cast<uint32_t*>(&hp);
+          dd[e] = *reinterpret_cast<uint32_t*>(&hd);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {  // 16-byte chunk index inside the 128-byte row, XOR-swizzled with (row & 7)
+          const int chunk = (c * 4 + q4) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(dsrow + chunk * 16) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->pds_ready);
+    }
+  } else if (warp < kBwdTmaWarp) {
+    // ============================== dQ drain, then dK / dV store ==============================
+    const uint32_t lane_base = uint32_t((warp & 3) * 32);
+    const int r = int(lane_base) + lane;
+    const uint32_t t_dq = tmem + (lane_base << 16) + kColBdQ;
+    for (int i = 0; i < n_qt; ++i) {
+      mbar_wait(&sb->dq_full, i & 1);
+      tc_fence_after();
+      uint32_t lo[32], hi[32];
+      tmem_ld32(t_dq, lo);
+      tmem_ld32(t_dq + 32, hi);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->dq_empty);
+      const int row = i * kBlockM + r;
+      if (row < a.Tq) {
+        float* dst = a.dq_accum + (int64_t(b) * a.Tq + row) * (int64_t(a.H) * kHeadDim) + h * kHeadDim;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          red_add_v4(dst + 4 * e, __uint_as_float(lo[4 * e]), __uint_as_float(lo[4 * e + 1]),
+                     __uint_as_float(lo[4 * e + 2]), __uint_as_float(lo[4 * e + 3]));
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          red_add_v4(dst + 32 + 4 * e, __uint_as_float(hi[4 * e]), __uint_as_float(hi[4 * e + 1]),
+                     __uint_as_float(hi[4 * e + 2]), __uint_as_float(hi[4 * e + 3]));
+      }
+    }
+    // all MMAs of the last tile are complete once dq_full(n_qt-1) fired (commit covers every earlier op)
+    const int key = key0 + r;
+    auto store_rows = [&](uint32_t col, __nv_bfloat16* base, int64_t sb_, int64_t st_, float scale) {
+      __nv_bfloat16* dst = base + int64_t(b) * sb_ + int64_t(key) * st_ + h * kHeadDim;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem + (lane_base << 16) + col + c * 32, v);
+        tmem_wait_ld();
+        if (key < a.Tk) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * q4 + 2 * e]) * scale,
+                                                        __uint_as_float(v[8 * q4 + 2 * e + 1]) * scale);
+              w[e] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+            *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    };
+    store_rows(kColBdV, a.dv, a.v_sb, a.v_st, 1.0f);
+    store_rows(kColBdK, a.dk, a.k_sb, a.k_st, 0.125f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kBwdMmaWarp) tmem_dealloc(tmem, kTmemCols);
+}
+
+// delta[b,h,t] = sum_c dO[b,t,h,c] * O[b,t,h,c]   (one warp per row)
+__global__ void __launch_bounds__(256)
+attn_bwd_delta_bf16_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int64_t o_sb,
+                           int64_t o_st, int B, int H, int Tq, float* __restrict__ delta) {
+  const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= int64_t(B) * H * Tq) return;
+  const int t = int(w % Tq), h = int((w / Tq) % H), b = int(w / (int64_t(Tq) * H));
+  const int64_t off = b * o_sb + int64_t(t) * o_st + h * kHeadDim + lane * 2;
+  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
+  const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_o + off));
+  const float acc = warp_sum(x.x * y.x + x.y * y.y);
+  if (lane == 0) delta[w] = acc;
+}
+
+// dq = bf16(0.125 * dq_accum)
+__global__ void __launch_bounds__(256)
+attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t q_sb, int64_t q_st,
+                           int Tq, int D, int64_t total4) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t e = i * 4;
+    const int c = int(e % D);
+    const int64_t bt = e / D;
+    const int t = int(bt % Tq);
+    const int64_t b = bt / Tq;
+    const float4 v = *reinterpret_cast<const float4*>(acc + e);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * 0.125f, v.y * 0.125f), hi = __floats2bfloat162_rn(v.z * 0.125f, v.w * 0.125f);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dq + b * q_sb + int64_t(t) * q_st + c) = u;
+  }
+}
+
+}  // namespace
+
+bool attn_tc_bwd_supported(const aga_attn_params& p) { return attn_tc_supported(p); }
+
+size_t attn_tc_bwd_workspace(const aga_attn_params& p) {
+  const size_t delta = align_up(size_t(p.B) * p.H * p.Tq * sizeof(float), 256);
+  const size_t dq = align_up(size_t(p.B) * p.Tq * p.H * kHeadDim * sizeof(float), 256);
+  return delta + dq;
+}
+
+int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
+  const aga_attn_params& p = bp.fwd;
+  float* delta = static_cast<float*>(ws);
+  float* dq_acc = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + align_up(size_t(p.B) * p.H * p.Tq * sizeof(float), 256));
+  const size_t dq_bytes = size_t(p.B) * p.Tq * p.H * kHeadDim * sizeof(float);
+  AGA_CUDA_TRY(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
+  const int64_t rows = int64_t(p.B) * p.H * p.Tq;
+  attn_bwd_delta_bf16_kernel<<<unsigned((rows * 32 + 255) / 256), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(p.out), static_cast<const __nv_bfloat16*>(bp.dout), p.o_stride_b, p.o_stride_t,
+      p.B, p.H, p.Tq, delta);
+  AGA_AFTER_LAUNCH();
+  CUtensorMap mq, mk, mv, mdo;
+  int st;
+  if ((st = make_map(&mq, p.q, p.B, p.H, p.Tq, p.q_stride_b, p.q_stride_t, kBlockM)) != AGA_OK) return st;
+  if ((st = make_map(&mk, p.k, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, kBlockN)) != AGA_OK) return st;
+  if ((st = make_map(&mv, p.v, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, kBlockN)) != AGA_OK) return st;
+  if ((st = make_map(&mdo, bp.dout, p.B, p.H, p.Tq, p.o_stride_b, p.o_stride_t, kBlockM)) != AGA_OK) return st;
+  BwdArgs a{p.B, p.H, p.Tq, p.Tk, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, p.lse, delta, dq_acc,
+            static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv)};
+  AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBwdSmemBytes)));
+  dim3 grid((p.Tk + kBlockN - 1) / kBlockN, p.H, p.B);
+  attn_bwd_tc_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(mq, mk, mv, mdo, a);
+  AGA_AFTER_LAUNCH();
+  const int D = p.H * kHeadDim;
+  const int64_t total4 = int64_t(p.B) * p.Tq * D / 4;
+  const unsigned gx = unsigned(std::min<int64_t>((total4 + 255) / 256, 148 * 16));
+  attn_bwd_dq_convert_kernel<<<gx ? gx : 1, 256, 0, s>>>(dq_acc, static_cast<__nv_bfloat16*>(bp.dq), p.q_stride_b,
+                                                          p.q_stride_t, p.Tq, D, total4);
+  AGA_AFTER_LAUNCH();
+  return AGA_OK;
+}
 
 }  // namespace aga

@@ -168,7 +168,7 @@ _IMPLS = {"auto": L.ATTN_AUTO, "simt": L.ATTN_SIMT, "tcgen05": L.ATTN_TCGEN05}
 _KINDS = {None: L.EXPORT_NONE, "none": L.EXPORT_NONE, "logits": L.EXPORT_LOGITS, "probs": L.EXPORT_PROBS}
 
 
-TC_BWD_AVAILABLE = False  # flipped by the library probe below once the tcgen05 backward exists
+TC_BWD_AVAILABLE = True  # the tcgen05 backward exists (attn_tc.cu)
 
 
 def _impl_name(q, causal, kind, impl, bwd=False) -> str:
