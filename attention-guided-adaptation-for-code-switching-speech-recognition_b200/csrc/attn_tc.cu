@@ -6,12 +6,13 @@
 //
 // One CTA = 256 query rows of one (batch, head): two 128-row tiles A and B, each owned by one softmax
 // warpgroup, sharing every K/V tile that TMA brings in (halves L2->smem traffic per FLOP).
-//   TMEM (512 columns): S_A [0,128) | S_B [128,256) | O_A [256,320) | O_B [320,384)
+//   TMEM (512 columns): S_A [0,128) | S_B [128,256) | O_A [256,320) | O_B [320,384) | P_A [384,448) | P_B [448,512)
 //     S_t = Q_t K^T   : tcgen05.mma  M=128 N=128 K=16 x4, A/B from smem (K-major, SWIZZLE_128B)
-//     P_t (bf16) overwrites the first 64 columns of S_t (two keys per 32-bit column)
+//     P_t (bf16, two keys per 32-bit column) has its own 64 columns, so S_t(j+1) can be issued as soon as the
+//     softmax has pulled S_t(j) into registers — the tensor core refills S while the exponentials run
 //     O_t += P_t V    : tcgen05.mma  M=128 N=64  K=16 x8, A from TMEM, B = V tile from smem (MN-major)
-//   The MMA warp issues  PV_A(j), S_A(j+1), PV_B(j), S_B(j+1): while warpgroup A runs the softmax of tile
-//   j+1 the tensor core works for warpgroup B, and vice versa.
+//   The MMA warp issues  S_A(j+1), S_B(j+1) (when the S registers were read), then PV_A(j), PV_B(j) (when P is
+//   written): both GEMMs of tile j+1 / j hide under the softmax of tile j.
 //   Online softmax in the exp2 domain with lazy rescaling: O_t is only rescaled (TMEM round trip) when the
 //   running row maximum grew by more than 2^8, otherwise the stale maximum keeps being used.
 #include "aga_common.cuh"
@@ -35,7 +36,7 @@ constexpr int kTmaWarp = 8;
 constexpr int kMmaWarp = 9;
 constexpr int kThreads = 320;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColO = 256;
+constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
 constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
@@ -44,7 +45,7 @@ struct FwdSmem {
   // barriers
   uint64_t q_full;
   uint64_t k_full[kStages], k_empty[kStages], v_full[kStages], v_empty[kStages];
-  uint64_t s_full[2], p_ready[2], pv_done[2];
+  uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2];
   uint32_t tmem_base;
 };
 constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + size_t(2 + 2 * kStages) * kTileBytes + sizeof(FwdSmem);
@@ -82,7 +83,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&sb->s_full[t], 1);
-      mbar_init(&sb->p_ready[t], 4);  // one arrival per softmax warp of the warpgroup
+      mbar_init(&sb->s_free[t], 4);   // one arrival per softmax warp of the warpgroup
+      mbar_init(&sb->p_ready[t], 4);
       mbar_init(&sb->pv_done[t], 1);
     }
     fence_barrier_init();
@@ -140,24 +142,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       for (int j = 0; j < n_kt; ++j) {
         const int s = j % kStages;
         const uint32_t ph = (j / kStages) & 1;
-        const int s1 = (j + 1) % kStages;
-        const uint32_t ph1 = ((j + 1) / kStages) & 1;
-        const bool more = j + 1 < n_kt;
+        if (j + 1 < n_kt) {  // refill S as soon as the softmax warps hold S(j) in registers
+          const int s1 = (j + 1) % kStages;
+          mbar_wait(&sb->k_full[s1], ((j + 1) / kStages) & 1);
+          for (int t = 0; t < n_tiles; ++t) {
+            mbar_wait(&sb->s_free[t], j & 1);
+            tc_fence_after();
+            issue_s(t, s1);
+          }
+          tc_commit(&sb->k_empty[s1]);
+        }
         mbar_wait(&sb->v_full[s], ph);
-        if (more) mbar_wait(&sb->k_full[s1], ph1);
         for (int t = 0; t < n_tiles; ++t) {
           mbar_wait(&sb->p_ready[t], j & 1);
           tc_fence_after();
           const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + s * kTileBytes));
 #pragma unroll
           for (int kk = 0; kk < kBlockN / 16; ++kk)  // A: +8 TMEM columns (16 bf16); B: +16 key rows = 2048 bytes
-            mma_ts(tmem + kColO + t * kHeadDim, tmem + kColS + t * kBlockN + kk * 8, dv + uint64_t(kk * 128), idesc_pv,
+            mma_ts(tmem + kColO + t * kHeadDim, tmem + kColP + t * 64 + kk * 8, dv + uint64_t(kk * 128), idesc_pv,
                    (j > 0 || kk > 0) ? 1u : 0u);
           tc_commit(&sb->pv_done[t]);
-          if (more) issue_s(t, s1);
         }
         tc_commit(&sb->v_empty[s]);
-        if (more) tc_commit(&sb->k_empty[s1]);
       }
     }
   } else {
@@ -168,32 +174,43 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (t == 0 || active_b) {
       const uint32_t t_s = tmem + (lane_base << 16) + kColS + t * kBlockN;
       const uint32_t t_o = tmem + (lane_base << 16) + kColO + t * kHeadDim;
+      const uint32_t t_p = tmem + (lane_base << 16) + kColP + t * 64;
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < n_kt; ++j) {
         mbar_wait(&sb->s_full[t], j & 1);
         tc_fence_after();
-        const int valid = a.Tk - j * kBlockN;  // keys of this tile that exist (>= 128 except on the last tile)
-        // ---- pass 1: row maximum
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_s + c * 32, r);
-          tmem_wait_ld();
-          if (valid >= (c + 1) * 32) {
+        // ---- the whole S row (128 fp32) into registers, then hand the TMEM columns back to the MMA warp
+        uint32_t sr[4][32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          } else {
+        for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, sr[c]);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->s_free[t]);
+        const int valid = a.Tk - j * kBlockN;  // keys of this tile that exist (>= 128 except on the last tile)
+        if (valid < kBlockN) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-          }
+              if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;  // -inf: exp2 -> 0
         }
-        const float m_new = fmaxf(m_used, mx * kScaleLog2);
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+        }
+        const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * kScaleLog2);
+        if (j > 0) {
+          mbar_wait(&sb->pv_done[t], (j - 1) & 1);  // P_t buffer consumed and O_t stable
+          tc_fence_after();
+        }
         if (j == 0) {
           m_used = m_new;
         } else if (__any_sync(0xffffffffu, m_new - m_used > kRescaleThreshold)) {
-          // s_full(j) completing implies PV(j-1) completed (in-order tensor pipe): O_t is stable here
           const float alpha = ex2(m_used - m_new);
           l *= alpha;
           m_used = m_new;
@@ -207,27 +224,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tmem_st32(t_o + c * 32, r);
           }
         }
-        // ---- pass 2: P = exp2(S*c - m), packed to bf16 over the S columns already consumed
-        float rs = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_s + c * 32, r);
-          tmem_wait_ld();
+        // ---- P = exp2(S*c - m) -> bf16 pairs -> its own TMEM columns
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), kScaleLog2, -m_used));
-            float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), kScaleLog2, -m_used));
-            if (c * 32 + 2 * i >= valid) p0 = 0.f;
-            if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-            rs += p0 + p1;
+            const float p0 = ex2(fmaf(__uint_as_float(sr[c][2 * i]), kScaleLog2, -m_used));
+            const float p1 = ex2(fmaf(__uint_as_float(sr[c][2 * i + 1]), kScaleLog2, -m_used));
+            rs0 += p0;
+            rs1 += p1;
             __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
             pk[i] = *reinterpret_cast<uint32_t*>(&hb);
           }
-          tmem_st16(t_s + c * 16, pk);
+          tmem_st16(t_p + c * 16, pk);
         }
-        l += rs;
+        l += rs0 + rs1;
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();

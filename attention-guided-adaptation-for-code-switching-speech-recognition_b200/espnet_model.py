@@ -75,6 +75,18 @@ def add_sos_eos(ys_pad: torch.Tensor, sos: int, eos: int, ignore_id: int):
     return (pad_list([torch.cat([_sos, y]) for y in ys], eos), pad_list([torch.cat([y, _eos]) for y in ys], ignore_id))
 
 
+def add_sos_eos_static(ys_pad: torch.Tensor, ys_lens: torch.Tensor, sos: int, eos: int, ignore_id: int):
+    """Same result as add_sos_eos for the batches ESPnet's collate_fn produces (ignore_id only as trailing padding,
+    ys_pad already cut to the longest target) without the per-utterance boolean indexing, i.e. without a
+    device->host sync: usable inside a CUDA graph."""
+    B, Lmax = ys_pad.shape
+    pad = ys_pad == ignore_id
+    ys_in = torch.cat([ys_pad.new_full((B, 1), sos), ys_pad.masked_fill(pad, eos)], dim=1)
+    ys_out = torch.cat([ys_pad, ys_pad.new_full((B, 1), ignore_id)], dim=1)
+    ys_out = ys_out.scatter(1, ys_lens.view(B, 1).to(torch.int64), eos)
+    return ys_in, ys_out
+
+
 class LabelSmoothingLoss(torch.nn.Module):
     """espnet/nets/pytorch_backend/transformer/label_smoothing_loss.py:14-63 (KL to the smoothed one-hot)."""
 
@@ -156,6 +168,9 @@ class ESPnetASRModel(torch.nn.Module):
         self.register_buffer("cs_head_mask", mask, persistent=False)
         self.register_buffer("lid_table", lid_table if lid_table is not None else load_lid_table(), persistent=False)
         self.lang_token_id = torch.tensor([[lang_token_id]]) if lang_token_id != -1 else None
+        # static_shapes=True: the caller guarantees `text` is already cut to the longest target and padded only at the
+        # end (what ESPnet's collate_fn produces); the step then runs without device->host syncs (CUDA-graph capturable)
+        self.static_shapes = False
 
     # ------------------------------------------------------------------ a11
     def create_attention_pattern(self, ground_truth_token: torch.Tensor, attention_default: float = 0.6) -> torch.Tensor:
@@ -194,7 +209,10 @@ class ESPnetASRModel(torch.nn.Module):
         if self.lang_token_id is not None:
             ys_pad = torch.cat([self.lang_token_id.repeat(ys_pad.size(0), 1).to(ys_pad.device), ys_pad], dim=1)
             ys_pad_lens = ys_pad_lens + 1
-        ys_in_pad, ys_out_pad = add_sos_eos(ys_pad, self.sos, self.eos, self.ignore_id)
+        if self.static_shapes:
+            ys_in_pad, ys_out_pad = add_sos_eos_static(ys_pad, ys_pad_lens, self.sos, self.eos, self.ignore_id)
+        else:
+            ys_in_pad, ys_out_pad = add_sos_eos(ys_pad, self.sos, self.eos, self.ignore_id)
         ys_in_lens = ys_pad_lens + 1
         decoder_out, att_map = self.decoder(encoder_out, encoder_out_lens, ys_in_pad, ys_in_lens)
         loss_att = self.criterion_att(decoder_out, ys_out_pad)
@@ -210,7 +228,8 @@ class ESPnetASRModel(torch.nn.Module):
         assert text_lengths.dim() == 1, text_lengths.shape
         assert speech.shape[0] == speech_lengths.shape[0] == text.shape[0] == text_lengths.shape[0]
         batch_size = speech.shape[0]
-        text = text[:, : int(text.shape[1]) if kwargs.get("static_text", False) else text_lengths.max()]
+        if not self.static_shapes:
+            text = text[:, : text_lengths.max()]  # "for data-parallel" (:566); needs a host sync
         encoder_out, encoder_out_lens = self.encode(speech, speech_lengths)
         loss_att, acc_att, cer_att, wer_att, loss_cs = self._calc_att_loss(encoder_out, encoder_out_lens, text, text_lengths)
         loss = loss_att

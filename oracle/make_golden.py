@@ -247,7 +247,7 @@ def _logmel64(x):
     return (ls + 4.0) / 4.0, None
 
 
-if __name__ == "__main__" and "--e2e" not in sys.argv:
+if __name__ == "__main__" and "--e2e" not in sys.argv and "--decode" not in sys.argv:
     main()
 
 
@@ -335,3 +335,53 @@ def e2e_golden():
 
 if __name__ == "__main__" and "--e2e" in sys.argv:
     e2e_golden()
+
+
+# ----------------------------------------------------------------------------- config 1: bundled utterance
+def decode_golden():
+    """BASELINE.json configs[0]: Whisper-small greedy decode of the bundled SEAME utterance on CPU with the decoder
+    self-attention maps dumped (code_util/whisper_check.py, attention_map.md) — run through the REFERENCE modules
+    (OpenAIWhisperEncoder.forward, OpenAIWhisperDecoder.batch_score) with the name-seeded weights (no checkpoint
+    exists offline).  Stores the decoded PCM, the greedy token ids and the last step's maps."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    sys.path.insert(0, os.path.join(HERE, "..", "tools"))
+    import aga_b200  # noqa: F401
+    from aga_b200.whisper_model import seeded_init_
+    from flac_decode import decode_flac
+    from whisper.model import ModelDimensions, Whisper
+    from espnet2.asr.decoder.whisper_decoder import OpenAIWhisperDecoder
+
+    pcm, sr, bps = decode_flac(f"{REF}/code_util/nc41m-46nc41mbp_0101-047421-047682.flac")
+    assert sr == 16000 and bps == 16 and pcm.shape == (1, 41760)
+    dims = ModelDimensions(80, 1500, 768, 12, 12, 51865, 448, 768, 12, 12)
+    whisper.load_model = lambda name, adapter=False, pe_whisper=False, side_network=False, side_network_conf=None, **kw: \
+        seeded_init_(Whisper(dims, pe_whisper, adapter, side_network, side_network_conf), seed=0)
+    whisper.available_models = lambda: ["small"]
+    enc = OpenAIWhisperEncoder(whisper_model="small", adapter=True).eval()
+    dec = OpenAIWhisperDecoder(51865, 768, whisper_model="small", adapter=True, whisper_cs=True, src_layer=1).eval()
+    speech = torch.from_numpy(pcm[0].astype(np.float32) / 32768.0)[None]  # librosa.load scaling
+    maps = {}
+    hooks = [blk.register_forward_hook(lambda m, i, o, l=l: maps.__setitem__(l, o[1].detach().clone()))
+             for l, blk in enumerate(dec.decoders.blocks)]
+    with torch.no_grad():
+        enc_out, enc_lens, _ = enc(speech, torch.tensor([speech.shape[1]]))
+        ys = torch.tensor([[50258, 50260, 50259, 50359, 50363]])  # asr_inference.py:324
+        ids, margins, chosen = [], [], []
+        for step in range(12):
+            logp, _ = dec.batch_score(ys, [None], enc_out)
+            top2 = logp[0].topk(2)
+            ids.append(int(top2.indices[0]))
+            margins.append(float(top2.values[0] - top2.values[1]))
+            chosen.append(float(top2.values[0]))
+            ys = torch.cat([ys, top2.indices[:1][None]], dim=1)
+    for h in hooks:
+        h.remove()
+    last_maps = torch.stack([maps[l][0] for l in range(12)]).numpy()  # (12, H, t, t) of the final step
+    np.savez_compressed(os.path.join(OUT, "decode_seame.npz"), pcm=pcm[0].astype(np.int16),
+                        enc_out_lens=enc_lens.numpy(), enc_out_slice=enc_out[0, :8, :16].numpy(),
+                        token_ids=np.array(ids), margins=np.array(margins), logp=np.array(chosen), last_maps=last_maps)
+    print("decode golden:", ids, "min margin", min(margins), "enc frames", int(enc_lens[0]))
+
+
+if __name__ == "__main__" and "--decode" in sys.argv:
+    decode_golden()
