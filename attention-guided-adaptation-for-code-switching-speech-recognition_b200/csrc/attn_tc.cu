@@ -1,5 +1,5 @@
 // bf16 flash attention forward on the 5th-gen tensor cores: tcgen05.mma with TMEM accumulators, TMA-staged
-// Q/K/V tiles, warp-specialised (2 softmax warpgroups + 1 TMA warp + 1 MMA warp), head dim 64.
+// Q/K/V tiles, warp-specialised (2 softmax warpgroups + 1 TMA warp + 2 MMA warps), head dim 64.
 //
 // Reference: MultiHeadAttention.qkv_attention, whisper/whisper/model.py:93-109 (non-causal: encoder self
 // attention 1500x1500 and decoder cross attention Tx1500 — 99.9 % of the attention FLOPs of a step).
@@ -21,6 +21,22 @@
 
 #include <cudaTypedefs.h>
 
+// Debug timeline (compile with -DAGA_TIMELINE): CTA (0,0,0) records clock64() at named points into a global
+// buffer set with aga_debug_set_timeline(); each role owns a row of 4096 slots.
+#ifdef AGA_TIMELINE
+__device__ long long* g_timeline = nullptr;
+#define TL_DECL(role) long long* tl_ptr = (g_timeline && (role) >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_timeline + (role) * 4096 : nullptr; int tl_n = 0
+#define TL(tag) do { if (tl_ptr && tl_n < 2046) { tl_ptr[2 * tl_n] = (tag); tl_ptr[2 * tl_n + 1] = clock64(); ++tl_n; } } while (0)
+#define TL_END() do { if (tl_ptr) { tl_ptr[2 * tl_n] = -1; } } while (0)
+extern "C" __attribute__((visibility("default"))) int aga_debug_set_timeline(long long* p) {
+  return cudaMemcpyToSymbol(g_timeline, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
+#else
+#define TL_DECL(role) do { } while (0)
+#define TL(tag) do { } while (0)
+#define TL_END() do { } while (0)
+#endif
+
 namespace aga {
 namespace {
 
@@ -33,8 +49,8 @@ constexpr int kStages = 3;
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 16 KiB
 constexpr int kNumSoftmaxWarps = 8;
 constexpr int kTmaWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kMmaWarp = 9;   // warps 9 and 10: one MMA-issuing warp per query tile
+constexpr int kThreads = 352;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
 constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
@@ -77,9 +93,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_init(&sb->q_full, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sb->k_full[s], 1);
-      mbar_init(&sb->k_empty[s], 1);
+      mbar_init(&sb->k_empty[s], active_b ? 2 : 1);  // one tcgen05.commit per MMA warp
       mbar_init(&sb->v_full[s], 1);
-      mbar_init(&sb->v_empty[s], 1);
+      mbar_init(&sb->v_empty[s], active_b ? 2 : 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&sb->s_full[t], 1);
@@ -105,66 +121,81 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   if (warp == kTmaWarp) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
+    if (elect_one()) {
       mbar_arrive_expect_tx(&sb->q_full, (active_b ? 2 : 1) * kTileBytes);
       tma_load_4d(sQ, &map_q, &sb->q_full, 0, h, row0, b);
       if (active_b) tma_load_4d(sQ + kTileBytes, &map_q, &sb->q_full, 0, h, row0 + kBlockM, b);
-      for (int j = 0; j < n_kt; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        mbar_wait(&sb->k_empty[s], ph ^ 1);  // first pass through the ring returns immediately
+    }
+    for (int j = 0; j < n_kt; ++j) {
+      const int s = j % kStages;
+      const uint32_t ph = (j / kStages) & 1;
+      mbar_wait(&sb->k_empty[s], ph ^ 1);  // first pass through the ring returns immediately
+      if (elect_one()) {
         mbar_arrive_expect_tx(&sb->k_full[s], kTileBytes);
         tma_load_4d(sK + s * kTileBytes, &map_k, &sb->k_full[s], 0, h, j * kBlockN, b);
-        mbar_wait(&sb->v_empty[s], ph ^ 1);
+      }
+      mbar_wait(&sb->v_empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&sb->v_full[s], kTileBytes);
         tma_load_4d(sV + s * kTileBytes, &map_v, &sb->v_full[s], 0, h, j * kBlockN, b);
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ============================== MMA issuer (one thread) ==============================
-    if (lane == 0) {
+  } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+    // ============================== MMA issuers: one converged warp per query tile, elected lane issues ==========
+    // (a single issuing thread for both tiles serialises ~6 barrier waits + 24 MMAs per key tile and becomes the
+    //  critical path; with one warp per tile the two in-order streams interleave on the tensor pipe)
+    const int t = warp - kMmaWarp;
+    if (t == 0 || active_b) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, kHeadDim, 0, 1);
-      const int n_tiles = active_b ? 2 : 1;
-      auto issue_s = [&](int t, int stage) {
-        const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + t * kTileBytes));
+      TL_DECL(lane == 0 ? 3 * t : -1);
+      const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + t * kTileBytes));
+      auto issue_s = [&](int stage) {
         const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + stage * kTileBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk)  // +32 bytes along K inside the 128-byte swizzle row
-          mma_ss(tmem + kColS + t * kBlockN, dq + uint64_t(kk * 2), dk + uint64_t(kk * 2), idesc_qk, kk > 0);
-        tc_commit(&sb->s_full[t]);
+          for (int kk = 0; kk < kHeadDim / 16; ++kk)  // +32 bytes along K inside the 128-byte swizzle row
+            mma_ss(tmem + kColS + t * kBlockN, dq + uint64_t(kk * 2), dk + uint64_t(kk * 2), idesc_qk, kk > 0);
+          tc_commit(&sb->s_full[t]);
+          tc_commit(&sb->k_empty[stage]);
+        }
+        __syncwarp();
       };
       mbar_wait(&sb->q_full, 0);
       mbar_wait(&sb->k_full[0], 0);
       tc_fence_after();
-      for (int t = 0; t < n_tiles; ++t) issue_s(t, 0);
-      tc_commit(&sb->k_empty[0]);
+      issue_s(0);
       for (int j = 0; j < n_kt; ++j) {
         const int s = j % kStages;
         const uint32_t ph = (j / kStages) & 1;
-        if (j + 1 < n_kt) {  // refill S as soon as the softmax warps hold S(j) in registers
+        if (j + 1 < n_kt) {  // S_t(j+1) as soon as the softmax holds S_t(j) in registers
           const int s1 = (j + 1) % kStages;
+          TL(10);
           mbar_wait(&sb->k_full[s1], ((j + 1) / kStages) & 1);
-          for (int t = 0; t < n_tiles; ++t) {
-            mbar_wait(&sb->s_free[t], j & 1);
-            tc_fence_after();
-            issue_s(t, s1);
-          }
-          tc_commit(&sb->k_empty[s1]);
+          mbar_wait(&sb->s_free[t], j & 1);
+          TL(12);
+          tc_fence_after();
+          issue_s(s1);
+          TL(14);
         }
         mbar_wait(&sb->v_full[s], ph);
-        for (int t = 0; t < n_tiles; ++t) {
-          mbar_wait(&sb->p_ready[t], j & 1);
-          tc_fence_after();
-          const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + s * kTileBytes));
+        mbar_wait(&sb->p_ready[t], j & 1);  // PV_t(j) as soon as P_t(j) is written
+        TL(16);
+        tc_fence_after();
+        const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + s * kTileBytes));
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kBlockN / 16; ++kk)  // A: +8 TMEM columns (16 bf16); B: +16 key rows = 2048 bytes
             mma_ts(tmem + kColO + t * kHeadDim, tmem + kColP + t * 64 + kk * 8, dv + uint64_t(kk * 128), idesc_pv,
                    (j > 0 || kk > 0) ? 1u : 0u);
           tc_commit(&sb->pv_done[t]);
+          tc_commit(&sb->v_empty[s]);
         }
-        tc_commit(&sb->v_empty[s]);
+        __syncwarp();
+        TL(18);
       }
+      TL_END();
     }
   } else {
     // ============================== softmax / correction / epilogue ==============================
@@ -176,8 +207,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const uint32_t t_o = tmem + (lane_base << 16) + kColO + t * kHeadDim;
       const uint32_t t_p = tmem + (lane_base << 16) + kColP + t * 64;
       float m_used = -INFINITY, l = 0.f;
+      TL_DECL((lane == 0 && (warp & 3) == 0) ? 1 + t : -1);
+
+#ifndef AGA_FWD_STAGGER
+#define AGA_FWD_STAGGER 1200
+#endif
+      if (t == 1 && n_kt > 2) {
+        // The two warpgroups share each SM sub-partition's MUFU.  Starting tile B half a period late puts its
+        // exp2 phase under tile A's load / max / wait phases (and vice versa) instead of on top of A's exp2 phase.
+        const long long t0 = clock64();
+        while (clock64() - t0 < AGA_FWD_STAGGER) {
+        }
+      }
       for (int j = 0; j < n_kt; ++j) {
+        TL(20);
         mbar_wait(&sb->s_full[t], j & 1);
+        TL(21);
         tc_fence_after();
         // ---- the whole S row (128 fp32) into registers, then hand the TMEM columns back to the MMA warp
         uint32_t sr[4][32];
@@ -187,6 +232,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sb->s_free[t]);
+        TL(22);
         const int valid = a.Tk - j * kBlockN;  // keys of this tile that exist (>= 128 except on the last tile)
         if (valid < kBlockN) {
 #pragma unroll
@@ -205,8 +251,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * kScaleLog2);
         if (j > 0) {
+          TL(23);
           mbar_wait(&sb->pv_done[t], (j - 1) & 1);  // P_t buffer consumed and O_t stable
           tc_fence_after();
+          TL(24);
         }
         if (j == 0) {
           m_used = m_new;
@@ -241,11 +289,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           tmem_st16(t_p + c * 16, pk);
         }
         l += rs0 + rs1;
+        TL(25);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sb->p_ready[t]);
+        TL(26);
       }
+      TL_END();
       // ---- epilogue: O / l -> bf16 -> global ; lse
       mbar_wait(&sb->pv_done[t], (n_kt - 1) & 1);
       tc_fence_after();
@@ -432,21 +483,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const uint32_t tmem = sb->tmem_base;
 
   if (warp == kBwdTmaWarp) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(&sb->kv_full, 2 * kTileBytes);
       tma_load_4d(sK, &map_k, &sb->kv_full, 0, h, key0, b);
       tma_load_4d(sV, &map_v, &sb->kv_full, 0, h, key0, b);
-      for (int i = 0; i < n_qt; ++i) {
-        const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(&sb->qdo_empty[s], ph ^ 1);
+    }
+    for (int i = 0; i < n_qt; ++i) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      mbar_wait(&sb->qdo_empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&sb->qdo_full[s], 2 * kTileBytes);
         tma_load_4d(sQ + s * kTileBytes, &map_q, &sb->qdo_full[s], 0, h, i * kBlockM, b);
         tma_load_4d(sdO + s * kTileBytes, &map_do, &sb->qdo_full[s], 0, h, i * kBlockM, b);
       }
     }
   } else if (warp == kBwdMmaWarp) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_nt = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // S, dP
       constexpr uint32_t idesc_tn = make_idesc_bf16(kBlockN, kHeadDim, 1, 1);  // dV, dK: A and B MN-major
       constexpr uint32_t idesc_nn = make_idesc_bf16(kBlockM, kHeadDim, 0, 1);  // dQ: A K-major, B MN-major
@@ -455,40 +508,52 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const uint64_t dP_mn = make_smem_desc_sw128_mn(smem_u32(sP), kPanelBytes);
       const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(sdS), kPanelBytes);
       mbar_wait(&sb->kv_full, 0);
+      TL_DECL(lane == 0 ? 0 : -1);
       for (int i = 0; i < n_qt; ++i) {
+        TL(10);
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
         const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + s * kTileBytes));
         const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + s * kTileBytes));
         mbar_wait(&sb->qdo_full[s], ph);
+        TL(11);
         tc_fence_after();
         // S and dP TMEM regions are free: the softmax of tile i-1 finished reading them before pds_ready(i-1)
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk)
-          mma_ss(tmem + kColBS, dQ_s + uint64_t(kk * 2), dK_k + uint64_t(kk * 2), idesc_nt, kk > 0);
+          for (int kk = 0; kk < kHeadDim / 16; ++kk)
+            mma_ss(tmem + kColBS, dQ_s + uint64_t(kk * 2), dK_k + uint64_t(kk * 2), idesc_nt, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk)
-          mma_ss(tmem + kColBdP, ddO_s + uint64_t(kk * 2), dV_k + uint64_t(kk * 2), idesc_nt, kk > 0);
-        tc_commit(&sb->sdp_full);
+          for (int kk = 0; kk < kHeadDim / 16; ++kk)
+            mma_ss(tmem + kColBdP, ddO_s + uint64_t(kk * 2), dV_k + uint64_t(kk * 2), idesc_nt, kk > 0);
+          tc_commit(&sb->sdp_full);
+        }
+        __syncwarp();
+        TL(12);
         mbar_wait(&sb->pds_ready, i & 1);
+        TL(13);
         if (i > 0) mbar_wait(&sb->dq_empty, (i - 1) & 1);
+        TL(14);
         tc_fence_after();
+        const uint64_t dS_k0 = make_smem_desc_sw128(smem_u32(sdS));
+        const uint64_t dS_k1 = make_smem_desc_sw128(smem_u32(sdS + kPanelBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kBlockM / 16; ++kk) {  // contraction over the 128 query rows: 16 rows = 2048 bytes
-          mma_ss(tmem + kColBdV, dP_mn + uint64_t(kk * 128), ddO_s + uint64_t(kk * 128), idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-        }
+          for (int kk = 0; kk < kBlockM / 16; ++kk)  // contraction over the 128 query rows: 16 rows = 2048 bytes
+            mma_ss(tmem + kColBdV, dP_mn + uint64_t(kk * 128), ddO_s + uint64_t(kk * 128), idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < kBlockM / 16; ++kk) {
-          mma_ss(tmem + kColBdK, dS_mn + uint64_t(kk * 128), dQ_s + uint64_t(kk * 128), idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-        }
+          for (int kk = 0; kk < kBlockM / 16; ++kk)
+            mma_ss(tmem + kColBdK, dS_mn + uint64_t(kk * 128), dQ_s + uint64_t(kk * 128), idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 16; ++kk) {  // contraction over the 128 keys: panel kk/4, +32 bytes per step
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sdS + (kk >> 2) * kPanelBytes)) + uint64_t((kk & 3) * 2);
-          mma_ss(tmem + kColBdQ, a_desc, dK_k + uint64_t(kk * 128), idesc_nn, kk > 0);
+          for (int kk = 0; kk < kBlockN / 16; ++kk)  // contraction over the 128 keys: panel kk/4, +32 bytes per step
+            mma_ss(tmem + kColBdQ, ((kk >> 2) ? dS_k1 : dS_k0) + uint64_t((kk & 3) * 2), dK_k + uint64_t(kk * 128), idesc_nn, kk > 0);
+          tc_commit(&sb->dq_full);
+          tc_commit(&sb->qdo_empty[s]);
         }
-        tc_commit(&sb->dq_full);
-        tc_commit(&sb->qdo_empty[s]);
+        __syncwarp();
+        TL(15);
       }
+      TL_END();
     }
   } else if (warp < kBwdSoftmaxWarps) {
     // ============================== P / dS producers ==============================
@@ -499,7 +564,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t t_dp = tmem + (lane_base << 16) + kColBdP + g * 64;
     uint8_t* prow = sP + g * kPanelBytes + r * 128;
     uint8_t* dsrow = sdS + g * kPanelBytes + r * 128;
+    TL_DECL((warp == 0 && lane == 0) ? 1 : -1);
     for (int i = 0; i < n_qt; ++i) {
+      TL(20);
       const int row = i * kBlockM + r;
       float lse2 = 0.f, dl = 0.f;
       if (row < a.Tq) {
@@ -508,7 +575,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         dl = a.delta[idx];
       }
       mbar_wait(&sb->sdp_full, i & 1);
+      TL(21);
       if (i > 0) mbar_wait(&sb->dq_full, (i - 1) & 1);  // P / dS smem consumed by the MMAs of tile i-1
+      TL(22);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -534,18 +603,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           *reinterpret_cast<uint4*>(dsrow + chunk * 16) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
         }
       }
+      TL(23);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb->pds_ready);
+      TL(24);
     }
+    TL_END();
   } else if (warp < kBwdTmaWarp) {
     // ============================== dQ drain, then dK / dV store ==============================
     const uint32_t lane_base = uint32_t((warp & 3) * 32);
     const int r = int(lane_base) + lane;
     const uint32_t t_dq = tmem + (lane_base << 16) + kColBdQ;
+    TL_DECL((warp == kBwdDqWarp0 && lane == 0) ? 2 : -1);
     for (int i = 0; i < n_qt; ++i) {
+      TL(30);
       mbar_wait(&sb->dq_full, i & 1);
+      TL(31);
       tc_fence_after();
       uint32_t lo[32], hi[32];
       tmem_ld32(t_dq, lo);
@@ -554,6 +629,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb->dq_empty);
+      TL(32);
       const int row = i * kBlockM + r;
       if (row < a.Tq) {
         float* dst = a.dq_accum + (int64_t(b) * a.Tq + row) * (int64_t(a.H) * kHeadDim) + h * kHeadDim;
@@ -567,6 +643,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                      __uint_as_float(hi[4 * e + 2]), __uint_as_float(hi[4 * e + 3]));
       }
     }
+    TL(33);
+    TL_END();
     // all MMAs of the last tile are complete once dq_full(n_qt-1) fired (commit covers every earlier op)
     const int key = key0 + r;
     auto store_rows = [&](uint32_t col, __nv_bfloat16* base, int64_t sb_, int64_t st_, float scale) {

@@ -241,5 +241,5 @@ class ESPnetASRModel(torch.nn.Module):
         stats["acc"] = acc_att
         stats["cer"], stats["wer"] = cer_att, wer_att
         stats["loss"] = loss.detach()
-        weight = torch.tensor(float(batch_size), device=loss.device)
+        weight = loss.new_full((), float(batch_size))  # no host->device copy (CUDA-graph capturable)
         return loss, stats, weight
