@@ -405,11 +405,12 @@ constexpr int kPanelBytes = kBlockM * 128;  // 128 rows x 64 bf16
 struct BwdSmem {
   uint64_t kv_full;
   uint64_t qdo_full[2], qdo_empty[2];
-  uint64_t sdp_full, pds_ready, dq_full, dq_empty;
+  uint64_t sdp_full, pds_ready, pds_free[2], dq_full, dq_empty;
   uint32_t tmem_base;
 };
-// K, V | 2 x (Q, dO) | P (2 panels) | dS (2 panels)
-constexpr size_t kBwdSmemBytes = 1024 + size_t(2 + 4) * kTileBytes + 4 * size_t(kPanelBytes) + sizeof(BwdSmem);
+// K, V | 2 x (Q, dO) | 2 x (P, dS) of 2 panels each  (= 224 KiB: P/dS are double-buffered so that the softmax of
+// tile i+1 overlaps the dV/dK/dQ GEMMs of tile i)
+constexpr size_t kBwdSmemBytes = 1024 + size_t(2 + 4) * kTileBytes + 8 * size_t(kPanelBytes) + sizeof(BwdSmem);
 
 struct BwdArgs {
   int B, H, Tq, Tk;
@@ -446,9 +447,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint8_t* sV = sK + kTileBytes;
   uint8_t* sQ = sV + kTileBytes;        // 2 stages
   uint8_t* sdO = sQ + 2 * kTileBytes;   // 2 stages
-  uint8_t* sP = sdO + 2 * kTileBytes;   // 2 panels
-  uint8_t* sdS = sP + 2 * kPanelBytes;  // 2 panels
-  BwdSmem* sb = reinterpret_cast<BwdSmem*>(sdS + 2 * kPanelBytes);
+  uint8_t* sP = sdO + 2 * kTileBytes;   // 2 buffers x 2 panels
+  uint8_t* sdS = sP + 4 * kPanelBytes;  // 2 buffers x 2 panels
+  BwdSmem* sb = reinterpret_cast<BwdSmem*>(sdS + 4 * kPanelBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -463,6 +464,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     mbar_init(&sb->sdp_full, 1);
     mbar_init(&sb->pds_ready, kBwdSoftmaxWarps);
+    mbar_init(&sb->pds_free[0], 1);
+    mbar_init(&sb->pds_free[1], 1);
     mbar_init(&sb->dq_full, 1);
     mbar_init(&sb->dq_empty, 4);
     fence_barrier_init();
@@ -505,20 +508,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       constexpr uint32_t idesc_nn = make_idesc_bf16(kBlockM, kHeadDim, 0, 1);  // dQ: A K-major, B MN-major
       const uint64_t dK_k = make_smem_desc_sw128(smem_u32(sK));
       const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV));
-      const uint64_t dP_mn = make_smem_desc_sw128_mn(smem_u32(sP), kPanelBytes);
-      const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(sdS), kPanelBytes);
       mbar_wait(&sb->kv_full, 0);
       TL_DECL(lane == 0 ? 0 : -1);
-      for (int i = 0; i < n_qt; ++i) {
-        TL(10);
+      auto issue_s_dp = [&](int i) {  // S = Q_i K^T, dP = dO_i V^T into TMEM
         const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
         const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + s * kTileBytes));
         const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + s * kTileBytes));
-        mbar_wait(&sb->qdo_full[s], ph);
-        TL(11);
+        mbar_wait(&sb->qdo_full[s], (i >> 1) & 1);
         tc_fence_after();
-        // S and dP TMEM regions are free: the softmax of tile i-1 finished reading them before pds_ready(i-1)
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kHeadDim / 16; ++kk)
@@ -529,14 +526,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           tc_commit(&sb->sdp_full);
         }
         __syncwarp();
-        TL(12);
-        mbar_wait(&sb->pds_ready, i & 1);
+      };
+      issue_s_dp(0);
+      for (int i = 0; i < n_qt; ++i) {
+        const int s = i & 1;
+        const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + s * kTileBytes));
+        const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + s * kTileBytes));
+        const uint8_t* bP = sP + s * 2 * kPanelBytes;
+        const uint8_t* bdS = sdS + s * 2 * kPanelBytes;
+        const uint64_t dP_mn = make_smem_desc_sw128_mn(smem_u32(bP), kPanelBytes);
+        const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(bdS), kPanelBytes);
+        const uint64_t dS_k0 = make_smem_desc_sw128(smem_u32(bdS));
+        const uint64_t dS_k1 = make_smem_desc_sw128(smem_u32(bdS + kPanelBytes));
+        TL(10);
+        mbar_wait(&sb->pds_ready, i & 1);  // softmax(i) is done with the S / dP columns and has written P / dS
         TL(13);
+        // next tile's S, dP first: its softmax then runs under this tile's dV / dK / dQ GEMMs
+        if (i + 1 < n_qt) issue_s_dp(i + 1);
+        TL(12);
         if (i > 0) mbar_wait(&sb->dq_empty, (i - 1) & 1);
         TL(14);
         tc_fence_after();
-        const uint64_t dS_k0 = make_smem_desc_sw128(smem_u32(sdS));
-        const uint64_t dS_k1 = make_smem_desc_sw128(smem_u32(sdS + kPanelBytes));
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kBlockM / 16; ++kk)  // contraction over the 128 query rows: 16 rows = 2048 bytes
@@ -548,6 +558,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           for (int kk = 0; kk < kBlockN / 16; ++kk)  // contraction over the 128 keys: panel kk/4, +32 bytes per step
             mma_ss(tmem + kColBdQ, ((kk >> 2) ? dS_k1 : dS_k0) + uint64_t((kk & 3) * 2), dK_k + uint64_t(kk * 128), idesc_nn, kk > 0);
           tc_commit(&sb->dq_full);
+          tc_commit(&sb->pds_free[s]);
           tc_commit(&sb->qdo_empty[s]);
         }
         __syncwarp();
@@ -562,8 +573,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int r = int(lane_base) + lane;  // row inside the query tile
     const uint32_t t_s = tmem + (lane_base << 16) + kColBS + g * 64;
     const uint32_t t_dp = tmem + (lane_base << 16) + kColBdP + g * 64;
-    uint8_t* prow = sP + g * kPanelBytes + r * 128;
-    uint8_t* dsrow = sdS + g * kPanelBytes + r * 128;
+    uint8_t* prow0 = sP + g * kPanelBytes + r * 128;
+    uint8_t* dsrow0 = sdS + g * kPanelBytes + r * 128;
     TL_DECL((warp == 0 && lane == 0) ? 1 : -1);
     for (int i = 0; i < n_qt; ++i) {
       TL(20);
@@ -574,9 +585,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         lse2 = a.lse[idx] * 1.4426950408889634f;
         dl = a.delta[idx];
       }
+      uint8_t* prow = prow0 + (i & 1) * 2 * kPanelBytes;
+      uint8_t* dsrow = dsrow0 + (i & 1) * 2 * kPanelBytes;
       mbar_wait(&sb->sdp_full, i & 1);
       TL(21);
-      if (i > 0) mbar_wait(&sb->dq_full, (i - 1) & 1);  // P / dS smem consumed by the MMAs of tile i-1
+      if (i >= 2) mbar_wait(&sb->pds_free[i & 1], ((i >> 1) - 1) & 1);  // buffer consumed by the GEMMs of tile i-2
       TL(22);
       tc_fence_after();
 #pragma unroll 1
