@@ -209,16 +209,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       float m_used = -INFINITY, l = 0.f;
       TL_DECL((lane == 0 && (warp & 3) == 0) ? 1 + t : -1);
 
-#ifndef AGA_FWD_STAGGER
-#define AGA_FWD_STAGGER 1200
-#endif
-      if (t == 1 && n_kt > 2) {
-        // The two warpgroups share each SM sub-partition's MUFU.  Starting tile B half a period late puts its
-        // exp2 phase under tile A's load / max / wait phases (and vice versa) instead of on top of A's exp2 phase.
-        const long long t0 = clock64();
-        while (clock64() - t0 < AGA_FWD_STAGGER) {
-        }
-      }
+      // The two warpgroups share each SM sub-partition's MUFU.  Their exp2 phases are forced to ALTERNATE with a pair
+      // of named barriers (id 2: "A may start its exp2 phase", id 3: "B may start"): while one warpgroup runs its
+      // exponentials at the full MUFU rate, the other does its barrier waits, TMEM loads, row maxima and stores.
+      const bool pingpong = active_b;
+      if (pingpong && t == 1) named_bar_arrive(2, 256);
       for (int j = 0; j < n_kt; ++j) {
         TL(20);
         mbar_wait(&sb->s_full[t], j & 1);
@@ -272,23 +267,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tmem_st32(t_o + c * 32, r);
           }
         }
-        // ---- P = exp2(S*c - m) -> bf16 pairs -> its own TMEM columns
-        float rs0 = 0.f, rs1 = 0.f;
+        // ---- P = exp2(S*c - m) -> bf16 pairs -> its own TMEM columns (packed f32x2 FMA / ADD halve the issue slots)
+        float neg_m = -m_used;
+        if (pingpong) neg_m = named_bar_sync_dep(2 + t, 256, neg_m);
+        float2 rs = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(kScaleLog2, kScaleLog2), nm2 = make_float2(neg_m, neg_m);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2(fmaf(__uint_as_float(sr[c][2 * i]), kScaleLog2, -m_used));
-            const float p1 = ex2(fmaf(__uint_as_float(sr[c][2 * i + 1]), kScaleLog2, -m_used));
-            rs0 += p0;
-            rs1 += p1;
-            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[c][2 * i]), __uint_as_float(sr[c][2 * i + 1])), sc2, nm2);
+            const float2 pp = make_float2(ex2(x.x), ex2(x.y));
+            rs = __fadd2_rn(rs, pp);
+            __nv_bfloat162 hb = __floats2bfloat162_rn(pp.x, pp.y);
             pk[i] = *reinterpret_cast<uint32_t*>(&hb);
           }
           tmem_st16(t_p + c * 16, pk);
         }
-        l += rs0 + rs1;
+        float tile_sum = rs.x + rs.y;
+        if (pingpong && !(t == 1 && j == n_kt - 1)) tile_sum = named_bar_arrive_dep(3 - t, 256, tile_sum);
+        l += tile_sum;
         TL(25);
         tmem_wait_st();
         tc_fence_before();
@@ -383,46 +382,54 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
 namespace {
 // =============================================================================================== backward
 // One CTA = one 128-key tile (K_j, V_j resident in smem) of one (batch, head); it walks the 128-row query tiles.
-// Five tcgen05 GEMMs per (i, j) pair, accumulators in TMEM (448 of 512 columns):
-//   S  = Q_i K_j^T          [  0,128)   SS, both K-major
-//   dP = dO_i V_j^T         [128,256)   SS, both K-major
-//   dV_j += P^T dO_i        [256,320)   A = P  (smem, MN-major: M = keys), B = dO_i (MN-major)
-//   dK_j += dS^T Q_i        [320,384)   A = dS (smem, MN-major),           B = Q_i  (MN-major)
-//   dQ_i  = dS K_j          [384,448)   A = dS (smem, K-major),            B = K_j  (MN-major)
-// The 8 softmax warps (two warpgroups, 64 key columns each) turn S, dP into P = exp2(S c - lse), dS = P (dP - delta)
-// (bf16, written to smem in the 128-byte-swizzled UMMA layout); 4 epilogue warps drain dQ_i with vector
-// red.global.add into an fp32 accumulator (converted to bf16 and scaled by a tiny kernel afterwards) and, at the
-// end, store dK_j, dV_j.  Rows/keys past the tensor ends are zero-filled by TMA, which makes their contributions
-// exactly zero — no masking is needed in the non-causal backward.
+// The score tiles are computed TRANSPOSED (keys in the TMEM lanes, queries along the columns), so that P^T and
+// dS^T — the M x K operands of the dV and dK GEMMs — never leave tensor memory.  Each query tile is handled as two
+// independent 64-query halves g = 0, 1 (one softmax warpgroup each):
+//   S^T_g  = K_j Q_ig^T       cols [64g, 64g+64)          SS, both K-major, N = 64
+//   dP^T_g = V_j dO_ig^T      cols [128+64g, 128+64g+64)  SS, both K-major, N = 64
+//   dV_j  += P^T_g dO_ig      [256,320)   A = P^T_g  (TMEM, bf16 pairs over the first 32 S^T_g columns), B = dO rows (MN-major)
+//   dK_j  += dS^T_g Q_ig      [320,384)   A = dS^T_g (TMEM, bf16 pairs over the first 32 dP^T_g columns), B = Q rows (MN-major)
+//   dQ_i   = dS K_j           [384,448)   A = dS^T rows in smem read as an MN-major operand (both halves), B = K_j (MN-major)
+// Softmax warpgroup g (lane = key): phase 1  P = exp2(S c - lse[q]) -> TMEM  (MUFU-bound);  phase 2
+// dS = P (dP - delta[q]) -> TMEM + one 128-byte swizzled smem row per thread (FMA / LSU-bound).  The two warpgroups
+// share each SM sub-partition, so their phase 1s are forced to ALTERNATE with a pair of named barriers: warpgroup 1
+// runs half a tile behind warpgroup 0 and every phase 1 has the MUFU to itself while the other warpgroup is in
+// phase 2.  lse / delta are per COLUMN here and are broadcast-read from small double-buffered smem tables.
+// 4 drain warps move dQ_i from TMEM into a swizzled fp32 staging buffer (two 64x32... halves of 32 columns) and add
+// it to the global accumulator with cp.reduce.async.bulk; the accumulator is tile-major
+// (b, h, q-tile, column half, 128 rows, 32) so that every bulk reduction is contiguous.
+// Rows/keys past the tensor ends are zero-filled by TMA, which makes their contributions exactly zero.
 constexpr int kBwdThreads = 448;
-constexpr int kBwdSoftmaxWarps = 8;
-constexpr int kBwdDqWarp0 = 8;
 constexpr int kBwdTmaWarp = 12;
 constexpr int kBwdMmaWarp = 13;
 constexpr uint32_t kColBS = 0, kColBdP = 128, kColBdV = 256, kColBdK = 320, kColBdQ = 384;
-constexpr int kPanelBytes = kBlockM * 128;  // 128 rows x 64 bf16
+constexpr int kPanelBytes = kBlockM * 128;             // 128 rows x 64 bf16
+constexpr int kDqStageBytes = kBlockM * 32 * 4;        // one 32-column half of a dQ tile, fp32: 16 KiB
+constexpr int kBwdStages = 3;  // (Q_i, dO_i) ring: the TMA of tile i+2 is in flight while tile i is being processed
 
 struct BwdSmem {
   uint64_t kv_full;
-  uint64_t qdo_full[2], qdo_empty[2];
-  uint64_t sdp_full, pds_ready, pds_free[2], dq_full, dq_empty;
+  uint64_t qdo_full[kBwdStages], qdo_empty[kBwdStages];
+  uint64_t s_full[2], dp_full[2], p_ready[2], ds_ready[2], ds_free[2], dq_full, dq_empty;
   uint32_t tmem_base;
+  alignas(16) float lse2[2][2][64];   // [query half g][tile parity][query]
+  alignas(16) float delta[2][2][64];
 };
-// K, V | 2 x (Q, dO) | 2 x (P, dS) of 2 panels each  (= 224 KiB: P/dS are double-buffered so that the softmax of
-// tile i+1 overlaps the dV/dK/dQ GEMMs of tile i)
-constexpr size_t kBwdSmemBytes = 1024 + size_t(2 + 4) * kTileBytes + 8 * size_t(kPanelBytes) + sizeof(BwdSmem);
+// K, V | kBwdStages x (Q, dO) | 2 x dS^T (2 panels each) | dQ staging
+constexpr size_t kBwdSmemBytes = 1024 + size_t(2 + 2 * kBwdStages) * kTileBytes + 4 * size_t(kPanelBytes) + kDqStageBytes + sizeof(BwdSmem);
+static_assert(kBwdSmemBytes <= 227 * 1024, "backward kernel exceeds the 227 KiB shared-memory limit");
 
 struct BwdArgs {
   int B, H, Tq, Tk;
   int64_t k_sb, k_st, v_sb, v_st;
   const float* lse;
   const float* delta;
-  float* dq_accum;  // (B, Tq, H*64) fp32, zero-initialised
+  float* dq_accum;  // (B, H, ceil(Tq/128), 2, 128, 32) fp32, zero-initialised, 16-byte chunks XOR-swizzled with (row & 7)
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
 };
 
-// MN-major operand spanning two 64-element panels along M (P^T / dS^T as A): LBO = panel stride
+// MN-major operand spanning two 64-element panels along M (dS^T rows as the A of dQ): LBO = panel stride
 __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
@@ -433,9 +440,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, 
   return d;
 }
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -445,11 +458,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + kTileBytes;
-  uint8_t* sQ = sV + kTileBytes;        // 2 stages
-  uint8_t* sdO = sQ + 2 * kTileBytes;   // 2 stages
-  uint8_t* sP = sdO + 2 * kTileBytes;   // 2 buffers x 2 panels
-  uint8_t* sdS = sP + 4 * kPanelBytes;  // 2 buffers x 2 panels
-  BwdSmem* sb = reinterpret_cast<BwdSmem*>(sdS + 4 * kPanelBytes);
+  uint8_t* sQ = sV + kTileBytes;                 // kBwdStages stages
+  uint8_t* sdO = sQ + kBwdStages * kTileBytes;   // kBwdStages stages
+  uint8_t* sdS = sdO + kBwdStages * kTileBytes;  // 2 buffers x 2 panels: [key][queries 0..63], [key][queries 64..127]
+  uint8_t* sdQ = sdS + 4 * kPanelBytes;          // fp32 staging, 4 warps x (32 rows x 128 B)
+  BwdSmem* sb = reinterpret_cast<BwdSmem*>(sdQ + kDqStageBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -458,14 +471,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   if (threadIdx.x == 0) {
     mbar_init(&sb->kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(&sb->qdo_full[s], 1);
       mbar_init(&sb->qdo_empty[s], 1);
     }
-    mbar_init(&sb->sdp_full, 1);
-    mbar_init(&sb->pds_ready, kBwdSoftmaxWarps);
-    mbar_init(&sb->pds_free[0], 1);
-    mbar_init(&sb->pds_free[1], 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&sb->s_full[g], 1);
+      mbar_init(&sb->dp_full[g], 1);
+      mbar_init(&sb->p_ready[g], 4);   // one arrival per warp of the warpgroup
+      mbar_init(&sb->ds_ready[g], 4);
+      mbar_init(&sb->ds_free[g], 1);   // indexed by dS^T buffer
+    }
     mbar_init(&sb->dq_full, 1);
     mbar_init(&sb->dq_empty, 4);
     fence_barrier_init();
@@ -492,8 +508,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tma_load_4d(sV, &map_v, &sb->kv_full, 0, h, key0, b);
     }
     for (int i = 0; i < n_qt; ++i) {
-      const int s = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
+      const int s = i % kBwdStages;
+      const uint32_t ph = (i / kBwdStages) & 1;
       mbar_wait(&sb->qdo_empty[s], ph ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&sb->qdo_full[s], 2 * kTileBytes);
@@ -502,134 +518,225 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     }
   } else if (warp == kBwdMmaWarp) {
-    {
-      constexpr uint32_t idesc_nt = make_idesc_bf16(kBlockM, kBlockN, 0, 0);   // S, dP
-      constexpr uint32_t idesc_tn = make_idesc_bf16(kBlockN, kHeadDim, 1, 1);  // dV, dK: A and B MN-major
-      constexpr uint32_t idesc_nn = make_idesc_bf16(kBlockM, kHeadDim, 0, 1);  // dQ: A K-major, B MN-major
-      const uint64_t dK_k = make_smem_desc_sw128(smem_u32(sK));
-      const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV));
-      mbar_wait(&sb->kv_full, 0);
-      TL_DECL(lane == 0 ? 0 : -1);
-      auto issue_s_dp = [&](int i) {  // S = Q_i K^T, dP = dO_i V^T into TMEM
-        const int s = i & 1;
-        const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + s * kTileBytes));
-        const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + s * kTileBytes));
-        mbar_wait(&sb->qdo_full[s], (i >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
+    constexpr uint32_t idesc_nt = make_idesc_bf16(kBlockN, 64, 0, 0);        // S^T_g, dP^T_g: A and B K-major, N = 64
+    constexpr uint32_t idesc_ts = make_idesc_bf16(kBlockN, kHeadDim, 0, 1);  // dV, dK: A in TMEM, B MN-major
+    constexpr uint32_t idesc_tn = make_idesc_bf16(kBlockM, kHeadDim, 1, 1);  // dQ: A and B MN-major
+    const uint64_t dK_d = make_smem_desc_sw128(smem_u32(sK));
+    const uint64_t dV_d = make_smem_desc_sw128(smem_u32(sV));
+    TL_DECL(lane == 0 ? 0 : -1);
+    // query half g of a 128-row tile = rows 64g .. 64g+63 = byte offset 64 * 128 (a multiple of the 1024-byte swizzle atom)
+    auto issue_s = [&](int i, int g) {  // S^T_g = K Q_ig^T
+      const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + (i % kBwdStages) * kTileBytes + g * 8192));
+      if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kHeadDim / 16; ++kk)
-            mma_ss(tmem + kColBS, dQ_s + uint64_t(kk * 2), dK_k + uint64_t(kk * 2), idesc_nt, kk > 0);
-#pragma unroll
-          for (int kk = 0; kk < kHeadDim / 16; ++kk)
-            mma_ss(tmem + kColBdP, ddO_s + uint64_t(kk * 2), dV_k + uint64_t(kk * 2), idesc_nt, kk > 0);
-          tc_commit(&sb->sdp_full);
-        }
-        __syncwarp();
-      };
-      issue_s_dp(0);
-      for (int i = 0; i < n_qt; ++i) {
-        const int s = i & 1;
-        const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + s * kTileBytes));
-        const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + s * kTileBytes));
-        const uint8_t* bP = sP + s * 2 * kPanelBytes;
-        const uint8_t* bdS = sdS + s * 2 * kPanelBytes;
-        const uint64_t dP_mn = make_smem_desc_sw128_mn(smem_u32(bP), kPanelBytes);
-        const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(bdS), kPanelBytes);
-        const uint64_t dS_k0 = make_smem_desc_sw128(smem_u32(bdS));
-        const uint64_t dS_k1 = make_smem_desc_sw128(smem_u32(bdS + kPanelBytes));
-        TL(10);
-        mbar_wait(&sb->pds_ready, i & 1);  // softmax(i) is done with the S / dP columns and has written P / dS
-        TL(13);
-        // next tile's S, dP first: its softmax then runs under this tile's dV / dK / dQ GEMMs
-        if (i + 1 < n_qt) issue_s_dp(i + 1);
-        TL(12);
-        if (i > 0) mbar_wait(&sb->dq_empty, (i - 1) & 1);
-        TL(14);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < kBlockM / 16; ++kk)  // contraction over the 128 query rows: 16 rows = 2048 bytes
-            mma_ss(tmem + kColBdV, dP_mn + uint64_t(kk * 128), ddO_s + uint64_t(kk * 128), idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-          for (int kk = 0; kk < kBlockM / 16; ++kk)
-            mma_ss(tmem + kColBdK, dS_mn + uint64_t(kk * 128), dQ_s + uint64_t(kk * 128), idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-          for (int kk = 0; kk < kBlockN / 16; ++kk)  // contraction over the 128 keys: panel kk/4, +32 bytes per step
-            mma_ss(tmem + kColBdQ, ((kk >> 2) ? dS_k1 : dS_k0) + uint64_t((kk & 3) * 2), dK_k + uint64_t(kk * 128), idesc_nn, kk > 0);
-          tc_commit(&sb->dq_full);
-          tc_commit(&sb->pds_free[s]);
-          tc_commit(&sb->qdo_empty[s]);
-        }
-        __syncwarp();
-        TL(15);
+        for (int kk = 0; kk < kHeadDim / 16; ++kk)
+          mma_ss(tmem + kColBS + g * 64, dK_d + uint64_t(kk * 2), dQ_s + uint64_t(kk * 2), idesc_nt, kk > 0);
+        tc_commit(&sb->s_full[g]);
       }
-      TL_END();
+      __syncwarp();
+    };
+    auto issue_dp = [&](int i, int g) {  // dP^T_g = V dO_ig^T
+      const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + (i % kBwdStages) * kTileBytes + g * 8192));
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk)
+          mma_ss(tmem + kColBdP + g * 64, dV_d + uint64_t(kk * 2), ddO_s + uint64_t(kk * 2), idesc_nt, kk > 0);
+        tc_commit(&sb->dp_full[g]);
+      }
+      __syncwarp();
+    };
+    // dV += P^T_g dO_ig (A: 4 x 8 packed columns over S^T_g; B: dO rows 64g + 16kk ..)
+    auto issue_dv = [&](int i, int g) {
+      const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + (i % kBwdStages) * kTileBytes + g * 8192));
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          mma_ts(tmem + kColBdV, tmem + kColBS + g * 64 + kk * 8, ddO_s + uint64_t(kk * 128), idesc_ts,
+                 (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
+      }
+      __syncwarp();
+    };
+    auto issue_dk = [&](int i, int g) {
+      const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + (i % kBwdStages) * kTileBytes + g * 8192));
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          mma_ts(tmem + kColBdK, tmem + kColBdP + g * 64 + kk * 8, dQ_s + uint64_t(kk * 128), idesc_ts,
+                 (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&sb->kv_full, 0);
+    mbar_wait(&sb->qdo_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(0, 1);
+    issue_dp(0, 0);
+    issue_dp(0, 1);
+    for (int i = 0; i < n_qt; ++i) {
+      const uint32_t par = i & 1;
+      const bool more = i + 1 < n_qt;
+      // ---- A: half 0 finished phase 1
+      TL(10);
+      mbar_wait(&sb->p_ready[0], par);
+      TL(11);
+      if (more) mbar_wait(&sb->qdo_full[(i + 1) % kBwdStages], ((i + 1) / kBwdStages) & 1);
+      tc_fence_after();
+      issue_dv(i, 0);
+      if (more) issue_s(i + 1, 0);  // overwrites P^T_0(i): behind dV_0(i) on the in-order tensor pipe
+      // ---- B1: half 1 finished phase 1
+      mbar_wait(&sb->p_ready[1], par);
+      TL(12);
+      tc_fence_after();
+      issue_dv(i, 1);
+      if (more) issue_s(i + 1, 1);
+      // ---- B2: half 0 finished phase 2
+      mbar_wait(&sb->ds_ready[0], par);
+      TL(13);
+      tc_fence_after();
+      issue_dk(i, 0);
+      if (more) issue_dp(i + 1, 0);  // overwrites dS^T_0(i): behind dK_0(i)
+      // ---- C: half 1 finished phase 2 -> dK_1, next dP_1, then dQ over both halves
+      mbar_wait(&sb->ds_ready[1], par);
+      TL(14);
+      tc_fence_after();
+      issue_dk(i, 1);
+      if (more) issue_dp(i + 1, 1);
+      if (i > 0) mbar_wait(&sb->dq_empty, (i - 1) & 1);
+      tc_fence_after();
+      const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(sdS + par * 2 * kPanelBytes), kPanelBytes);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kBlockN / 16; ++kk)  // contraction over 128 keys: 16 key rows = 2048 bytes in both operands
+          mma_ss(tmem + kColBdQ, dS_mn + uint64_t(kk * 128), dK_d + uint64_t(kk * 128), idesc_tn, kk > 0);
+        tc_commit(&sb->dq_full);
+        tc_commit(&sb->ds_free[par]);
+        tc_commit(&sb->qdo_empty[i % kBwdStages]);
+      }
+      __syncwarp();
+      TL(15);
     }
-  } else if (warp < kBwdSoftmaxWarps) {
-    // ============================== P / dS producers ==============================
-    const int g = warp >> 2;  // column half
+    TL_END();
+  } else if (warp < 8) {
+    // ============================== P^T / dS^T producers: warpgroup g owns query half g ==============================
+    const int g = warp >> 2;
     const uint32_t lane_base = uint32_t((warp & 3) * 32);
-    const int r = int(lane_base) + lane;  // row inside the query tile
+    const int r = int(lane_base) + lane;  // key row inside the tile
     const uint32_t t_s = tmem + (lane_base << 16) + kColBS + g * 64;
     const uint32_t t_dp = tmem + (lane_base << 16) + kColBdP + g * 64;
-    uint8_t* prow0 = sP + g * kPanelBytes + r * 128;
-    uint8_t* dsrow0 = sdS + g * kPanelBytes + r * 128;
-    TL_DECL((warp == 0 && lane == 0) ? 1 : -1);
+    // per-query lse / delta tables of this half: thread wt < 64 owns lse[wt], the others delta[wt - 64]
+    const int wt = threadIdx.x & 127;
+    const bool is_lse = wt < 64;
+    const float* stat_src = (is_lse ? a.lse : a.delta) + (int64_t(b) * a.H + h) * a.Tq;
+    const float stat_mul = is_lse ? 1.4426950408889634f : 1.0f;
+    const int stat_col = wt & 63;
+    auto stat_slot = [&](int buf) { return (is_lse ? sb->lse2[g][buf] : sb->delta[g][buf]) + stat_col; };
+    auto stat_load = [&](int i) {
+      const int row = i * kBlockM + g * 64 + stat_col;
+      return (i < n_qt && row < a.Tq) ? stat_src[row] * stat_mul : 0.f;
+    };
+    *stat_slot(0) = stat_load(0);
+    float stat_next = stat_load(1);
+    if (g == 1) named_bar_arrive(4, 256);  // warpgroup 0 may run the first phase 1
+    TL_DECL(((warp & 3) == 0 && lane == 0) ? 1 + g : -1);
     for (int i = 0; i < n_qt; ++i) {
+      const uint32_t par = i & 1;
       TL(20);
-      const int row = i * kBlockM + r;
-      float lse2 = 0.f, dl = 0.f;
-      if (row < a.Tq) {
-        const int64_t idx = (int64_t(b) * a.H + h) * a.Tq + row;
-        lse2 = a.lse[idx] * 1.4426950408889634f;
-        dl = a.delta[idx];
-      }
-      uint8_t* prow = prow0 + (i & 1) * 2 * kPanelBytes;
-      uint8_t* dsrow = dsrow0 + (i & 1) * 2 * kPanelBytes;
-      mbar_wait(&sb->sdp_full, i & 1);
+      named_bar_sync(2 + g, 128);  // table `par` complete; the warpgroup is done with table `par ^ 1`
+      *stat_slot(par ^ 1) = stat_next;
+      stat_next = stat_load(i + 2);
+      const float4* lse4 = reinterpret_cast<const float4*>(sb->lse2[g][par]);
+      const float4* del4 = reinterpret_cast<const float4*>(sb->delta[g][par]);
+      mbar_wait(&sb->s_full[g], par);
       TL(21);
-      if (i >= 2) mbar_wait(&sb->pds_free[i & 1], ((i >> 1) - 1) & 1);  // buffer consumed by the GEMMs of tile i-2
-      TL(22);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(t_s + c * 32, sv);
-        tmem_ld32(t_dp + c * 32, dv);
+      uint32_t pk[32];
+      {
+        uint32_t sv[2][32];
+        tmem_ld32(t_s, sv[0]);
+        tmem_ld32(t_s + 32, sv[1]);
         tmem_wait_ld();
-        uint32_t pp[16], dd[16];
+        // ---- phase 1 (MUFU): wait for the other warpgroup to leave its phase 1
+        const float sc = named_bar_sync_dep(4 + g, 256, kScaleLog2);
+        TL(22);
+        const float2 sc2 = make_float2(sc, sc);
+        float chk = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float p0 = ex2(fmaf(__uint_as_float(sv[2 * e]), kScaleLog2, -lse2));
-          const float p1 = ex2(fmaf(__uint_as_float(sv[2 * e + 1]), kScaleLog2, -lse2));
-          const float d0 = p0 * (__uint_as_float(dv[2 * e]) - dl);
-          const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - dl);
-          __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1), hd = __floats2bfloat162_rn(d0, d1);
-          pp[e] = *reinterpret_cast<uint32_t*>(&hp);
-          dd[e] = *reinterpret_cast<uint32_t*>(&hd);
-        }
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {  // 16-byte chunk index inside the 128-byte row, XOR-swizzled with (row & 7)
-          const int chunk = (c * 4 + q4) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
-          *reinterpret_cast<uint4*>(dsrow + chunk * 16) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
-        }
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 L = lse4[c * 8 + e4];
+            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sv[c][4 * e4 + 0]), __uint_as_float(sv[c][4 * e4 + 1])), sc2,
+                                         make_float2(-L.x, -L.y));
+            const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sv[c][4 * e4 + 2]), __uint_as_float(sv[c][4 * e4 + 3])), sc2,
+                                         make_float2(-L.z, -L.w));
+            const float p0 = ex2(x0.x), p1 = ex2(x0.y), p2 = ex2(x1.x), p3 = ex2(x1.y);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
+            pk[c * 16 + 2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[c * 16 + 2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            chk = __uint_as_float(pk[c * 16 + 2 * e4] ^ pk[c * 16 + 2 * e4 + 1] ^ __float_as_uint(chk));
+          }
+        // hand the MUFU to the other warpgroup (the value threaded through depends on every exponential above)
+        if (!(g == 1 && i == n_qt - 1)) pk[31] ^= __float_as_uint(named_bar_arrive_dep(5 - g, 256, chk)) ^ __float_as_uint(chk);
       }
-      TL(23);
-      fence_proxy_async_smem();
+      tmem_st32(t_s, pk);  // 64 queries as bf16 pairs over the first 32 of this half's S^T columns
+      tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sb->pds_ready);
+      if (lane == 0) mbar_arrive(&sb->p_ready[g]);
+      TL(23);
+      // ---- phase 2 (FMA / LSU)
+      uint8_t* dsrow = sdS + (par * 2 + g) * kPanelBytes + r * 128;
+      mbar_wait(&sb->dp_full[g], par);
+      if (i >= 2) mbar_wait(&sb->ds_free[par], ((i >> 1) - 1) & 1);  // dQ(i-2) has consumed this dS^T buffer
       TL(24);
+      tc_fence_after();
+      uint32_t dd[32];
+      {
+        uint32_t dv[2][32];
+        tmem_ld32(t_dp, dv[0]);
+        tmem_ld32(t_dp + 32, dv[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 D = del4[c * 8 + e4];
+            const uint32_t w0 = pk[c * 16 + 2 * e4], w1 = pk[c * 16 + 2 * e4 + 1];
+            const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(dv[c][4 * e4 + 0]), __uint_as_float(dv[c][4 * e4 + 1])),
+                                         make_float2(-D.x, -D.y));
+            const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(dv[c][4 * e4 + 2]), __uint_as_float(dv[c][4 * e4 + 3])),
+                                         make_float2(-D.z, -D.w));
+            const float2 d0 = __fmul2_rn(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), a0);
+            const float2 d1 = __fmul2_rn(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), a1);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(d0.x, d0.y), h1 = __floats2bfloat162_rn(d1.x, d1.y);
+            dd[c * 16 + 2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
+            dd[c * 16 + 2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+      }
+      tmem_st32(t_dp, dd);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4)  // 16-byte chunk q4 = queries 8 q4 .. 8 q4 + 7, XOR-swizzled with (row & 7)
+        *reinterpret_cast<uint4*>(dsrow + ((q4 ^ (r & 7)) * 16)) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+      fence_proxy_async_smem();
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->ds_ready[g]);
+      TL(25);
     }
     TL_END();
   } else if (warp < kBwdTmaWarp) {
     // ============================== dQ drain, then dK / dV store ==============================
-    const uint32_t lane_base = uint32_t((warp & 3) * 32);
+    const int w4 = warp & 3;
+    const uint32_t lane_base = uint32_t(w4 * 32);
     const int r = int(lane_base) + lane;
     const uint32_t t_dq = tmem + (lane_base << 16) + kColBdQ;
-    TL_DECL((warp == kBwdDqWarp0 && lane == 0) ? 2 : -1);
+    uint8_t* stage = sdQ + w4 * (32 * 128);  // this warp's 32 rows x 32 fp32
+    uint8_t* my_row = stage + lane * 128;
+    // tile (b, h, i) = 2 halves x (128 rows x 32 floats); this warp owns rows [32 w4, 32 w4 + 32) of each half
+    float* gdst = a.dq_accum + (int64_t(b) * a.H + h) * n_qt * (kBlockM * kHeadDim) + lane_base * 32;
+    TL_DECL((warp == 8 && lane == 0) ? 3 : -1);
     for (int i = 0; i < n_qt; ++i) {
       TL(30);
       mbar_wait(&sb->dq_full, i & 1);
@@ -642,20 +749,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb->dq_empty);
-      TL(32);
-      const int row = i * kBlockM + r;
-      if (row < a.Tq) {
-        float* dst = a.dq_accum + (int64_t(b) * a.Tq + row) * (int64_t(a.H) * kHeadDim) + h * kHeadDim;
+      float* gtile = gdst + int64_t(i) * (kBlockM * kHeadDim);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          red_add_v4(dst + 4 * e, __uint_as_float(lo[4 * e]), __uint_as_float(lo[4 * e + 1]),
-                     __uint_as_float(lo[4 * e + 2]), __uint_as_float(lo[4 * e + 3]));
+      for (int half = 0; half < 2; ++half) {
+        if (lane == 0) bulk_wait_read0();  // the previous bulk reduction has finished reading the staging rows
+        __syncwarp();
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          red_add_v4(dst + 32 + 4 * e, __uint_as_float(hi[4 * e]), __uint_as_float(hi[4 * e + 1]),
-                     __uint_as_float(hi[4 * e + 2]), __uint_as_float(hi[4 * e + 3]));
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t* v = half ? hi : lo;
+          *reinterpret_cast<uint4*>(my_row + ((e ^ (lane & 7)) * 16)) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+#ifndef AGA_BWD_NO_RED
+        if (lane == 0) bulk_reduce_add_f32(gtile + half * (kBlockM * 32), stage, 32 * 128);
+#endif
       }
+      TL(32);
     }
+    if (lane == 0) bulk_wait0();
     TL(33);
     TL_END();
     // all MMAs of the last tile are complete once dq_full(n_qt-1) fired (commit covers every earlier op)
@@ -705,22 +817,31 @@ attn_bwd_delta_bf16_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloa
   if (lane == 0) delta[w] = acc;
 }
 
-// dq = bf16(0.125 * dq_accum)
+// dq = bf16(0.125 * dq_accum): un-tiles / un-swizzles the (b, h, q-tile, 128, 64) fp32 accumulator; 8 columns per thread
 __global__ void __launch_bounds__(256)
 attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t q_sb, int64_t q_st,
-                           int Tq, int D, int64_t total4) {
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t e = i * 4;
-    const int c = int(e % D);
-    const int64_t bt = e / D;
+                           int H, int Tq, int n_qt, int64_t total8) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total8; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c8 = int(i & 7);
+    const int64_t bth = i >> 3;
+    const int h = int(bth % H);
+    const int64_t bt = bth / H;
     const int t = int(bt % Tq);
     const int64_t b = bt / Tq;
-    const float4 v = *reinterpret_cast<const float4*>(acc + e);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * 0.125f, v.y * 0.125f), hi = __floats2bfloat162_rn(v.z * 0.125f, v.w * 0.125f);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&lo);
-    u.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(dq + b * q_sb + int64_t(t) * q_st + c) = u;
+    // tile (b, h, t >> 7) = 2 column halves x (128 rows x 32 floats); 8 columns = chunks 2 c8 and 2 c8 + 1 of half c8 >> 2
+    const float* row = acc + ((b * H + h) * n_qt + (t >> 7)) * int64_t(kBlockM * kHeadDim) + (c8 >> 2) * (kBlockM * 32) +
+                       (t & 127) * 32;
+    const int ch = (2 * c8) & 7;
+    const float4 v0 = *reinterpret_cast<const float4*>(row + ((ch ^ (t & 7)) * 4));
+    const float4 v1 = *reinterpret_cast<const float4*>(row + (((ch + 1) ^ (t & 7)) * 4));
+    __nv_bfloat162 w0 = __floats2bfloat162_rn(v0.x * 0.125f, v0.y * 0.125f), w1 = __floats2bfloat162_rn(v0.z * 0.125f, v0.w * 0.125f);
+    __nv_bfloat162 w2 = __floats2bfloat162_rn(v1.x * 0.125f, v1.y * 0.125f), w3 = __floats2bfloat162_rn(v1.z * 0.125f, v1.w * 0.125f);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&w0);
+    u.y = *reinterpret_cast<uint32_t*>(&w1);
+    u.z = *reinterpret_cast<uint32_t*>(&w2);
+    u.w = *reinterpret_cast<uint32_t*>(&w3);
+    *reinterpret_cast<uint4*>(dq + b * q_sb + int64_t(t) * q_st + h * kHeadDim + c8 * 8) = u;
   }
 }
 
@@ -730,7 +851,8 @@ bool attn_tc_bwd_supported(const aga_attn_params& p) { return attn_tc_supported(
 
 size_t attn_tc_bwd_workspace(const aga_attn_params& p) {
   const size_t delta = align_up(size_t(p.B) * p.H * p.Tq * sizeof(float), 256);
-  const size_t dq = align_up(size_t(p.B) * p.Tq * p.H * kHeadDim * sizeof(float), 256);
+  const size_t n_qt = size_t(p.Tq + kBlockM - 1) / kBlockM;
+  const size_t dq = align_up(size_t(p.B) * p.H * n_qt * kBlockM * kHeadDim * sizeof(float), 256);
   return delta + dq;
 }
 
@@ -738,7 +860,8 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
   const aga_attn_params& p = bp.fwd;
   float* delta = static_cast<float*>(ws);
   float* dq_acc = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + align_up(size_t(p.B) * p.H * p.Tq * sizeof(float), 256));
-  const size_t dq_bytes = size_t(p.B) * p.Tq * p.H * kHeadDim * sizeof(float);
+  const int n_qt = (p.Tq + kBlockM - 1) / kBlockM;
+  const size_t dq_bytes = size_t(p.B) * p.H * n_qt * kBlockM * kHeadDim * sizeof(float);
   AGA_CUDA_TRY(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   const int64_t rows = int64_t(p.B) * p.H * p.Tq;
   attn_bwd_delta_bf16_kernel<<<unsigned((rows * 32 + 255) / 256), 256, 0, s>>>(
@@ -757,11 +880,10 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
   dim3 grid((p.Tk + kBlockN - 1) / kBlockN, p.H, p.B);
   attn_bwd_tc_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(mq, mk, mv, mdo, a);
   AGA_AFTER_LAUNCH();
-  const int D = p.H * kHeadDim;
-  const int64_t total4 = int64_t(p.B) * p.Tq * D / 4;
-  const unsigned gx = unsigned(std::min<int64_t>((total4 + 255) / 256, 148 * 16));
+  const int64_t total8 = int64_t(p.B) * p.Tq * p.H * (kHeadDim / 8);
+  const unsigned gx = unsigned(std::min<int64_t>((total8 + 255) / 256, 148 * 16));
   attn_bwd_dq_convert_kernel<<<gx ? gx : 1, 256, 0, s>>>(dq_acc, static_cast<__nv_bfloat16*>(bp.dq), p.q_stride_b,
-                                                          p.q_stride_t, p.Tq, D, total4);
+                                                          p.q_stride_t, p.H, p.Tq, n_qt, total8);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }

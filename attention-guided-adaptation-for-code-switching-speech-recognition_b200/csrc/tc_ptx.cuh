@@ -54,6 +54,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// named barriers (ids 1..15; id 0 is __syncthreads): `count` threads in total take part (syncing + arriving)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// The same with a register value threaded through the instruction.  A "memory" clobber orders memory accesses only;
+// the exponentials these barriers are meant to fence are pure register work, which the compiler is otherwise free to
+// hoist above a bar.sync or sink below a bar.arrive.  Consumers of the returned value stay below the barrier,
+// producers of the argument stay above it.
+__device__ __forceinline__ float named_bar_sync_dep(int id, int count, float v) {
+  asm volatile("bar.sync %1, %2;" : "+f"(v) : "r"(id), "r"(count) : "memory");
+  return v;
+}
+__device__ __forceinline__ float named_bar_arrive_dep(int id, int count, float v) {
+  asm volatile("bar.arrive %1, %2;" : "+f"(v) : "r"(id), "r"(count) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -139,9 +155,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 
 __device__ __forceinline__ float ex2(float x) {
+#ifdef AGA_NO_EX2  // experiment builds only: takes the MUFU out of the picture
+  return x * 0.5f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 // ---------------------------------------------------------------- UMMA descriptors

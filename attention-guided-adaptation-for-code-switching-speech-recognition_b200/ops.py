@@ -297,6 +297,61 @@ def qkv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int
 
 
 # ------------------------------------------------------------------------------------------------
+# 8f #2. LayerNorm with fp32 statistics (whisper/model.py:30-32)
+# ------------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        _require_cuda(x, "x")
+        if x.dtype not in _DTYPES:
+            raise L.AgaError(f"layer_norm supports fp32 and bf16 rows, got {x.dtype}")
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        if not x2.is_contiguous() or x2.data_ptr() % 16:
+            x2 = x2.contiguous()
+        rows = x2.shape[0]
+        w32 = weight.detach().float().contiguous()
+        b32 = bias.detach().float().contiguous()
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        tm = _Timed("layernorm_fwd", 2.0 * rows * D * x2.element_size(), x.device)
+        L.check(L.lib().aga_layernorm_fwd(_ptr(x2), _DTYPES[x2.dtype], rows, D, _ptr(w32), _ptr(b32), float(eps), _ptr(y),
+                                          _ptr(mean), _ptr(rstd), _stream_ptr(x.device)), "aga_layernorm_fwd")
+        tm.done(x.device)
+        ctx.save_for_backward(x2, w32, mean, rstd)
+        ctx.shape = x.shape
+        ctx.param_dtypes = (weight.dtype, bias.dtype)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w32, mean, rstd = ctx.saved_tensors
+        rows, D = x2.shape
+        dy2 = dy.reshape(rows, D).to(x2.dtype)
+        if not dy2.is_contiguous() or dy2.data_ptr() % 16:
+            dy2 = dy2.contiguous()
+        need_params = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx = torch.empty_like(x2)
+        dgamma = torch.empty(D, dtype=torch.float32, device=x2.device) if need_params else None
+        dbeta = torch.empty(D, dtype=torch.float32, device=x2.device) if need_params else None
+        tm = _Timed("layernorm_bwd", 3.0 * rows * D * x2.element_size(), x2.device)
+        L.check(L.lib().aga_layernorm_bwd(_ptr(dy2), _ptr(x2), _DTYPES[x2.dtype], rows, D, _ptr(w32), _ptr(mean),
+                                          _ptr(rstd), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _stream_ptr(x2.device)),
+                "aga_layernorm_bwd")
+        tm.done(x2.device)
+        wd, bd = ctx.param_dtypes
+        return (dx.view(ctx.shape), dgamma.to(wd) if ctx.needs_input_grad[1] else None,
+                dbeta.to(bd) if ctx.needs_input_grad[2] else None, None)
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """whisper.model.LayerNorm.forward (whisper/model.py:30-32): statistics in fp32, result in x.dtype, one kernel.
+    Differentiable in x, weight and bias."""
+    return _LayerNormFn.apply(x, weight, bias, float(eps))
+
+
+# ------------------------------------------------------------------------------------------------
 # a11 / a12 / a10
 # ------------------------------------------------------------------------------------------------
 def attention_pattern(tokens: torch.Tensor, lid_table: torch.Tensor, c: float = 0.6) -> torch.Tensor:

@@ -57,23 +57,38 @@ def available_models():
 
 
 class LayerNorm(nn.LayerNorm):
-    """fp32 statistics whatever the activation dtype (whisper/model.py:30-32)."""
+    """fp32 statistics whatever the activation dtype (whisper/model.py:30-32), one CUDA kernel each way."""
 
     def forward(self, x: Tensor) -> Tensor:
-        return F.layer_norm(x.float(), self.normalized_shape, self.weight, self.bias, self.eps).to(x.dtype)
+        return ops.layer_norm(x, self.weight, self.bias, self.eps)
+
+
+def cast_param(owner: nn.Module, slot: str, p: Optional[Tensor], dtype: torch.dtype) -> Optional[Tensor]:
+    """``p.to(dtype)`` as the reference writes it (whisper/model.py:35-49), except that the cast of a FROZEN
+    parameter is done once and kept: under ``--freeze_param`` every Whisper weight is constant, and re-casting
+    all of them fp32->bf16 on every call was 10 % of the training step.  Same values, no graph edge needed."""
+    if p is None or p.dtype == dtype:
+        return p
+    if p.requires_grad and torch.is_grad_enabled():
+        return p.to(dtype)
+    c = owner.__dict__.get(slot)
+    if c is None or c[0] != p._version or c[1] != p.data_ptr() or c[2].dtype != dtype or c[2].device != p.device:
+        c = (p._version, p.data_ptr(), p.detach().to(dtype))
+        owner.__dict__[slot] = c
+    return c[2]
 
 
 class Linear(nn.Linear):
     """Weights follow the activation dtype (whisper/model.py:35-41)."""
 
     def forward(self, x: Tensor) -> Tensor:
-        b = None if self.bias is None else self.bias.to(x.dtype)
-        return F.linear(x, self.weight.to(x.dtype), b)
+        return F.linear(x, cast_param(self, "_w_cast", self.weight, x.dtype), cast_param(self, "_b_cast", self.bias, x.dtype))
 
 
 class Conv1d(nn.Conv1d):
     def _conv_forward(self, x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
-        return super()._conv_forward(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
+        return super()._conv_forward(x, cast_param(self, "_w_cast", weight, x.dtype),
+                                     cast_param(self, "_b_cast", bias, x.dtype))
 
 
 def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> Tensor:
@@ -227,7 +242,7 @@ class TextDecoder(nn.Module):
         for block in self.blocks:
             x, _ = block(x, xa, mask=self.mask, kv_cache=kv_cache)
         x = self.ln(x)
-        return (x @ self.token_embedding.weight.to(x.dtype).t()).float()
+        return (x @ cast_param(self, "_emb_cast", self.token_embedding.weight, x.dtype).t()).float()
 
 
 class Whisper(nn.Module):

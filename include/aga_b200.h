@@ -158,6 +158,20 @@ AGA_API int aga_attention_pattern(const int64_t* tokens, const uint8_t* lid_tabl
  * fp32 in the reference's order so near-ties decide identically. */
 AGA_API int aga_head_vote(const float* probs, int L, int B, int H, int T, uint8_t* decisions, int32_t* counts, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm with fp32 statistics on bf16 / fp32 rows (the first "next" row).
+ * Replaces whisper.model.LayerNorm.forward (W/model.py:30-32: `super().forward(x.float()).type(x.dtype)`),
+ * called four times per ResidualAttentionBlock (attn_ln, adapter_attn_ln, mlp_ln, adapter_mlp_ln; the two
+ * adapter LNs are trainable) — one kernel instead of up-cast + normalise + down-cast.
+ *   x, y, dy, dx : (rows, D) contiguous, dtype AGA_F32 or AGA_BF16, 16-byte aligned; D in {384,512,768,1024,1280}
+ *   gamma, beta  : (D) fp32;  mean, rstd : (rows) fp32, written by fwd and read by bwd
+ *   dgamma, dbeta: (D) fp32, OVERWRITTEN with this call's parameter gradients, or both NULL (frozen LN)
+ * ------------------------------------------------------------------------------------------ */
+AGA_API int aga_layernorm_fwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* beta,
+                      float eps, void* y, float* mean, float* rstd, void* stream);
+AGA_API int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
+                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

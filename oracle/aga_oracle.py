@@ -399,6 +399,27 @@ def calculate_cs_loss(
 # a13. label-smoothing loss + accuracy — espnet/nets/pytorch_backend/transformer/
 #      label_smoothing_loss.py:41-63 ; nets_utils.py:304-324 ; add_sos_eos.py:12-31
 # ----------------------------------------------------------------------------
+def layer_norm(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """whisper/whisper/model.py:30-32 (LayerNorm.forward = F.layer_norm(x.float()).type(x.dtype)), in float64."""
+    x = np.asarray(x, dtype=np.float64)
+    mu = x.mean(axis=-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(axis=-1, keepdims=True)  # biased, as torch
+    return (x - mu) / np.sqrt(var + eps) * np.asarray(gamma, np.float64) + np.asarray(beta, np.float64)
+
+
+def layer_norm_bwd(dy: np.ndarray, x: np.ndarray, gamma: np.ndarray, eps: float = 1e-5):
+    """Gradient of layer_norm w.r.t. (x, gamma, beta) — what autograd derives for whisper/model.py:30-32."""
+    x = np.asarray(x, np.float64)
+    dy = np.asarray(dy, np.float64)
+    D = x.shape[-1]
+    mu = x.mean(axis=-1, keepdims=True)
+    rstd = 1.0 / np.sqrt(((x - mu) ** 2).mean(axis=-1, keepdims=True) + eps)
+    xh = (x - mu) * rstd
+    g = dy * np.asarray(gamma, np.float64)
+    dx = rstd * (g - g.mean(axis=-1, keepdims=True) - xh * (g * xh).mean(axis=-1, keepdims=True))
+    return dx, (dy * xh).reshape(-1, D).sum(0), dy.reshape(-1, D).sum(0)
+
+
 def add_sos_eos(ys_pad: np.ndarray, sos: int, eos: int, ignore_id: int):
     ys = [y[y != ignore_id] for y in ys_pad]
     T = max(len(y) for y in ys) + 1

@@ -88,19 +88,25 @@ def head_vote(probs, counts=None):
     return torch.from_numpy((s1 > s2).astype(np.uint8)), c if counts is None else counts + c.to(counts.device)
 
 
+def layer_norm(x, weight, bias, eps=1e-5):
+    """whisper/whisper/model.py:30-32: up-cast, F.layer_norm, down-cast."""
+    return F.layer_norm(x.float(), (x.shape[-1],), weight, bias, eps).type(x.dtype)
+
+
 @contextlib.contextmanager
 def patched_ops():
     """Route the mirror modules' hot-path calls to the eager port (CPU baseline / eager-GPU comparator only)."""
     import aga_b200
     from aga_b200 import ops
     saved = {n: getattr(ops, n) for n in ("log_mel_spectrogram", "qkv_attention", "attention_pattern", "guided_loss",
-                                          "head_vote")}
+                                          "head_vote", "layer_norm")}
     try:
         ops.log_mel_spectrogram = log_mel_spectrogram
         ops.qkv_attention = qkv_attention
         ops.attention_pattern = attention_pattern
         ops.guided_loss = guided_loss
         ops.head_vote = head_vote
+        ops.layer_norm = layer_norm
         yield
     finally:
         for n, f in saved.items():

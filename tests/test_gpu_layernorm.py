@@ -1,0 +1,74 @@
+"""GPU parity of the fused LayerNorm (whisper/whisper/model.py:30-32) against the oracle and the reference expression."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import aga_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def A():
+    import aga_b200
+    return aga_b200
+
+
+def _case(rows_shape, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(*rows_shape, D, generator=g) * 1.7 + 0.3
+    w = 1.0 + 0.1 * torch.randn(D, generator=g)
+    b = 0.1 * torch.randn(D, generator=g)
+    dy = torch.randn(*rows_shape, D, generator=g)
+    return x, w, b, dy
+
+
+@pytest.mark.parametrize("shape,D", [((2, 37), 384), ((3, 50), 512), ((16, 1500), 768), ((2, 64), 1024), ((1, 9), 1280)])
+def test_layernorm_fp32_vs_oracle(A, shape, D):
+    x, w, b, dy = _case(shape, D, D)
+    xd = x.cuda().requires_grad_()
+    wd, bd = w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y = A.layer_norm(xd, wd, bd, 1e-5)
+    y.backward(dy.cuda())
+    ref = O.layer_norm(x.numpy(), w.numpy(), b.numpy())
+    dx, dg, db = O.layer_norm_bwd(dy.numpy(), x.numpy(), w.numpy())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), ref, rtol=1e-4, atol=1e-5)  # fp32 tolerance of the north star
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), dx, rtol=1e-4, atol=1e-5)
+    scale = max(1.0, float(np.abs(dg).max()))
+    np.testing.assert_allclose(wd.grad.cpu().numpy(), dg, rtol=1e-4, atol=1e-4 * scale)
+    np.testing.assert_allclose(bd.grad.cpu().numpy(), db, rtol=1e-4, atol=1e-4 * scale)
+
+
+@pytest.mark.parametrize("shape,D", [((16, 1500), 768), ((4, 64), 768), ((2, 100), 1280)])
+def test_layernorm_bf16_matches_reference_expression(A, shape, D):
+    """bf16 rows: same result as the reference's up-cast / F.layer_norm / down-cast chain on the GPU (one bf16 rounding)."""
+    x, w, b, dy = _case(shape, D, 7 + D)
+    xb = x.bfloat16().cuda()
+    x1 = xb.clone().requires_grad_()
+    w1, b1 = w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y1 = A.layer_norm(x1, w1, b1, 1e-5)
+    assert y1.dtype == torch.bfloat16
+    y1.backward(dy.bfloat16().cuda())
+    x2 = xb.clone().requires_grad_()
+    w2, b2 = w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y2 = F.layer_norm(x2.float(), (D,), w2, b2, 1e-5).type(torch.bfloat16)
+    y2.backward(dy.bfloat16().cuda())
+    torch.testing.assert_close(y1.float(), y2.float(), rtol=2e-2, atol=2e-2)
+    assert (y1 == y2).float().mean() > 0.99  # identical up to rare last-bit ties of the final rounding
+    torch.testing.assert_close(x1.grad.float(), x2.grad.float(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(w1.grad, w2.grad, rtol=2e-3, atol=2e-3 * float(w2.grad.abs().max()))
+    torch.testing.assert_close(b1.grad, b2.grad, rtol=2e-3, atol=2e-3 * float(b2.grad.abs().max()))
+
+
+def test_layernorm_frozen_params_and_errors(A):
+    x, w, b, dy = _case((4, 10), 768, 1)
+    xd = x.cuda().requires_grad_()
+    y = A.layer_norm(xd, w.cuda(), b.cuda(), 1e-5)  # frozen gamma / beta: no parameter-gradient pass
+    y.backward(dy.cuda())
+    dx, _, _ = O.layer_norm_bwd(dy.numpy(), x.numpy(), w.numpy())
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), dx, rtol=1e-4, atol=1e-5)
+    with pytest.raises(A.AgaError):
+        A.layer_norm(torch.zeros(2, 768), w, b)  # CPU tensors are rejected: no fallback
+    with pytest.raises(A.AgaError):
+        A.layer_norm(torch.zeros(2, 100, device="cuda"), torch.ones(100, device="cuda"), torch.zeros(100, device="cuda"))
