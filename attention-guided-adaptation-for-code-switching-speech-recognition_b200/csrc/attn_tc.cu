@@ -212,7 +212,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       // The two warpgroups share each SM sub-partition's MUFU.  Their exp2 phases are forced to ALTERNATE with a pair
       // of named barriers (id 2: "A may start its exp2 phase", id 3: "B may start"): while one warpgroup runs its
       // exponentials at the full MUFU rate, the other does its barrier waits, TMEM loads, row maxima and stores.
+#ifdef AGA_FWD_TOKEN  // measured slower than free-running warpgroups (a lone warp per sub-partition issues MUFU at half rate)
       const bool pingpong = active_b;
+#else
+      const bool pingpong = false;
+#endif
       if (pingpong && t == 1) named_bar_arrive(2, 256);
       for (int j = 0; j < n_kt; ++j) {
         TL(20);
@@ -399,9 +403,9 @@ namespace {
 // it to the global accumulator with cp.reduce.async.bulk; the accumulator is tile-major
 // (b, h, q-tile, column half, 128 rows, 32) so that every bulk reduction is contiguous.
 // Rows/keys past the tensor ends are zero-filled by TMA, which makes their contributions exactly zero.
-constexpr int kBwdThreads = 448;
+constexpr int kBwdThreads = 512;
 constexpr int kBwdTmaWarp = 12;
-constexpr int kBwdMmaWarp = 13;
+constexpr int kBwdMmaWarp = 13;  // warps 13, 14: the S / dV / dP / dK streams of query halves 0, 1; warp 15: the dQ stream
 constexpr uint32_t kColBS = 0, kColBdP = 128, kColBdV = 256, kColBdK = 320, kColBdQ = 384;
 constexpr int kPanelBytes = kBlockM * 128;             // 128 rows x 64 bf16
 constexpr int kDqStageBytes = kBlockM * 32 * 4;        // one 32-column half of a dQ tile, fp32: 16 KiB
@@ -410,7 +414,7 @@ constexpr int kBwdStages = 3;  // (Q_i, dO_i) ring: the TMA of tile i+2 is in fl
 struct BwdSmem {
   uint64_t kv_full;
   uint64_t qdo_full[kBwdStages], qdo_empty[kBwdStages];
-  uint64_t s_full[2], dp_full[2], p_ready[2], ds_ready[2], ds_free[2], dq_full, dq_empty;
+  uint64_t s_full[2], dp_full[2], p_ready[2], ds_ready[2], ds_free[2], dq_full, dq_empty, dv_init, dk_init;
   uint32_t tmem_base;
   alignas(16) float lse2[2][2][64];   // [query half g][tile parity][query]
   alignas(16) float delta[2][2][64];
@@ -473,7 +477,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_init(&sb->kv_full, 1);
     for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(&sb->qdo_full[s], 1);
-      mbar_init(&sb->qdo_empty[s], 1);
+      mbar_init(&sb->qdo_empty[s], 2);  // one tcgen05.commit per half stream
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&sb->s_full[g], 1);
@@ -484,6 +488,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     mbar_init(&sb->dq_full, 1);
     mbar_init(&sb->dq_empty, 4);
+    mbar_init(&sb->dv_init, 1);
+    mbar_init(&sb->dk_init, 1);
     fence_barrier_init();
   }
   if (warp == kBwdMmaWarp) {
@@ -517,106 +523,102 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tma_load_4d(sdO + s * kTileBytes, &map_do, &sb->qdo_full[s], 0, h, i * kBlockM, b);
       }
     }
-  } else if (warp == kBwdMmaWarp) {
+  } else if (warp == kBwdMmaWarp || warp == kBwdMmaWarp + 1) {
+    // ============================== MMA stream of query half g ==============================
+    // One issuing warp per half (and one more for dQ): every "softmax event -> group of 4 MMAs" costs a few hundred
+    // cycles of barrier wait + descriptor set-up in the issuing thread, and a single in-order issuer for all ten
+    // groups of a tile was the critical path of the kernel (and made half 1's events wait behind half 0's).
+    const int g = warp - kBwdMmaWarp;
     constexpr uint32_t idesc_nt = make_idesc_bf16(kBlockN, 64, 0, 0);        // S^T_g, dP^T_g: A and B K-major, N = 64
     constexpr uint32_t idesc_ts = make_idesc_bf16(kBlockN, kHeadDim, 0, 1);  // dV, dK: A in TMEM, B MN-major
-    constexpr uint32_t idesc_tn = make_idesc_bf16(kBlockM, kHeadDim, 1, 1);  // dQ: A and B MN-major
     const uint64_t dK_d = make_smem_desc_sw128(smem_u32(sK));
     const uint64_t dV_d = make_smem_desc_sw128(smem_u32(sV));
-    TL_DECL(lane == 0 ? 0 : -1);
+    const uint32_t t_sg = tmem + kColBS + g * 64, t_dpg = tmem + kColBdP + g * 64;
+    TL_DECL((lane == 0 && g == 0) ? 0 : -1);
     // query half g of a 128-row tile = rows 64g .. 64g+63 = byte offset 64 * 128 (a multiple of the 1024-byte swizzle atom)
-    auto issue_s = [&](int i, int g) {  // S^T_g = K Q_ig^T
-      const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + (i % kBwdStages) * kTileBytes + g * 8192));
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk)
-          mma_ss(tmem + kColBS + g * 64, dK_d + uint64_t(kk * 2), dQ_s + uint64_t(kk * 2), idesc_nt, kk > 0);
-        tc_commit(&sb->s_full[g]);
-      }
-      __syncwarp();
-    };
-    auto issue_dp = [&](int i, int g) {  // dP^T_g = V dO_ig^T
-      const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + (i % kBwdStages) * kTileBytes + g * 8192));
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk)
-          mma_ss(tmem + kColBdP + g * 64, dV_d + uint64_t(kk * 2), ddO_s + uint64_t(kk * 2), idesc_nt, kk > 0);
-        tc_commit(&sb->dp_full[g]);
-      }
-      __syncwarp();
-    };
-    // dV += P^T_g dO_ig (A: 4 x 8 packed columns over S^T_g; B: dO rows 64g + 16kk ..)
-    auto issue_dv = [&](int i, int g) {
-      const uint64_t ddO_s = make_smem_desc_sw128(smem_u32(sdO + (i % kBwdStages) * kTileBytes + g * 8192));
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          mma_ts(tmem + kColBdV, tmem + kColBS + g * 64 + kk * 8, ddO_s + uint64_t(kk * 128), idesc_ts,
-                 (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
-      }
-      __syncwarp();
-    };
-    auto issue_dk = [&](int i, int g) {
-      const uint64_t dQ_s = make_smem_desc_sw128(smem_u32(sQ + (i % kBwdStages) * kTileBytes + g * 8192));
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          mma_ts(tmem + kColBdK, tmem + kColBdP + g * 64 + kk * 8, dQ_s + uint64_t(kk * 128), idesc_ts,
-                 (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
-      }
-      __syncwarp();
-    };
+    auto q_desc = [&](int i) { return make_smem_desc_sw128(smem_u32(sQ + (i % kBwdStages) * kTileBytes + g * 8192)); };
+    auto do_desc = [&](int i) { return make_smem_desc_sw128(smem_u32(sdO + (i % kBwdStages) * kTileBytes + g * 8192)); };
     mbar_wait(&sb->kv_full, 0);
     mbar_wait(&sb->qdo_full[0], 0);
     tc_fence_after();
-    issue_s(0, 0);
-    issue_s(0, 1);
-    issue_dp(0, 0);
-    issue_dp(0, 1);
+    {
+      const uint64_t dq0 = q_desc(0), ddo0 = do_desc(0);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_sg, dK_d + uint64_t(kk * 2), dq0 + uint64_t(kk * 2), idesc_nt, kk > 0);
+        tc_commit(&sb->s_full[g]);
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_dpg, dV_d + uint64_t(kk * 2), ddo0 + uint64_t(kk * 2), idesc_nt, kk > 0);
+        tc_commit(&sb->dp_full[g]);
+      }
+      __syncwarp();
+    }
     for (int i = 0; i < n_qt; ++i) {
       const uint32_t par = i & 1;
       const bool more = i + 1 < n_qt;
-      // ---- A: half 0 finished phase 1
+      const uint64_t dq_i = q_desc(i), ddo_i = do_desc(i), dq_n = q_desc(i + 1), ddo_n = do_desc(i + 1);
+      // ---- phase 1 of half g done: dV += P^T_g dO_g, then S^T_g(i+1) over the same columns (in-order tensor pipe)
       TL(10);
-      mbar_wait(&sb->p_ready[0], par);
-      TL(11);
+      mbar_wait(&sb->p_ready[g], par);
       if (more) mbar_wait(&sb->qdo_full[(i + 1) % kBwdStages], ((i + 1) / kBwdStages) & 1);
+      if (i == 0 && g == 1) mbar_wait(&sb->dv_init, 0);  // half 0's first (overwriting) dV MMA has executed
+      TL(11);
       tc_fence_after();
-      issue_dv(i, 0);
-      if (more) issue_s(i + 1, 0);  // overwrites P^T_0(i): behind dV_0(i) on the in-order tensor pipe
-      // ---- B1: half 1 finished phase 1
-      mbar_wait(&sb->p_ready[1], par);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          mma_ts(tmem + kColBdV, t_sg + kk * 8, ddo_i + uint64_t(kk * 128), idesc_ts, (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
+        if (i == 0 && g == 0) tc_commit(&sb->dv_init);
+        if (more) {
+#pragma unroll
+          for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_sg, dK_d + uint64_t(kk * 2), dq_n + uint64_t(kk * 2), idesc_nt, kk > 0);
+          tc_commit(&sb->s_full[g]);
+        }
+      }
+      __syncwarp();
+      // ---- phase 2 of half g done: dK += dS^T_g Q_g, then dP^T_g(i+1) over the same columns
       TL(12);
-      tc_fence_after();
-      issue_dv(i, 1);
-      if (more) issue_s(i + 1, 1);
-      // ---- B2: half 0 finished phase 2
-      mbar_wait(&sb->ds_ready[0], par);
+      mbar_wait(&sb->ds_ready[g], par);
+      if (i == 0 && g == 1) mbar_wait(&sb->dk_init, 0);
       TL(13);
       tc_fence_after();
-      issue_dk(i, 0);
-      if (more) issue_dp(i + 1, 0);  // overwrites dS^T_0(i): behind dK_0(i)
-      // ---- C: half 1 finished phase 2 -> dK_1, next dP_1, then dQ over both halves
-      mbar_wait(&sb->ds_ready[1], par);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          mma_ts(tmem + kColBdK, t_dpg + kk * 8, dq_i + uint64_t(kk * 128), idesc_ts, (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
+        if (i == 0 && g == 0) tc_commit(&sb->dk_init);
+        tc_commit(&sb->qdo_empty[i % kBwdStages]);  // this half's last read of (Q_i, dO_i)
+        if (more) {
+#pragma unroll
+          for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_dpg, dV_d + uint64_t(kk * 2), ddo_n + uint64_t(kk * 2), idesc_nt, kk > 0);
+          tc_commit(&sb->dp_full[g]);
+        }
+      }
+      __syncwarp();
       TL(14);
-      tc_fence_after();
-      issue_dk(i, 1);
-      if (more) issue_dp(i + 1, 1);
+    }
+    TL_END();
+  } else if (warp == kBwdMmaWarp + 2) {
+    // ============================== dQ stream: dQ_i = dS K_j once both halves of dS^T(i) are in smem ====================
+    constexpr uint32_t idesc_tn = make_idesc_bf16(kBlockM, kHeadDim, 1, 1);  // A and B MN-major
+    const uint64_t dK_d = make_smem_desc_sw128(smem_u32(sK));
+    mbar_wait(&sb->kv_full, 0);
+    for (int i = 0; i < n_qt; ++i) {
+      const uint32_t par = i & 1;
+      const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(sdS + par * 2 * kPanelBytes), kPanelBytes);
+      mbar_wait(&sb->ds_ready[0], par);
+      mbar_wait(&sb->ds_ready[1], par);
       if (i > 0) mbar_wait(&sb->dq_empty, (i - 1) & 1);
       tc_fence_after();
-      const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(sdS + par * 2 * kPanelBytes), kPanelBytes);
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < kBlockN / 16; ++kk)  // contraction over 128 keys: 16 key rows = 2048 bytes in both operands
           mma_ss(tmem + kColBdQ, dS_mn + uint64_t(kk * 128), dK_d + uint64_t(kk * 128), idesc_tn, kk > 0);
         tc_commit(&sb->dq_full);
         tc_commit(&sb->ds_free[par]);
-        tc_commit(&sb->qdo_empty[i % kBwdStages]);
       }
       __syncwarp();
-      TL(15);
     }
-    TL_END();
   } else if (warp < 8) {
     // ============================== P^T / dS^T producers: warpgroup g owns query half g ==============================
     const int g = warp >> 2;
@@ -630,23 +632,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const float* stat_src = (is_lse ? a.lse : a.delta) + (int64_t(b) * a.H + h) * a.Tq;
     const float stat_mul = is_lse ? 1.4426950408889634f : 1.0f;
     const int stat_col = wt & 63;
-    auto stat_slot = [&](int buf) { return (is_lse ? sb->lse2[g][buf] : sb->delta[g][buf]) + stat_col; };
-    auto stat_load = [&](int i) {
+    auto stat_slot = [&](int buf) { return smem_u32((is_lse ? sb->lse2[g][buf] : sb->delta[g][buf]) + stat_col); };
+    auto stat_load = [&](int i) {  // raw value: the scaling happens when it is stored, a tile later (no stall on the load)
       const int row = i * kBlockM + g * 64 + stat_col;
-      return (i < n_qt && row < a.Tq) ? stat_src[row] * stat_mul : 0.f;
+      return (i < n_qt && row < a.Tq) ? stat_src[row] : 0.f;
     };
-    *stat_slot(0) = stat_load(0);
+    sts32f(stat_slot(0), stat_load(0) * stat_mul);
     float stat_next = stat_load(1);
+    const uint32_t lse_tab = smem_u32(sb->lse2[g][0]), del_tab = smem_u32(sb->delta[g][0]);  // [parity][64] floats
+    const uint32_t ds_base = smem_u32(sdS + g * kPanelBytes + r * 128);
+#ifndef AGA_BWD_NO_TOKEN
     if (g == 1) named_bar_arrive(4, 256);  // warpgroup 0 may run the first phase 1
+#endif
     TL_DECL(((warp & 3) == 0 && lane == 0) ? 1 + g : -1);
     for (int i = 0; i < n_qt; ++i) {
       const uint32_t par = i & 1;
       TL(20);
       named_bar_sync(2 + g, 128);  // table `par` complete; the warpgroup is done with table `par ^ 1`
-      *stat_slot(par ^ 1) = stat_next;
+      sts32f(stat_slot(par ^ 1), stat_next * stat_mul);
       stat_next = stat_load(i + 2);
-      const float4* lse4 = reinterpret_cast<const float4*>(sb->lse2[g][par]);
-      const float4* del4 = reinterpret_cast<const float4*>(sb->delta[g][par]);
+      const uint32_t lse4 = lse_tab + par * 256, del4 = del_tab + par * 256;
       mbar_wait(&sb->s_full[g], par);
       TL(21);
       tc_fence_after();
@@ -657,7 +662,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tmem_ld32(t_s + 32, sv[1]);
         tmem_wait_ld();
         // ---- phase 1 (MUFU): wait for the other warpgroup to leave its phase 1
+#ifndef AGA_BWD_NO_TOKEN
         const float sc = named_bar_sync_dep(4 + g, 256, kScaleLog2);
+#else
+        const float sc = kScaleLog2;
+#endif
         TL(22);
         const float2 sc2 = make_float2(sc, sc);
         float chk = 0.f;
@@ -665,7 +674,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 L = lse4[c * 8 + e4];
+            const float4 L = lds128f(lse4 + (c * 8 + e4) * 16);
             const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sv[c][4 * e4 + 0]), __uint_as_float(sv[c][4 * e4 + 1])), sc2,
                                          make_float2(-L.x, -L.y));
             const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sv[c][4 * e4 + 2]), __uint_as_float(sv[c][4 * e4 + 3])), sc2,
@@ -677,7 +686,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             chk = __uint_as_float(pk[c * 16 + 2 * e4] ^ pk[c * 16 + 2 * e4 + 1] ^ __float_as_uint(chk));
           }
         // hand the MUFU to the other warpgroup (the value threaded through depends on every exponential above)
+#ifndef AGA_BWD_NO_TOKEN
         if (!(g == 1 && i == n_qt - 1)) pk[31] ^= __float_as_uint(named_bar_arrive_dep(5 - g, 256, chk)) ^ __float_as_uint(chk);
+#endif
       }
       tmem_st32(t_s, pk);  // 64 queries as bf16 pairs over the first 32 of this half's S^T columns
       tmem_wait_st();
@@ -686,7 +697,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (lane == 0) mbar_arrive(&sb->p_ready[g]);
       TL(23);
       // ---- phase 2 (FMA / LSU)
-      uint8_t* dsrow = sdS + (par * 2 + g) * kPanelBytes + r * 128;
+      const uint32_t dsrow = ds_base + par * 2 * kPanelBytes;
       mbar_wait(&sb->dp_full[g], par);
       if (i >= 2) mbar_wait(&sb->ds_free[par], ((i >> 1) - 1) & 1);  // dQ(i-2) has consumed this dS^T buffer
       TL(24);
@@ -701,7 +712,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 D = del4[c * 8 + e4];
+            const float4 D = lds128f(del4 + (c * 8 + e4) * 16);
             const uint32_t w0 = pk[c * 16 + 2 * e4], w1 = pk[c * 16 + 2 * e4 + 1];
             const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(dv[c][4 * e4 + 0]), __uint_as_float(dv[c][4 * e4 + 1])),
                                          make_float2(-D.x, -D.y));
@@ -717,7 +728,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tmem_st32(t_dp, dd);
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4)  // 16-byte chunk q4 = queries 8 q4 .. 8 q4 + 7, XOR-swizzled with (row & 7)
-        *reinterpret_cast<uint4*>(dsrow + ((q4 ^ (r & 7)) * 16)) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+        sts128(dsrow + ((q4 ^ (r & 7)) * 16), dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
       fence_proxy_async_smem();
       tmem_wait_st();
       tc_fence_before();
@@ -733,7 +744,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int r = int(lane_base) + lane;
     const uint32_t t_dq = tmem + (lane_base << 16) + kColBdQ;
     uint8_t* stage = sdQ + w4 * (32 * 128);  // this warp's 32 rows x 32 fp32
-    uint8_t* my_row = stage + lane * 128;
+    const uint32_t my_row = smem_u32(stage + lane * 128);
     // tile (b, h, i) = 2 halves x (128 rows x 32 floats); this warp owns rows [32 w4, 32 w4 + 32) of each half
     float* gdst = a.dq_accum + (int64_t(b) * a.H + h) * n_qt * (kBlockM * kHeadDim) + lane_base * 32;
     TL_DECL((warp == 8 && lane == 0) ? 3 : -1);
@@ -757,7 +768,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const uint32_t* v = half ? hi : lo;
-          *reinterpret_cast<uint4*>(my_row + ((e ^ (lane & 7)) * 16)) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          sts128(my_row + ((e ^ (lane & 7)) * 16), v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         }
         fence_proxy_async_smem();
         __syncwarp();

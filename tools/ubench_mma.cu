@@ -20,7 +20,8 @@ __device__ __forceinline__ uint64_t desc_mn2(uint32_t addr, uint32_t lbo) {
 
 // mode: 0 SS K-major N=128 | 1 SS K-major N=64 | 2 TS (A in TMEM) B MN-major N=64 | 3 SS A MN-major (2 panels) B MN-major N=64
 //       4 SS K-major N=256 | 5 TS B K-major N=128 | 6 SS K-major N=64 alternating two accumulators | 7 SS K-major N=32
-__global__ void __launch_bounds__(128) k_mma(int mode, int n, long long* out) {
+template <int mode>
+__global__ void __launch_bounds__(128) k_mma(int n, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -48,17 +49,18 @@ __global__ void __launch_bounds__(128) k_mma(int mode, int n, long long* out) {
       __syncwarp();
       t0 = clock64();
       if (elect_one()) {
-        for (int i = 0; i < n; ++i) {
-          const int kk = i & 3;
-          switch (mode) {
-            case 0: mma_ss(tmem, dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 128, 0, 0), 1); break;
-            case 1: mma_ss(tmem, dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 64, 0, 0), 1); break;
-            case 2: mma_ts(tmem + 256, tmem + kk * 8, dB + kk * 128, make_idesc_bf16(128, 64, 0, 1), 1); break;
-            case 3: mma_ss(tmem, dAmn + kk * 128, dB + kk * 128, make_idesc_bf16(128, 64, 1, 1), 1); break;
-            case 4: mma_ss(tmem, dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 256, 0, 0), 1); break;
-            case 5: mma_ts(tmem + 256, tmem + kk * 8, dB + kk * 2, make_idesc_bf16(128, 128, 0, 0), 1); break;
-            case 6: mma_ss(tmem + (i & 4 ? 64 : 0), dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 64, 0, 0), 1); break;
-            default: mma_ss(tmem, dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 32, 0, 0), 1); break;
+        for (int i = 0; i < n; i += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int kk = u & 3;
+            if (mode == 0) mma_ss(tmem, dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 128, 0, 0), 1);
+            if (mode == 1) mma_ss(tmem, dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 64, 0, 0), 1);
+            if (mode == 2) mma_ts(tmem + 256, tmem + kk * 8, dB + kk * 128, make_idesc_bf16(128, 64, 0, 1), 1);
+            if (mode == 3) mma_ss(tmem, dAmn + kk * 128, dB + kk * 128, make_idesc_bf16(128, 64, 1, 1), 1);
+            if (mode == 4) mma_ss(tmem, dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 256, 0, 0), 1);
+            if (mode == 5) mma_ts(tmem + 256, tmem + kk * 8, dB + kk * 2, make_idesc_bf16(128, 128, 0, 0), 1);
+            if (mode == 6) mma_ss(tmem + (u & 4 ? 64 : 0), dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 64, 0, 0), 1);
+            if (mode == 7) mma_ss(tmem, dA + kk * 2, dB + kk * 2, make_idesc_bf16(128, 32, 0, 0), 1);
           }
         }
         tc_commit(&bar);
@@ -77,13 +79,29 @@ __global__ void __launch_bounds__(128) k_mma(int mode, int n, long long* out) {
 int main() {
   long long* out;
   cudaMalloc(&out, 148 * sizeof(long long));
-  cudaFuncSetAttribute(k_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_mma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_mma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_mma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_mma<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const char* names[] = {"SS K-major N=128", "SS K-major N=64", "TS B MN-major N=64", "SS A MN-major(2 panels) B MN-major N=64",
                          "SS K-major N=256", "TS B K-major N=128", "SS K-major N=64, two accumulators", "SS K-major N=32"};
-  for (int grid : {1, 148}) {
+  for (int grid : {1}) {
     for (int mode = 0; mode < 8; ++mode) {
       for (int n : {32, 256}) {
-        k_mma<<<grid, 128, 100 * 1024>>>(mode, n, out);
+        switch (mode) {
+          case 0: k_mma<0><<<grid, 128, 100 * 1024>>>(n, out); break;
+          case 1: k_mma<1><<<grid, 128, 100 * 1024>>>(n, out); break;
+          case 2: k_mma<2><<<grid, 128, 100 * 1024>>>(n, out); break;
+          case 3: k_mma<3><<<grid, 128, 100 * 1024>>>(n, out); break;
+          case 4: k_mma<4><<<grid, 128, 100 * 1024>>>(n, out); break;
+          case 5: k_mma<5><<<grid, 128, 100 * 1024>>>(n, out); break;
+          case 6: k_mma<6><<<grid, 128, 100 * 1024>>>(n, out); break;
+          default: k_mma<7><<<grid, 128, 100 * 1024>>>(n, out); break;
+        }
         cudaError_t e = cudaDeviceSynchronize();
         long long h[148];
         cudaMemcpy(h, out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
