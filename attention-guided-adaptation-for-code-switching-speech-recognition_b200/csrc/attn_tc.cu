@@ -31,7 +31,35 @@ __device__ long long* g_timeline = nullptr;
 extern "C" __attribute__((visibility("default"))) int aga_debug_set_timeline(long long* p) {
   return cudaMemcpyToSymbol(g_timeline, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
 }
+// Per-CTA log: (clock64, globaltimer) at entry and exit plus the SM id, 8 slots per CTA.
+__device__ long long* g_cta_log = nullptr;
+extern "C" __attribute__((visibility("default"))) int aga_debug_set_cta_log(long long* p) {
+  return cudaMemcpyToSymbol(g_cta_log, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void cta_log(int slot) {
+  if (g_cta_log && threadIdx.x == 0) {
+    long long* rec = g_cta_log + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    rec[slot * 2] = clock64();
+    rec[slot * 2 + 1] = global_timer_ns();
+    rec[4] = smid;
+  }
+}
+__device__ __forceinline__ void cta_mark(int idx) {  // extra clock marks: rec[5] main loop entered, rec[6] main loop left
+  if (g_cta_log && threadIdx.x == 0)
+    g_cta_log[((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + idx] = clock64();
+}
+#define CTA_LOG(slot) cta_log(slot)
+#define CTA_MARK(idx) cta_mark(idx)
 #else
+#define CTA_LOG(slot) do { } while (0)
+#define CTA_MARK(idx) do { } while (0)
 #define TL_DECL(role) do { } while (0)
 #define TL(tag) do { } while (0)
 #define TL_END() do { } while (0)
@@ -47,12 +75,21 @@ constexpr int kBlockN = 128;  // keys per K/V tile
 constexpr int kHeadDim = 64;
 constexpr int kStages = 3;
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 16 KiB
-constexpr int kNumSoftmaxWarps = 8;
-constexpr int kTmaWarp = 8;
-constexpr int kMmaWarp = 9;   // warps 9 and 10: one MMA-issuing warp per query tile
-constexpr int kThreads = 352;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
+// Forward CTA shapes.  NT = query tiles (of 128 rows) per CTA:
+//   NT = 2: two softmax warpgroups share every K/V tile (half the L2 -> smem traffic), one CTA per SM, all 512 TMEM columns;
+//   NT = 1: 192 threads, 256 TMEM columns, 97 KiB of smem -> TWO CTAs per SM, whose prologues / epilogues and
+//           non-MUFU phases overlap with the other CTA's exponentials without any cross-warpgroup protocol.
+template <int NT> struct FwdCfg {
+  static constexpr int kSoftmaxWarps = 4 * NT;
+  static constexpr int kTmaWarp = 4 * NT;
+  static constexpr int kMmaWarp = 4 * NT + 1;  // NT warps: one MMA-issuing warp per query tile
+  static constexpr int kThreads = 32 * (4 * NT + 1 + NT);
+  static constexpr uint32_t kCols = 256 * NT;
+  static constexpr uint32_t kColS = 0, kColO = 128 * NT, kColP = 192 * NT;
+  static constexpr int kStages = NT == 1 ? 2 : 3;  // K/V ring depth (an iteration is several TMA latencies long)
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(NT + 2 * kStages) * kTileBytes + 256 /*FwdSmem*/;
+};
 constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
@@ -64,7 +101,7 @@ struct FwdSmem {
   uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2];
   uint32_t tmem_base;
 };
-constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + size_t(2 + 2 * kStages) * kTileBytes + sizeof(FwdSmem);
+static_assert(sizeof(FwdSmem) <= 256, "FwdCfg::kSmemBytes reserves 256 bytes for the barrier block");
 
 struct FwdArgs {
   int B, H, Tq, Tk;
@@ -73,21 +110,26 @@ struct FwdArgs {
   float* lse;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NT>
+__global__ void __launch_bounds__(FwdCfg<NT>::kThreads, NT == 1 ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                               // 2 tiles
-  uint8_t* sK = sQ + 2 * kTileBytes;                // kStages tiles
+  using Cfg = FwdCfg<NT>;
+  constexpr int kTmaWarp = Cfg::kTmaWarp, kMmaWarp = Cfg::kMmaWarp, kStages = Cfg::kStages;
+  constexpr uint32_t kColS = Cfg::kColS, kColO = Cfg::kColO, kColP = Cfg::kColP;
+  uint8_t* sQ = smem;                               // NT tiles
+  uint8_t* sK = sQ + NT * kTileBytes;               // kStages tiles
   uint8_t* sV = sK + kStages * kTileBytes;          // kStages tiles
   FwdSmem* sb = reinterpret_cast<FwdSmem*>(sV + kStages * kTileBytes);
 
+  CTA_LOG(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int row0 = qt * 2 * kBlockM;
+  const int row0 = qt * NT * kBlockM;
   const int n_kt = (a.Tk + kBlockN - 1) / kBlockN;
-  const bool active_b = row0 + kBlockM < a.Tq;  // tile B holds at least one valid row
+  const bool active_b = NT == 2 && row0 + kBlockM < a.Tq;  // tile B exists and holds at least one valid row
 
   if (threadIdx.x == 0) {
     mbar_init(&sb->q_full, 1);
@@ -106,7 +148,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(&sb->tmem_base, kTmemCols);
+    tmem_alloc(&sb->tmem_base, Cfg::kCols);
     tmem_relinquish();
   }
   if (warp == kTmaWarp && lane == 0) {
@@ -141,7 +183,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tma_load_4d(sV + s * kTileBytes, &map_v, &sb->v_full[s], 0, h, j * kBlockN, b);
       }
     }
-  } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+  } else if (warp >= kMmaWarp) {
     // ============================== MMA issuers: one converged warp per query tile, elected lane issues ==========
     // (a single issuing thread for both tiles serialises ~6 barrier waits + 24 MMAs per key tile and becomes the
     //  critical path; with one warp per tile the two in-order streams interleave on the tensor pipe)
@@ -272,6 +314,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           }
         }
         // ---- P = exp2(S*c - m) -> bf16 pairs -> its own TMEM columns (packed f32x2 FMA / ADD halve the issue slots)
+        if (j == 0) CTA_MARK(5);
         float neg_m = -m_used;
         if (pingpong) neg_m = named_bar_sync_dep(2 + t, 256, neg_m);
         float2 rs = make_float2(0.f, 0.f);
@@ -299,6 +342,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0) mbar_arrive(&sb->p_ready[t]);
         TL(26);
       }
+      CTA_MARK(6);
       TL_END();
       // ---- epilogue: O / l -> bf16 -> global ; lse
       mbar_wait(&sb->pv_done[t], (n_kt - 1) & 1);
@@ -329,7 +373,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
+  CTA_LOG(1);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, Cfg::kCols);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -376,9 +421,15 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
   if ((st = make_map(&mk, p.k, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, kBlockN)) != AGA_OK) return st;
   if ((st = make_map(&mv, p.v, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, kBlockN)) != AGA_OK) return st;
   FwdArgs a{p.B, p.H, p.Tq, p.Tk, p.o_stride_b, p.o_stride_t, static_cast<__nv_bfloat16*>(p.out), p.lse};
-  AGA_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFwdSmemBytes)));
-  dim3 grid((p.Tq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
-  attn_fwd_tc_kernel<<<grid, kThreads, kFwdSmemBytes, s>>>(mq, mk, mv, a);
+#ifdef AGA_FWD_TWO_TILES  // one CTA per SM, two query tiles sharing each K/V tile
+  constexpr int NT = 2;
+#else                     // two independent single-tile CTAs per SM (measured faster: see DESIGN.md)
+  constexpr int NT = 1;
+#endif
+  AGA_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(FwdCfg<NT>::kSmemBytes)));
+  dim3 grid((p.Tq + NT * kBlockM - 1) / (NT * kBlockM), p.H, p.B);
+  attn_fwd_tc_kernel<NT><<<grid, FwdCfg<NT>::kThreads, FwdCfg<NT>::kSmemBytes, s>>>(mq, mk, mv, a);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }
@@ -399,13 +450,15 @@ namespace {
 // share each SM sub-partition, so their phase 1s are forced to ALTERNATE with a pair of named barriers: warpgroup 1
 // runs half a tile behind warpgroup 0 and every phase 1 has the MUFU to itself while the other warpgroup is in
 // phase 2.  lse / delta are per COLUMN here and are broadcast-read from small double-buffered smem tables.
-// 4 drain warps move dQ_i from TMEM into a swizzled fp32 staging buffer (two 64x32... halves of 32 columns) and add
+// 4 drain warps move dQ_i from TMEM into a swizzled fp32 staging buffer (one 32-column half at a time) and add
 // it to the global accumulator with cp.reduce.async.bulk; the accumulator is tile-major
 // (b, h, q-tile, column half, 128 rows, 32) so that every bulk reduction is contiguous.
 // Rows/keys past the tensor ends are zero-filled by TMA, which makes their contributions exactly zero.
-constexpr int kBwdThreads = 512;
-constexpr int kBwdTmaWarp = 12;
-constexpr int kBwdMmaWarp = 13;  // warps 13, 14: the S / dV / dP / dK streams of query halves 0, 1; warp 15: the dQ stream
+constexpr int kBwdThreads = 768;
+constexpr int kBwdSoftmaxWarps = 16;  // 2 halves x 2 column slices x 4 lane quadrants
+constexpr int kBwdDrainWarp0 = 16;    // 4 warps
+constexpr int kBwdTmaWarp = 20;
+constexpr int kBwdMmaWarp = 21;  // warps 21, 22: the S / dV / dP / dK streams of query halves 0, 1; warp 23: the dQ stream
 constexpr uint32_t kColBS = 0, kColBdP = 128, kColBdV = 256, kColBdK = 320, kColBdQ = 384;
 constexpr int kPanelBytes = kBlockM * 128;             // 128 rows x 64 bf16
 constexpr int kDqStageBytes = kBlockM * 32 * 4;        // one 32-column half of a dQ tile, fp32: 16 KiB
@@ -416,8 +469,7 @@ struct BwdSmem {
   uint64_t qdo_full[kBwdStages], qdo_empty[kBwdStages];
   uint64_t s_full[2], dp_full[2], p_ready[2], ds_ready[2], ds_free[2], dq_full, dq_empty, dv_init, dk_init;
   uint32_t tmem_base;
-  alignas(16) float lse2[2][2][64];   // [query half g][tile parity][query]
-  alignas(16) float delta[2][2][64];
+  alignas(16) float stats[kBwdStages][2][kBlockM];  // per stage: lse * log2(e) | delta of the 128 queries (bulk-copied with Q, dO)
 };
 // K, V | kBwdStages x (Q, dO) | 2 x dS^T (2 panels each) | dQ staging
 constexpr size_t kBwdSmemBytes = 1024 + size_t(2 + 2 * kBwdStages) * kTileBytes + 4 * size_t(kPanelBytes) + kDqStageBytes + sizeof(BwdSmem);
@@ -426,8 +478,7 @@ static_assert(kBwdSmemBytes <= 227 * 1024, "backward kernel exceeds the 227 KiB 
 struct BwdArgs {
   int B, H, Tq, Tk;
   int64_t k_sb, k_st, v_sb, v_st;
-  const float* lse;
-  const float* delta;
+  const float* stats;  // (B, H, ceil(Tq/128), 2, 128) fp32: lse * log2(e) | delta per query tile, zero past Tq
   float* dq_accum;  // (B, H, ceil(Tq/128), 2, 128, 32) fp32, zero-initialised, 16-byte chunks XOR-swizzled with (row & 7)
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
@@ -468,6 +519,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint8_t* sdQ = sdS + 4 * kPanelBytes;          // fp32 staging, 4 warps x (32 rows x 128 B)
   BwdSmem* sb = reinterpret_cast<BwdSmem*>(sdQ + kDqStageBytes);
 
+  CTA_LOG(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int key0 = kt * kBlockN;
@@ -482,8 +534,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int g = 0; g < 2; ++g) {
       mbar_init(&sb->s_full[g], 1);
       mbar_init(&sb->dp_full[g], 1);
-      mbar_init(&sb->p_ready[g], 4);   // one arrival per warp of the warpgroup
-      mbar_init(&sb->ds_ready[g], 4);
+      mbar_init(&sb->p_ready[g], 8);   // one arrival per warp of the half's two warpgroups
+      mbar_init(&sb->ds_ready[g], 8);
       mbar_init(&sb->ds_free[g], 1);   // indexed by dS^T buffer
     }
     mbar_init(&sb->dq_full, 1);
@@ -518,7 +570,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const uint32_t ph = (i / kBwdStages) & 1;
       mbar_wait(&sb->qdo_empty[s], ph ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&sb->qdo_full[s], 2 * kTileBytes);
+        mbar_arrive_expect_tx(&sb->qdo_full[s], 2 * kTileBytes + 2 * kBlockM * 4);
+        bulk_load(sb->stats[s], a.stats + ((int64_t(b) * a.H + h) * n_qt + i) * (2 * kBlockM), 2 * kBlockM * 4, &sb->qdo_full[s]);
         tma_load_4d(sQ + s * kTileBytes, &map_q, &sb->qdo_full[s], 0, h, i * kBlockM, b);
         tma_load_4d(sdO + s * kTileBytes, &map_do, &sb->qdo_full[s], 0, h, i * kBlockM, b);
       }
@@ -567,7 +620,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          mma_ts(tmem + kColBdV, t_sg + kk * 8, ddo_i + uint64_t(kk * 128), idesc_ts, (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
+          mma_ts(tmem + kColBdV, t_sg + (kk >> 1) * 32 + (kk & 1) * 8, ddo_i + uint64_t(kk * 128), idesc_ts,
+                 (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
         if (i == 0 && g == 0) tc_commit(&sb->dv_init);
         if (more) {
 #pragma unroll
@@ -585,7 +639,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          mma_ts(tmem + kColBdK, t_dpg + kk * 8, dq_i + uint64_t(kk * 128), idesc_ts, (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
+          mma_ts(tmem + kColBdK, t_dpg + (kk >> 1) * 32 + (kk & 1) * 8, dq_i + uint64_t(kk * 128), idesc_ts,
+                 (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
         if (i == 0 && g == 0) tc_commit(&sb->dk_init);
         tc_commit(&sb->qdo_empty[i % kBwdStages]);  // this half's last read of (Q_i, dO_i)
         if (more) {
@@ -619,78 +674,66 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       __syncwarp();
     }
-  } else if (warp < 8) {
-    // ============================== P^T / dS^T producers: warpgroup g owns query half g ==============================
-    const int g = warp >> 2;
+  } else if (warp < kBwdSoftmaxWarps) {
+    // ============================== P^T / dS^T producers ==============================
+    // Query half g (64 columns) is owned by two warpgroups: `sub` selects a 32-column slice, warp & 3 the lane quadrant.
+    // (A lone warp per SM sub-partition issues MUFU at about half the unit's rate; two co-resident warps saturate it.)
+    const int g = warp >> 3, sub = (warp >> 2) & 1;
     const uint32_t lane_base = uint32_t((warp & 3) * 32);
     const int r = int(lane_base) + lane;  // key row inside the tile
-    const uint32_t t_s = tmem + (lane_base << 16) + kColBS + g * 64;
-    const uint32_t t_dp = tmem + (lane_base << 16) + kColBdP + g * 64;
-    // per-query lse / delta tables of this half: thread wt < 64 owns lse[wt], the others delta[wt - 64]
-    const int wt = threadIdx.x & 127;
-    const bool is_lse = wt < 64;
-    const float* stat_src = (is_lse ? a.lse : a.delta) + (int64_t(b) * a.H + h) * a.Tq;
-    const float stat_mul = is_lse ? 1.4426950408889634f : 1.0f;
-    const int stat_col = wt & 63;
-    auto stat_slot = [&](int buf) { return smem_u32((is_lse ? sb->lse2[g][buf] : sb->delta[g][buf]) + stat_col); };
-    auto stat_load = [&](int i) {  // raw value: the scaling happens when it is stored, a tile later (no stall on the load)
-      const int row = i * kBlockM + g * 64 + stat_col;
-      return (i < n_qt && row < a.Tq) ? stat_src[row] : 0.f;
-    };
-    sts32f(stat_slot(0), stat_load(0) * stat_mul);
-    float stat_next = stat_load(1);
-    const uint32_t lse_tab = smem_u32(sb->lse2[g][0]), del_tab = smem_u32(sb->delta[g][0]);  // [parity][64] floats
+    // S^T / dP^T columns of this slice; the bf16 pairs (16 columns) are written over the slice's own first 16 columns
+    const uint32_t t_s = tmem + (lane_base << 16) + kColBS + g * 64 + sub * 32;
+    const uint32_t t_dp = tmem + (lane_base << 16) + kColBdP + g * 64 + sub * 32;
+    const uint32_t stats0 = smem_u32(sb->stats[0][0]) + (g * 64 + sub * 32) * 4;  // this slice's 32 queries of stage 0's lse row
     const uint32_t ds_base = smem_u32(sdS + g * kPanelBytes + r * 128);
 #ifndef AGA_BWD_NO_TOKEN
-    if (g == 1) named_bar_arrive(4, 256);  // warpgroup 0 may run the first phase 1
+    if (g == 1) named_bar_arrive(4, 512);  // half 0 may run the first phase 1
 #endif
-    TL_DECL(((warp & 3) == 0 && lane == 0) ? 1 + g : -1);
+    TL_DECL(((warp & 7) == 0 && lane == 0) ? 1 + g : -1);
     for (int i = 0; i < n_qt; ++i) {
       const uint32_t par = i & 1;
       TL(20);
-      named_bar_sync(2 + g, 128);  // table `par` complete; the warpgroup is done with table `par ^ 1`
-      sts32f(stat_slot(par ^ 1), stat_next * stat_mul);
-      stat_next = stat_load(i + 2);
-      const uint32_t lse4 = lse_tab + par * 256, del4 = del_tab + par * 256;
+      const int stage = i % kBwdStages;
+      const uint32_t lse4 = stats0 + stage * (2 * kBlockM * 4), del4 = lse4 + kBlockM * 4;
+      mbar_wait(&sb->qdo_full[stage], (i / kBwdStages) & 1);  // the tile's lse / delta rows have landed (long ago)
+      TL(26);
       mbar_wait(&sb->s_full[g], par);
       TL(21);
       tc_fence_after();
-      uint32_t pk[32];
+      uint32_t pk[16];
       {
-        uint32_t sv[2][32];
-        tmem_ld32(t_s, sv[0]);
-        tmem_ld32(t_s + 32, sv[1]);
+        uint32_t sv[32];
+        tmem_ld32(t_s, sv);
         tmem_wait_ld();
-        // ---- phase 1 (MUFU): wait for the other warpgroup to leave its phase 1
+        // ---- phase 1 (MUFU): wait for the other half to leave its phase 1
 #ifndef AGA_BWD_NO_TOKEN
-        const float sc = named_bar_sync_dep(4 + g, 256, kScaleLog2);
+        const float sc = named_bar_sync_dep(4 + g, 512, kScaleLog2);
 #else
         const float sc = kScaleLog2;
 #endif
         TL(22);
+        if (i == 0) CTA_MARK(5);
         const float2 sc2 = make_float2(sc, sc);
         float chk = 0.f;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 L = lds128f(lse4 + (c * 8 + e4) * 16);
-            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sv[c][4 * e4 + 0]), __uint_as_float(sv[c][4 * e4 + 1])), sc2,
-                                         make_float2(-L.x, -L.y));
-            const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sv[c][4 * e4 + 2]), __uint_as_float(sv[c][4 * e4 + 3])), sc2,
-                                         make_float2(-L.z, -L.w));
-            const float p0 = ex2(x0.x), p1 = ex2(x0.y), p2 = ex2(x1.x), p3 = ex2(x1.y);
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
-            pk[c * 16 + 2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
-            pk[c * 16 + 2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-            chk = __uint_as_float(pk[c * 16 + 2 * e4] ^ pk[c * 16 + 2 * e4 + 1] ^ __float_as_uint(chk));
-          }
-        // hand the MUFU to the other warpgroup (the value threaded through depends on every exponential above)
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 L = lds128f(lse4 + e4 * 16);
+          const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sv[4 * e4 + 0]), __uint_as_float(sv[4 * e4 + 1])), sc2,
+                                       make_float2(-L.x, -L.y));
+          const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sv[4 * e4 + 2]), __uint_as_float(sv[4 * e4 + 3])), sc2,
+                                       make_float2(-L.z, -L.w));
+          const float p0 = ex2(x0.x), p1 = ex2(x0.y), p2 = ex2(x1.x), p3 = ex2(x1.y);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
+          pk[2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          chk = __uint_as_float(pk[2 * e4] ^ pk[2 * e4 + 1] ^ __float_as_uint(chk));
+        }
+        // hand the MUFU to the other half (the value threaded through depends on every exponential above)
 #ifndef AGA_BWD_NO_TOKEN
-        if (!(g == 1 && i == n_qt - 1)) pk[31] ^= __float_as_uint(named_bar_arrive_dep(5 - g, 256, chk)) ^ __float_as_uint(chk);
+        if (!(g == 1 && i == n_qt - 1)) pk[15] ^= __float_as_uint(named_bar_arrive_dep(5 - g, 512, chk)) ^ __float_as_uint(chk);
 #endif
       }
-      tmem_st32(t_s, pk);  // 64 queries as bf16 pairs over the first 32 of this half's S^T columns
+      tmem_st16(t_s, pk);  // 32 queries as bf16 pairs over the first 16 of this slice's S^T columns
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -702,33 +745,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (i >= 2) mbar_wait(&sb->ds_free[par], ((i >> 1) - 1) & 1);  // dQ(i-2) has consumed this dS^T buffer
       TL(24);
       tc_fence_after();
-      uint32_t dd[32];
+      uint32_t dd[16];
       {
-        uint32_t dv[2][32];
-        tmem_ld32(t_dp, dv[0]);
-        tmem_ld32(t_dp + 32, dv[1]);
+        uint32_t dv[32];
+        tmem_ld32(t_dp, dv);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 D = lds128f(del4 + (c * 8 + e4) * 16);
-            const uint32_t w0 = pk[c * 16 + 2 * e4], w1 = pk[c * 16 + 2 * e4 + 1];
-            const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(dv[c][4 * e4 + 0]), __uint_as_float(dv[c][4 * e4 + 1])),
-                                         make_float2(-D.x, -D.y));
-            const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(dv[c][4 * e4 + 2]), __uint_as_float(dv[c][4 * e4 + 3])),
-                                         make_float2(-D.z, -D.w));
-            const float2 d0 = __fmul2_rn(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), a0);
-            const float2 d1 = __fmul2_rn(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), a1);
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(d0.x, d0.y), h1 = __floats2bfloat162_rn(d1.x, d1.y);
-            dd[c * 16 + 2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
-            dd[c * 16 + 2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-          }
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 D = lds128f(del4 + e4 * 16);
+          const uint32_t w0 = pk[2 * e4], w1 = pk[2 * e4 + 1];
+          const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(dv[4 * e4 + 0]), __uint_as_float(dv[4 * e4 + 1])),
+                                       make_float2(-D.x, -D.y));
+          const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(dv[4 * e4 + 2]), __uint_as_float(dv[4 * e4 + 3])),
+                                       make_float2(-D.z, -D.w));
+          const float2 d0 = __fmul2_rn(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), a0);
+          const float2 d1 = __fmul2_rn(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), a1);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(d0.x, d0.y), h1 = __floats2bfloat162_rn(d1.x, d1.y);
+          dd[2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
+          dd[2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
       }
-      tmem_st32(t_dp, dd);
+      tmem_st16(t_dp, dd);
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4)  // 16-byte chunk q4 = queries 8 q4 .. 8 q4 + 7, XOR-swizzled with (row & 7)
-        sts128(dsrow + ((q4 ^ (r & 7)) * 16), dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+      for (int q4 = 0; q4 < 4; ++q4)  // 16-byte chunk sub*4 + q4 = queries 32 sub + 8 q4 .. + 7, XOR-swizzled with (row & 7)
+        sts128(dsrow + (((sub * 4 + q4) ^ (r & 7)) * 16), dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
       fence_proxy_async_smem();
       tmem_wait_st();
       tc_fence_before();
@@ -736,7 +776,36 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (lane == 0) mbar_arrive(&sb->ds_ready[g]);
       TL(25);
     }
+    CTA_MARK(6);
     TL_END();
+    // ---- dK_j / dV_j: final once both halves' last dK MMAs have completed (their commits on the last (Q, dO) stage);
+    //      the 16 softmax warps store one 32-column chunk each while the drain warps finish the last dQ tile
+    mbar_wait(&sb->qdo_empty[(n_qt - 1) % kBwdStages], ((n_qt - 1) / kBwdStages) & 1);
+    tc_fence_after();
+    {
+      const int chunk = g * 2 + sub;  // 0, 1: dV columns 0-31, 32-63;  2, 3: dK
+      const bool is_dk = chunk >= 2;
+      const int key = key0 + r;
+      uint32_t v[32];
+      tmem_ld32(tmem + (lane_base << 16) + (is_dk ? kColBdK : kColBdV) + (chunk & 1) * 32, v);
+      tmem_wait_ld();
+      if (key < a.Tk) {
+        const float scale = is_dk ? 0.125f : 1.0f;
+        __nv_bfloat16* dst = (is_dk ? a.dk + int64_t(b) * a.k_sb + int64_t(key) * a.k_st
+                                    : a.dv + int64_t(b) * a.v_sb + int64_t(key) * a.v_st) + h * kHeadDim + (chunk & 1) * 32;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * q4 + 2 * e]) * scale,
+                                                      __uint_as_float(v[8 * q4 + 2 * e + 1]) * scale);
+            w[e] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+          *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
   } else if (warp < kBwdTmaWarp) {
     // ============================== dQ drain, then dK / dV store ==============================
     const int w4 = warp & 3;
@@ -747,7 +816,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t my_row = smem_u32(stage + lane * 128);
     // tile (b, h, i) = 2 halves x (128 rows x 32 floats); this warp owns rows [32 w4, 32 w4 + 32) of each half
     float* gdst = a.dq_accum + (int64_t(b) * a.H + h) * n_qt * (kBlockM * kHeadDim) + lane_base * 32;
-    TL_DECL((warp == 8 && lane == 0) ? 3 : -1);
+    TL_DECL((warp == kBwdDrainWarp0 && lane == 0) ? 3 : -1);
     for (int i = 0; i < n_qt; ++i) {
       TL(30);
       mbar_wait(&sb->dq_full, i & 1);
@@ -778,54 +847,51 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       TL(32);
     }
-    if (lane == 0) bulk_wait0();
+    if (lane == 0) bulk_wait_read0();  // the staging rows must outlive the last bulk reduction's reads; the adds themselves
+                                       // complete asynchronously (kernel completion orders them before the convert kernel)
     TL(33);
     TL_END();
-    // all MMAs of the last tile are complete once dq_full(n_qt-1) fired (commit covers every earlier op)
-    const int key = key0 + r;
-    auto store_rows = [&](uint32_t col, __nv_bfloat16* base, int64_t sb_, int64_t st_, float scale) {
-      __nv_bfloat16* dst = base + int64_t(b) * sb_ + int64_t(key) * st_ + h * kHeadDim;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem + (lane_base << 16) + col + c * 32, v);
-        tmem_wait_ld();
-        if (key < a.Tk) {
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * q4 + 2 * e]) * scale,
-                                                        __uint_as_float(v[8 * q4 + 2 * e + 1]) * scale);
-              w[e] = *reinterpret_cast<uint32_t*>(&hb);
-            }
-            *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
-      }
-    };
-    store_rows(kColBdV, a.dv, a.v_sb, a.v_st, 1.0f);
-    store_rows(kColBdK, a.dk, a.k_sb, a.k_st, 0.125f);
   }
   tc_fence_before();
   __syncthreads();
+  CTA_LOG(1);
   if (warp == kBwdMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
-// delta[b,h,t] = sum_c dO[b,t,h,c] * O[b,t,h,c]   (one warp per row)
+// Per-query statistics of the backward, laid out per 128-row query tile so that one 1 KiB bulk copy brings a tile's
+// rows into shared memory:  stats[b,h,tile] = { lse[t] * log2(e) : 128 } { delta[t] = sum_c dO[b,t,h,c] * O[b,t,h,c] : 128 },
+// zero for rows past Tq.  8 lanes per row, 16-byte loads.
 __global__ void __launch_bounds__(256)
-attn_bwd_delta_bf16_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int64_t o_sb,
-                           int64_t o_st, int B, int H, int Tq, float* __restrict__ delta) {
-  const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= int64_t(B) * H * Tq) return;
-  const int t = int(w % Tq), h = int((w / Tq) % H), b = int(w / (int64_t(Tq) * H));
-  const int64_t off = b * o_sb + int64_t(t) * o_st + h * kHeadDim + lane * 2;
-  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
-  const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_o + off));
-  const float acc = warp_sum(x.x * y.x + x.y * y.y);
-  if (lane == 0) delta[w] = acc;
+attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int64_t o_sb, int64_t o_st,
+                      const float* __restrict__ lse, int B, int H, int Tq, int n_qt, float* __restrict__ stats) {
+  const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t row_id = gid >> 3;  // (b, h, padded t)
+  const int sub = int(gid & 7);
+  const int Tp = n_qt * kBlockM;
+  if (row_id >= int64_t(B) * H * Tp) return;
+  const int t = int(row_id % Tp), h = int((row_id / Tp) % H), b = int(row_id / (int64_t(Tp) * H));
+  float acc = 0.f, l2 = 0.f;
+  if (t < Tq) {
+    const int64_t off = b * o_sb + int64_t(t) * o_st + h * kHeadDim + sub * 8;
+    const uint4 x = *reinterpret_cast<const uint4*>(o + off);
+    const uint4 y = *reinterpret_cast<const uint4*>(d_o + off);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[e]));
+      const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[e]));
+      acc = fmaf(xf.x, yf.x, fmaf(xf.y, yf.y, acc));
+    }
+    l2 = lse[(int64_t(b) * H + h) * Tq + t] * 1.4426950408889634f;
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub == 0) {
+    float* dst = stats + ((int64_t(b) * H + h) * n_qt + (t >> 7)) * (2 * kBlockM) + (t & 127);
+    dst[0] = l2;
+    dst[kBlockM] = acc;
+  }
 }
 
 // dq = bf16(0.125 * dq_accum): un-tiles / un-swizzles the (b, h, q-tile, 128, 64) fp32 accumulator; 8 columns per thread
@@ -861,23 +927,24 @@ attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restr
 bool attn_tc_bwd_supported(const aga_attn_params& p) { return attn_tc_supported(p); }
 
 size_t attn_tc_bwd_workspace(const aga_attn_params& p) {
-  const size_t delta = align_up(size_t(p.B) * p.H * p.Tq * sizeof(float), 256);
   const size_t n_qt = size_t(p.Tq + kBlockM - 1) / kBlockM;
+  const size_t stats = align_up(size_t(p.B) * p.H * n_qt * 2 * kBlockM * sizeof(float), 256);
   const size_t dq = align_up(size_t(p.B) * p.H * n_qt * kBlockM * kHeadDim * sizeof(float), 256);
-  return delta + dq;
+  return stats + dq;
 }
 
 int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
   const aga_attn_params& p = bp.fwd;
-  float* delta = static_cast<float*>(ws);
-  float* dq_acc = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + align_up(size_t(p.B) * p.H * p.Tq * sizeof(float), 256));
   const int n_qt = (p.Tq + kBlockM - 1) / kBlockM;
+  float* stats = static_cast<float*>(ws);
+  float* dq_acc = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) +
+                                           align_up(size_t(p.B) * p.H * n_qt * 2 * kBlockM * sizeof(float), 256));
   const size_t dq_bytes = size_t(p.B) * p.H * n_qt * kBlockM * kHeadDim * sizeof(float);
   AGA_CUDA_TRY(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
-  const int64_t rows = int64_t(p.B) * p.H * p.Tq;
-  attn_bwd_delta_bf16_kernel<<<unsigned((rows * 32 + 255) / 256), 256, 0, s>>>(
+  const int64_t stat_threads = int64_t(p.B) * p.H * n_qt * kBlockM * 8;
+  attn_bwd_stats_kernel<<<unsigned((stat_threads + 255) / 256), 256, 0, s>>>(
       static_cast<const __nv_bfloat16*>(p.out), static_cast<const __nv_bfloat16*>(bp.dout), p.o_stride_b, p.o_stride_t,
-      p.B, p.H, p.Tq, delta);
+      p.lse, p.B, p.H, p.Tq, n_qt, stats);
   AGA_AFTER_LAUNCH();
   CUtensorMap mq, mk, mv, mdo;
   int st;
@@ -885,7 +952,7 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
   if ((st = make_map(&mk, p.k, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, kBlockN)) != AGA_OK) return st;
   if ((st = make_map(&mv, p.v, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, kBlockN)) != AGA_OK) return st;
   if ((st = make_map(&mdo, bp.dout, p.B, p.H, p.Tq, p.o_stride_b, p.o_stride_t, kBlockM)) != AGA_OK) return st;
-  BwdArgs a{p.B, p.H, p.Tq, p.Tk, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, p.lse, delta, dq_acc,
+  BwdArgs a{p.B, p.H, p.Tq, p.Tk, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, stats, dq_acc,
             static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv)};
   AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBwdSmemBytes)));
   dim3 grid((p.Tk + kBlockN - 1) / kBlockN, p.H, p.B);

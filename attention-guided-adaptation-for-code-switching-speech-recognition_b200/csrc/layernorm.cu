@@ -46,11 +46,17 @@ template <> struct Vec4<__nv_bfloat16> {
 };
 
 // lane l owns columns {128*c + 4*l .. +3 : c < NC}
+template <typename T> __device__ __forceinline__ float round_to(float v);
+template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// residual != nullptr: normalises s = T(x + residual) (the sum is rounded to the row dtype first, as the reference's
+// `x + self.model(x)` is) and, when sum_out != nullptr, also writes s — the tensor the backward needs.
 template <typename T, int NC>
 __global__ void __launch_bounds__(kLnWarps * 32)
-layernorm_fwd_kernel(const T* __restrict__ x, int64_t rows, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float eps, T* __restrict__ y, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out) {
+layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, int64_t rows, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, T* __restrict__ y, T* __restrict__ sum_out,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   constexpr int D = NC * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
@@ -61,6 +67,13 @@ layernorm_fwd_kernel(const T* __restrict__ x, int64_t rows, const float* __restr
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     Vec4<T>::load(xr + c * 128 + lane * 4, v[c]);
+    if (residual) {
+      float rv[4];
+      Vec4<T>::load(residual + row * D + c * 128 + lane * 4, rv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[c][e] = round_to<T>(v[c][e] + rv[e]);
+      if (sum_out) Vec4<T>::store(sum_out + row * D + c * 128 + lane * 4, v[c]);
+    }
     sum += (v[c][0] + v[c][1]) + (v[c][2] + v[c][3]);
   }
   const float mean = warp_sum(sum) * (1.0f / D);
@@ -91,11 +104,13 @@ layernorm_fwd_kernel(const T* __restrict__ x, int64_t rows, const float* __restr
   }
 }
 
-template <typename T, int NC, bool kParamGrads>
+// kParamGrads == 2 additionally accumulates dxsum[c] = sum_rows dx[row, c]: when the normalised tensor is
+// x + Linear(...)(x), that column sum IS the gradient of the Linear's bias (saves a separate reduction pass).
+template <typename T, int NC, int kParamGrads>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t rows, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int D = NC * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[NC][4];
@@ -104,12 +119,18 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t 
     const float4 t = __ldg(reinterpret_cast<const float4*>(gamma + c * 128 + lane * 4));
     g[c][0] = t.x; g[c][1] = t.y; g[c][2] = t.z; g[c][3] = t.w;
   }
-  float ag[NC][4], ab[NC][4];
+  float ag[NC][4], ab[NC][4], ax[kParamGrads == 2 ? NC : 1][4];
   if (kParamGrads) {
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
       for (int e = 0; e < 4; ++e) ag[c][e] = ab[c][e] = 0.f;
+  }
+  if (kParamGrads == 2) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ax[c][e] = 0.f;
   }
   const int64_t stride = int64_t(gridDim.x) * kLnWarps;
   for (int64_t row = int64_t(blockIdx.x) * kLnWarps + warp; row < rows; row += stride) {
@@ -138,25 +159,29 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t 
     for (int c = 0; c < NC; ++c) {
       float o[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = rs * (gy[c][e] - c1 - xh[c][e] * c2);
+      for (int e = 0; e < 4; ++e) {
+        o[e] = rs * (gy[c][e] - c1 - xh[c][e] * c2);
+        if (kParamGrads == 2) ax[c][e] += o[e];
+      }
       Vec4<T>::store(dx + row * D + c * 128 + lane * 4, o);
     }
   }
   if (kParamGrads) {
     __shared__ float red[kLnWarps][128];
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll 1
+    for (int pass = 0; pass < (kParamGrads == 2 ? 3 : 2); ++pass) {
+#pragma unroll
       for (int c = 0; c < NC; ++c) {
         __syncthreads();
 #pragma unroll
-        for (int e = 0; e < 4; ++e) red[warp][lane * 4 + e] = pass == 0 ? ag[c][e] : ab[c][e];
+        for (int e = 0; e < 4; ++e)
+          red[warp][lane * 4 + e] = pass == 0 ? ag[c][e] : (pass == 1 ? ab[c][e] : ax[kParamGrads == 2 ? c : 0][e]);
         __syncthreads();
         if (threadIdx.x < 128) {
           float t = 0.f;
 #pragma unroll
           for (int w = 0; w < kLnWarps; ++w) t += red[w][threadIdx.x];
-          atomicAdd((pass == 0 ? dgamma : dbeta) + c * 128 + threadIdx.x, t);
+          atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum)) + c * 128 + threadIdx.x, t);
         }
       }
     }
@@ -164,28 +189,35 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t 
 }
 
 template <typename T, int NC>
-int launch_fwd(const void* x, int64_t rows, const float* gamma, const float* beta, float eps, void* y, float* mean,
-               float* rstd, cudaStream_t s) {
+int launch_fwd(const void* x, const void* residual, int64_t rows, const float* gamma, const float* beta, float eps, void* y,
+               void* sum_out, float* mean, float* rstd, cudaStream_t s) {
   const unsigned grid = unsigned((rows + kLnWarps - 1) / kLnWarps);
-  layernorm_fwd_kernel<T, NC><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(x), rows, gamma, beta, eps,
-                                                              static_cast<T*>(y), mean, rstd);
+  layernorm_fwd_kernel<T, NC><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(residual), rows,
+                                                              gamma, beta, eps, static_cast<T*>(y), static_cast<T*>(sum_out),
+                                                              mean, rstd);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }
 
 template <typename T, int NC>
 int launch_bwd(const void* dy, const void* x, int64_t rows, const float* gamma, const float* mean, const float* rstd,
-               void* dx, float* dgamma, float* dbeta, cudaStream_t s) {
+               void* dx, float* dgamma, float* dbeta, float* dxsum, cudaStream_t s) {
   const int64_t want = (rows + kLnWarps - 1) / kLnWarps;
   const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 4)));
   if (dgamma && dbeta) {
     AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, NC * 128 * sizeof(float), s));
     AGA_CUDA_TRY(cudaMemsetAsync(dbeta, 0, NC * 128 * sizeof(float), s));
-    layernorm_bwd_kernel<T, NC, true><<<grid, kLnWarps * 32, 0, s>>>(
-        static_cast<const T*>(dy), static_cast<const T*>(x), rows, gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta);
+    if (dxsum) {
+      AGA_CUDA_TRY(cudaMemsetAsync(dxsum, 0, NC * 128 * sizeof(float), s));
+      layernorm_bwd_kernel<T, NC, 2><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
+                                                                     gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta, dxsum);
+    } else {
+      layernorm_bwd_kernel<T, NC, 1><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
+                                                                     gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta, nullptr);
+    }
   } else {
-    layernorm_bwd_kernel<T, NC, false><<<grid, kLnWarps * 32, 0, s>>>(
-        static_cast<const T*>(dy), static_cast<const T*>(x), rows, gamma, mean, rstd, static_cast<T*>(dx), nullptr, nullptr);
+    layernorm_bwd_kernel<T, NC, 0><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows, gamma,
+                                                                   mean, rstd, static_cast<T*>(dx), nullptr, nullptr, nullptr);
   }
   AGA_AFTER_LAUNCH();
   return AGA_OK;
@@ -214,24 +246,27 @@ int check(const void* a, const void* b, int dtype, int64_t rows, int D) {
 
 using namespace aga;
 
-extern "C" int aga_layernorm_fwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* beta,
-                                 float eps, void* y, float* mean, float* rstd, void* stream) {
+extern "C" int aga_layernorm_fwd(const void* x, const void* residual, int dtype, int64_t rows, int D, const float* gamma,
+                                 const float* beta, float eps, void* y, void* sum_out, float* mean, float* rstd,
+                                 void* stream) {
   int st = check(x, y, dtype, rows, D);
   if (st != AGA_OK) return st;
-  if (!gamma || !beta || !mean || !rstd) return AGA_ERR_INVALID_ARGUMENT;
+  if (!gamma || !beta || !mean || !rstd || (sum_out && !residual)) return AGA_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(sum_out)) & 15) return AGA_ERR_UNSUPPORTED;
   const bool bf16 = dtype == AGA_BF16;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  AGA_LN_DISPATCH(launch_fwd, x, rows, gamma, beta, eps, y, mean, rstd, s)
+  AGA_LN_DISPATCH(launch_fwd, x, residual, rows, gamma, beta, eps, y, sum_out, mean, rstd, s)
 }
 
 extern "C" int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
                                  const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                                 void* stream) {
+                                 float* dxsum, void* stream) {
   int st = check(x, dx, dtype, rows, D);
   if (st != AGA_OK) return st;
-  if (!dy || !gamma || !mean || !rstd || ((dgamma == nullptr) != (dbeta == nullptr))) return AGA_ERR_INVALID_ARGUMENT;
+  if (!dy || !gamma || !mean || !rstd || ((dgamma == nullptr) != (dbeta == nullptr)) || (dxsum && !dgamma))
+    return AGA_ERR_INVALID_ARGUMENT;
   if (reinterpret_cast<uintptr_t>(dy) & 15) return AGA_ERR_UNSUPPORTED;
   const bool bf16 = dtype == AGA_BF16;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  AGA_LN_DISPATCH(launch_bwd, dy, x, rows, gamma, mean, rstd, dx, dgamma, dbeta, s)
+  AGA_LN_DISPATCH(launch_bwd, dy, x, rows, gamma, mean, rstd, dx, dgamma, dbeta, dxsum, s)
 }

@@ -299,6 +299,39 @@ def qkv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int
 # ------------------------------------------------------------------------------------------------
 # 8f #2. LayerNorm with fp32 statistics (whisper/model.py:30-32)
 # ------------------------------------------------------------------------------------------------
+def _rows(t: torch.Tensor, D: int) -> torch.Tensor:
+    t2 = t.reshape(-1, D)
+    return t2 if (t2.is_contiguous() and t2.data_ptr() % 16 == 0) else t2.contiguous()
+
+
+def _ln_fwd(x2, residual2, w32, b32, eps, want_sum):
+    """x2 (rows, D) [+ residual2] -> (y, s, mean, rstd); s = x2 + residual2 in x2.dtype (or x2 itself)."""
+    rows, D = x2.shape
+    y = torch.empty_like(x2)
+    s = torch.empty_like(x2) if (residual2 is not None and want_sum) else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    tm = _Timed("layernorm_fwd", (2.0 + (residual2 is not None) + (s is not None)) * rows * D * x2.element_size(), x2.device)
+    L.check(L.lib().aga_layernorm_fwd(_ptr(x2), _ptr(residual2), _DTYPES[x2.dtype], rows, D, _ptr(w32), _ptr(b32), float(eps),
+                                      _ptr(y), _ptr(s), _ptr(mean), _ptr(rstd), _stream_ptr(x2.device)), "aga_layernorm_fwd")
+    tm.done(x2.device)
+    return y, (s if s is not None else x2), mean, rstd
+
+
+def _ln_bwd(dy2, s2, w32, mean, rstd, need_params, need_dxsum=False):
+    rows, D = s2.shape
+    dx = torch.empty_like(s2)
+    dgamma = torch.empty(D, dtype=torch.float32, device=s2.device) if need_params else None
+    dbeta = torch.empty(D, dtype=torch.float32, device=s2.device) if need_params else None
+    dxsum = torch.empty(D, dtype=torch.float32, device=s2.device) if (need_params and need_dxsum) else None
+    tm = _Timed("layernorm_bwd", 3.0 * rows * D * s2.element_size(), s2.device)
+    L.check(L.lib().aga_layernorm_bwd(_ptr(dy2), _ptr(s2), _DTYPES[s2.dtype], rows, D, _ptr(w32), _ptr(mean), _ptr(rstd),
+                                      _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), _stream_ptr(s2.device)),
+            "aga_layernorm_bwd")
+    tm.done(s2.device)
+    return dx, dgamma, dbeta, dxsum
+
+
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
@@ -306,19 +339,10 @@ class _LayerNormFn(torch.autograd.Function):
         if x.dtype not in _DTYPES:
             raise L.AgaError(f"layer_norm supports fp32 and bf16 rows, got {x.dtype}")
         D = x.shape[-1]
-        x2 = x.reshape(-1, D)
-        if not x2.is_contiguous() or x2.data_ptr() % 16:
-            x2 = x2.contiguous()
-        rows = x2.shape[0]
+        x2 = _rows(x, D)
         w32 = weight.detach().float().contiguous()
         b32 = bias.detach().float().contiguous()
-        y = torch.empty_like(x2)
-        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
-        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-        tm = _Timed("layernorm_fwd", 2.0 * rows * D * x2.element_size(), x.device)
-        L.check(L.lib().aga_layernorm_fwd(_ptr(x2), _DTYPES[x2.dtype], rows, D, _ptr(w32), _ptr(b32), float(eps), _ptr(y),
-                                          _ptr(mean), _ptr(rstd), _stream_ptr(x.device)), "aga_layernorm_fwd")
-        tm.done(x.device)
+        y, _, mean, rstd = _ln_fwd(x2, None, w32, b32, eps, False)
         ctx.save_for_backward(x2, w32, mean, rstd)
         ctx.shape = x.shape
         ctx.param_dtypes = (weight.dtype, bias.dtype)
@@ -328,18 +352,9 @@ class _LayerNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x2, w32, mean, rstd = ctx.saved_tensors
         rows, D = x2.shape
-        dy2 = dy.reshape(rows, D).to(x2.dtype)
-        if not dy2.is_contiguous() or dy2.data_ptr() % 16:
-            dy2 = dy2.contiguous()
+        dy2 = _rows(dy.to(x2.dtype), D)
         need_params = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dx = torch.empty_like(x2)
-        dgamma = torch.empty(D, dtype=torch.float32, device=x2.device) if need_params else None
-        dbeta = torch.empty(D, dtype=torch.float32, device=x2.device) if need_params else None
-        tm = _Timed("layernorm_bwd", 3.0 * rows * D * x2.element_size(), x2.device)
-        L.check(L.lib().aga_layernorm_bwd(_ptr(dy2), _ptr(x2), _DTYPES[x2.dtype], rows, D, _ptr(w32), _ptr(mean),
-                                          _ptr(rstd), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _stream_ptr(x2.device)),
-                "aga_layernorm_bwd")
-        tm.done(x2.device)
+        dx, dgamma, dbeta, _ = _ln_bwd(dy2, x2, w32, mean, rstd, need_params)
         wd, bd = ctx.param_dtypes
         return (dx.view(ctx.shape), dgamma.to(wd) if ctx.needs_input_grad[1] else None,
                 dbeta.to(bd) if ctx.needs_input_grad[2] else None, None)
@@ -349,6 +364,56 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
     """whisper.model.LayerNorm.forward (whisper/model.py:30-32): statistics in fp32, result in x.dtype, one kernel.
     Differentiable in x, weight and bias."""
     return _LayerNormFn.apply(x, weight, bias, float(eps))
+
+
+class _AdapterLayerNormFn(torch.autograd.Function):
+    """LN(x + W2 gelu(W1 x + b1) + b2): the Adapter (whisper/model.py:181-194) and the post-LayerNorm that replaces x
+    (whisper/model.py:234-236, 244-246) as ONE autograd node.  The two small GEMMs stay cuBLAS; the residual add is
+    folded into the LayerNorm kernel, the gradient of b2 falls out of the LayerNorm backward (column sums of dx), and
+    dx = dx_ln + dh1 W1 is one addmm — three full-size elementwise / reduction passes fewer per adapter."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, eps):
+        _require_cuda(x, "x")
+        if x.dtype not in _DTYPES:
+            raise L.AgaError(f"adapter_layer_norm supports fp32 and bf16 rows, got {x.dtype}")
+        D = x.shape[-1]
+        x2 = _rows(x, D)
+        dt = x2.dtype
+        w1c, w2c = w1.detach().to(dt), w2.detach().to(dt)
+        h1 = torch.addmm(b1.detach().to(dt), x2, w1c.t())
+        g = torch.nn.functional.gelu(h1)
+        y = torch.addmm(b2.detach().to(dt), g, w2c.t())
+        g32 = gamma.detach().float().contiguous()
+        be32 = beta.detach().float().contiguous()
+        z, s, mean, rstd = _ln_fwd(x2, y, g32, be32, eps, True)
+        ctx.save_for_backward(x2, h1, g, s, mean, rstd, w1c, w2c, g32)
+        ctx.shape = x.shape
+        ctx.param_dtypes = tuple(t.dtype for t in (w1, b1, w2, b2, gamma, beta))
+        return z.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dz):
+        x2, h1, g, s, mean, rstd, w1c, w2c, g32 = ctx.saved_tensors
+        rows, D = x2.shape
+        dz2 = _rows(dz.to(x2.dtype), D)
+        ds, dgamma, dbeta, db2 = _ln_bwd(dz2, s, g32, mean, rstd, True, need_dxsum=True)
+        dg = ds @ w2c                                  # (rows, bottleneck)
+        dw2 = ds.t() @ g                               # (D, bottleneck)
+        dh1 = torch.ops.aten.gelu_backward(dg, h1)
+        db1 = dh1.sum(0, dtype=torch.float32)
+        dw1 = dh1.t() @ x2                             # (bottleneck, D)
+        dx = torch.addmm(ds, dh1, w1c)                 # the residual branch's gradient rides the GEMM's beta = 1
+        dts = ctx.param_dtypes
+        return (dx.view(ctx.shape), dw1.to(dts[0]), db1.to(dts[1]), dw2.to(dts[2]), db2.to(dts[3]), dgamma.to(dts[4]),
+                dbeta.to(dts[5]), None)
+
+
+def adapter_layer_norm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                       gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """``ln(x + adapter(x))`` of ResidualAttentionBlock.forward (whisper/model.py:234-236, 244-246) as one node;
+    w1 (bottleneck, D), w2 (D, bottleneck) are the Adapter's ``model.0`` / ``model.2`` parameters."""
+    return _AdapterLayerNormFn.apply(x, w1, b1, w2, b2, gamma, beta, float(eps))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -185,13 +185,19 @@ class ResidualAttentionBlock(nn.Module):
         a, second = self.attn(self.attn_ln(x), mask=mask, kv_cache=kv_cache)
         x = x + a
         if self.adapter_flag:
-            x = self.adapter_attn_ln(self.adapter_attn(x))  # post-LN replaces x (:234-236)
+            x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)  # post-LN replaces x (:234-236)
         if self.cross_attn is not None:
             x = x + self.cross_attn(self.cross_attn_ln(x), xa, kv_cache=kv_cache)[0]
         x = x + self.mlp(self.mlp_ln(x))
         if self.adapter_flag:
-            x = self.adapter_mlp_ln(self.adapter_mlp(x))
+            x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x, second
+
+    @staticmethod
+    def _adapter_ln(adapter: "Adapter", ln: "LayerNorm", x: Tensor) -> Tensor:
+        """``ln(adapter(x))`` = LN(x + W2 gelu(W1 x)) as one fused autograd node."""
+        m = adapter.model
+        return ops.adapter_layer_norm(x, m[0].weight, m[0].bias, m[2].weight, m[2].bias, ln.weight, ln.bias, ln.eps)
 
 
 class AudioEncoder(nn.Module):

@@ -164,13 +164,17 @@ AGA_API int aga_head_vote(const float* probs, int L, int B, int H, int T, uint8_
  * called four times per ResidualAttentionBlock (attn_ln, adapter_attn_ln, mlp_ln, adapter_mlp_ln; the two
  * adapter LNs are trainable) — one kernel instead of up-cast + normalise + down-cast.
  *   x, y, dy, dx : (rows, D) contiguous, dtype AGA_F32 or AGA_BF16, 16-byte aligned; D in {384,512,768,1024,1280}
- *   gamma, beta  : (D) fp32;  mean, rstd : (rows) fp32, written by fwd and read by bwd
+ *   residual     : NULL, or (rows, D): the kernel normalises s = dtype(x + residual) — the Adapter's `x + self.model(x)`
+ *                  (W/model.py:193) feeding its post-LayerNorm (W/model.py:234-236) — and writes s to sum_out if non-NULL
+ *   gamma, beta  : (D) fp32;  mean, rstd : (rows) fp32, written by fwd and read by bwd (x of bwd = the normalised tensor)
  *   dgamma, dbeta: (D) fp32, OVERWRITTEN with this call's parameter gradients, or both NULL (frozen LN)
+ *   dxsum        : NULL, or (D) fp32 OVERWRITTEN with sum_rows dx — the bias gradient of the Linear that produced `residual`
  * ------------------------------------------------------------------------------------------ */
-AGA_API int aga_layernorm_fwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* beta,
-                      float eps, void* y, float* mean, float* rstd, void* stream);
+AGA_API int aga_layernorm_fwd(const void* x, const void* residual, int dtype, int64_t rows, int D, const float* gamma,
+                      const float* beta, float eps, void* y, void* sum_out, float* mean, float* rstd, void* stream);
 AGA_API int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
-                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, void* stream);
+                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
+                      void* stream);
 
 #ifdef __cplusplus
 }

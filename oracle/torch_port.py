@@ -93,13 +93,19 @@ def layer_norm(x, weight, bias, eps=1e-5):
     return F.layer_norm(x.float(), (x.shape[-1],), weight, bias, eps).type(x.dtype)
 
 
+def adapter_layer_norm(x, w1, b1, w2, b2, gamma, beta, eps=1e-5):
+    """whisper/whisper/model.py:193 (Adapter.forward) followed by the post-LayerNorm of :234-236 / :244-246."""
+    y = x + F.linear(F.gelu(F.linear(x, w1.to(x.dtype), b1.to(x.dtype))), w2.to(x.dtype), b2.to(x.dtype))
+    return layer_norm(y, gamma, beta, eps)
+
+
 @contextlib.contextmanager
 def patched_ops():
     """Route the mirror modules' hot-path calls to the eager port (CPU baseline / eager-GPU comparator only)."""
     import aga_b200
     from aga_b200 import ops
     saved = {n: getattr(ops, n) for n in ("log_mel_spectrogram", "qkv_attention", "attention_pattern", "guided_loss",
-                                          "head_vote", "layer_norm")}
+                                          "head_vote", "layer_norm", "adapter_layer_norm")}
     try:
         ops.log_mel_spectrogram = log_mel_spectrogram
         ops.qkv_attention = qkv_attention
@@ -107,6 +113,7 @@ def patched_ops():
         ops.guided_loss = guided_loss
         ops.head_vote = head_vote
         ops.layer_norm = layer_norm
+        ops.adapter_layer_norm = adapter_layer_norm
         yield
     finally:
         for n, f in saved.items():

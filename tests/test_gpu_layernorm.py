@@ -72,3 +72,35 @@ def test_layernorm_frozen_params_and_errors(A):
         A.layer_norm(torch.zeros(2, 768), w, b)  # CPU tensors are rejected: no fallback
     with pytest.raises(A.AgaError):
         A.layer_norm(torch.zeros(2, 100, device="cuda"), torch.ones(100, device="cuda"), torch.zeros(100, device="cuda"))
+
+
+def _adapter_ref(x, w1, b1, w2, b2, gamma, beta):
+    """whisper/whisper/model.py:193 + :234-236: LN(x + W2 gelu(W1 x + b1) + b2), eager PyTorch."""
+    y = x + F.linear(F.gelu(F.linear(x, w1.to(x.dtype), b1.to(x.dtype))), w2.to(x.dtype), b2.to(x.dtype))
+    return F.layer_norm(y.float(), (x.shape[-1],), gamma, beta, 1e-5).type(x.dtype)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("shape,D", [((4, 300), 768), ((2, 64), 1024)])
+def test_adapter_layer_norm_matches_reference_expression(A, dtype, tol, shape, D):
+    g = torch.Generator().manual_seed(D + shape[1])
+    Bn = D // 4
+    x = torch.randn(*shape, D, generator=g).to(dtype).cuda()
+    params = [torch.randn(Bn, D, generator=g) / D ** 0.5, 0.02 * torch.randn(Bn, generator=g),
+              torch.randn(D, Bn, generator=g) / Bn ** 0.5, 0.02 * torch.randn(D, generator=g),
+              1.0 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)]
+    dz = torch.randn(*shape, D, generator=g).to(dtype).cuda()
+    outs = []
+    for fn in (A.adapter_layer_norm, _adapter_ref):
+        xs = x.clone().requires_grad_()
+        ps = [p.cuda().requires_grad_() for p in params]
+        z = fn(xs, *ps)
+        z.backward(dz)
+        outs.append((z, xs.grad, [p.grad for p in ps]))
+    (z1, dx1, g1), (z2, dx2, g2) = outs
+    assert z1.dtype == dtype
+    torch.testing.assert_close(z1.float(), z2.float(), rtol=tol, atol=tol)
+    torch.testing.assert_close(dx1.float(), dx2.float(), rtol=tol, atol=tol * float(dx2.float().abs().max()))
+    for a, b in zip(g1, g2):
+        assert a.dtype == torch.float32
+        torch.testing.assert_close(a, b, rtol=tol, atol=tol * float(b.abs().max()))

@@ -30,8 +30,9 @@ def dump(buf, roles, max_rows=70):
     return rows
 
 def main():
-    B, H, T = 2, 2, 1500
     which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+    B, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (2, 2)  # 16 12 = every SM busy
+    T = 1500
     q, k, v = (torch.randn(B, T, H * 64, device="cuda").bfloat16().requires_grad_() for _ in range(3))
     buf = torch.zeros(8 * 4096, dtype=torch.int64, device="cuda")
     out, _, _ = A.qkv_attention(q, k, v, H)  # warm
