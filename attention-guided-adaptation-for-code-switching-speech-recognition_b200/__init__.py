@@ -6,7 +6,7 @@ name carries hyphens).  See DESIGN.md for the path, its boundary and the kernels
 from . import _lib
 from ._lib import AgaError, launch_count
 from .ops import (adapter_layer_norm, attention_pattern, guided_loss, head_vote, layer_norm, log_mel_spectrogram, mel_filterbank_numpy, mel_filters,
-                  qkv_attention)
+                  qkv_attention, qkv_attention_packed)
 
 __all__ = ["AgaError", "adapter_layer_norm", "launch_count", "attention_pattern", "guided_loss", "head_vote", "layer_norm", "log_mel_spectrogram",
-           "mel_filterbank_numpy", "mel_filters", "qkv_attention"]
+           "mel_filterbank_numpy", "mel_filters", "qkv_attention", "qkv_attention_packed"]

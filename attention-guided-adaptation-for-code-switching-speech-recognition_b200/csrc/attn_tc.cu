@@ -93,6 +93,10 @@ template <int NT> struct FwdCfg {
 constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
+#ifndef AGA_FWD_POLY
+#define AGA_FWD_POLY 0  // measured on B200: 0 -> 0.188 ms, 2 -> 0.192, 3 -> 0.198, 4 -> 0.194 (the loop is not MUFU-bound)
+#endif
+constexpr int kFwdPolyPairs = AGA_FWD_POLY;  // of every 8 element pairs of the forward softmax, this many use ex2_poly2
 
 struct FwdSmem {
   // barriers
@@ -325,7 +329,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[c][2 * i]), __uint_as_float(sr[c][2 * i + 1])), sc2, nm2);
-            const float2 pp = make_float2(ex2(x.x), ex2(x.y));
+            // kFwdPolyPairs of every 8 pairs take the FMA-pipe exp2, the rest the MUFU
+            const float2 pp = (i & 7) < kFwdPolyPairs ? ex2_poly2(x) : make_float2(ex2(x.x), ex2(x.y));
             rs = __fadd2_rn(rs, pp);
             __nv_bfloat162 hb = __floats2bfloat162_rn(pp.x, pp.y);
             pk[i] = *reinterpret_cast<uint32_t*>(&hb);

@@ -182,6 +182,24 @@ __device__ __forceinline__ float ex2(float x) {
 #endif
 }
 
+// exp2 of a pair on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding the result receives), exponent patched in
+// with an integer add.  Inputs are clamped to >= -125 (2^-125 ~ 0).  Used for a fraction of the softmax elements so
+// that the MUFU (16 ex2 / clk / SM) stops being the only pipe that works during the exponential phase.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 nf = __fadd2_rn(t, make_float2(-kMagic, -kMagic));
+  const float2 f = __fadd2_rn(x, make_float2(-nf.x, -nf.y));
+  float2 p = __ffma2_rn(make_float2(0.055171646f, 0.055171646f), f, make_float2(0.24261113f, 0.24261113f));
+  p = __ffma2_rn(p, f, make_float2(0.69326097f, 0.69326097f));
+  p = __ffma2_rn(p, f, make_float2(0.99992806f, 0.99992806f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor for a tile stored as rows of 128 bytes with the 128-byte swizzle
 // (exactly what a TMA box of 64 bf16 x R rows with CU_TENSOR_MAP_SWIZZLE_128B writes; base 1024-aligned).

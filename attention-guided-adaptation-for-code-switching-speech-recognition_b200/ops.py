@@ -203,6 +203,69 @@ def _fill_params(p: L.AttnParams, q, k, v, out, lse, n_head, causal, kind, cols,
     p.export_buf = 0 if export_buf is None else export_buf.data_ptr()
 
 
+def _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl):
+    """One aga_attn_fwd call on (possibly strided) q (B,Tq,D), k, v (B,Tk,D) -> (out, lse, export_buf or None)."""
+    B, Tq, D = q.shape
+    if D != n_head * 64:
+        raise L.AgaError("head dim must be 64 (every Whisper size)")
+    lib = L.lib()
+    out = torch.empty((B, Tq, D), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, n_head, Tq), dtype=torch.float32, device=q.device)
+    export_buf = None
+    if kind != L.EXPORT_NONE:
+        lo, hi = cols
+        # rows of unselected heads are never written by the kernel: define them as zero
+        alloc = torch.zeros if head_sel is not None else torch.empty
+        export_buf = alloc((B, n_head, Tq, hi - lo), dtype=torch.float32, device=q.device)
+    p = L.AttnParams()
+    _fill_params(p, q, k, v, out, lse, n_head, causal, kind, cols, head_sel, export_buf, impl)
+    nbytes = C.c_size_t()
+    L.check(lib.aga_attn_fwd_workspace_bytes(C.byref(p), C.byref(nbytes)), "aga_attn_fwd_workspace_bytes")
+    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
+    flops = 4.0 * B * n_head * Tq * k.shape[1] * 64 * (0.5 if causal else 1.0)
+    tm = _Timed(f"attn_fwd_{_impl_name(q, causal, kind, impl)}_{Tq}x{k.shape[1]}", flops, q.device)
+    L.check(lib.aga_attn_fwd(C.byref(p), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_fwd")
+    tm.done(q.device)
+    return out, lse, export_buf
+
+
+def _attn_backward(q, k, v, out, lse, head_sel, probs, cfg, dout, dexport, dq, dk, dv):
+    """One aga_attn_bwd call; dq / dk / dv are caller-allocated and share the strides of q / k / v."""
+    n_head, causal, kind, cols, impl, has_sel = cfg
+    lib = L.lib()
+    if dout is None:
+        dout = torch.zeros_like(out)
+    dout = dout.to(out.dtype)
+    if dout.stride() != out.stride():
+        dout = dout.contiguous()
+    bp = L.AttnBwdParams()
+    export_buf = probs if probs.numel() else None
+    if dexport is not None:
+        dexport = dexport.float().contiguous()
+    _fill_params(bp.fwd, q, k, v, out, lse, n_head, causal, kind if dexport is not None else L.EXPORT_NONE, cols,
+                 head_sel if has_sel else None, export_buf, impl)
+    if dexport is not None and kind == L.EXPORT_LOGITS:
+        bp.fwd.export_buf = dexport.data_ptr()  # logits export: only the gradient is needed (non-null marker)
+    bp.dout = dout.data_ptr()
+    bp.d_export = 0 if dexport is None else dexport.data_ptr()
+    bp.dq, bp.dk, bp.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    assert dq.stride() == q.stride() and dk.stride() == k.stride() and dv.stride() == v.stride()
+    nbytes = C.c_size_t()
+    L.check(lib.aga_attn_bwd_workspace_bytes(C.byref(bp), C.byref(nbytes)), "aga_attn_bwd_workspace_bytes")
+    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
+    flops = 10.0 * q.shape[0] * n_head * q.shape[1] * k.shape[1] * 64 * (0.5 if causal else 1.0)
+    tm = _Timed(f"attn_bwd_{_impl_name(q, causal, kind, impl, bwd=True)}_{q.shape[1]}x{k.shape[1]}", flops, q.device)
+    L.check(lib.aga_attn_bwd(C.byref(bp), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_bwd")
+    tm.done(q.device)
+
+
+def _save(ctx, tensors, out, lse, head_sel, export_buf, n_head, causal, kind, cols, impl):
+    ctx.save_for_backward(*tensors, out, lse, head_sel if head_sel is not None else torch.empty(0),
+                          export_buf if (export_buf is not None and kind == L.EXPORT_PROBS) else torch.empty(0))
+    ctx.cfg = (n_head, causal, kind, cols, impl, head_sel is not None)
+    ctx.mark_non_differentiable(lse)
+
+
 class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, n_head, causal, kind, cols, head_sel, impl):
@@ -213,68 +276,56 @@ class _AttnFn(torch.autograd.Function):
         k = k.to(q.dtype)
         v = v.to(q.dtype)
         q, k, v = _prep(q), _prep(k), _prep(v)
-        B, Tq, D = q.shape
-        if D != n_head * 64:
-            raise L.AgaError("head dim must be 64 (every Whisper size)")
-        lib = L.lib()
-        out = torch.empty((B, Tq, D), dtype=q.dtype, device=q.device)
-        lse = torch.empty((B, n_head, Tq), dtype=torch.float32, device=q.device)
-        export_buf = None
-        if kind != L.EXPORT_NONE:
-            lo, hi = cols
-            # rows of unselected heads are never written by the kernel: define them as zero
-            alloc = torch.zeros if head_sel is not None else torch.empty
-            export_buf = alloc((B, n_head, Tq, hi - lo), dtype=torch.float32, device=q.device)
-        p = L.AttnParams()
-        _fill_params(p, q, k, v, out, lse, n_head, causal, kind, cols, head_sel, export_buf, impl)
-        nbytes = C.c_size_t()
-        L.check(lib.aga_attn_fwd_workspace_bytes(C.byref(p), C.byref(nbytes)), "aga_attn_fwd_workspace_bytes")
-        ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
-        flops = 4.0 * B * n_head * Tq * k.shape[1] * 64 * (0.5 if causal else 1.0)
-        tm = _Timed(f"attn_fwd_{_impl_name(q, causal, kind, impl)}_{Tq}x{k.shape[1]}", flops, q.device)
-        L.check(lib.aga_attn_fwd(C.byref(p), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_fwd")
-        tm.done(q.device)
-        ctx.save_for_backward(q, k, v, out, lse, head_sel if head_sel is not None else torch.empty(0),
-                              export_buf if (export_buf is not None and kind == L.EXPORT_PROBS) else torch.empty(0))
-        ctx.cfg = (n_head, causal, kind, cols, impl, head_sel is not None)
-        if export_buf is None:
-            ctx.mark_non_differentiable(lse)
-            return out, lse, None
-        ctx.mark_non_differentiable(lse)
+        out, lse, export_buf = _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl)
+        _save(ctx, (q, k, v), out, lse, head_sel, export_buf, n_head, causal, kind, cols, impl)
         return out, lse, export_buf
 
     @staticmethod
     def backward(ctx, dout, _dlse, dexport):
         q, k, v, out, lse, head_sel, probs = ctx.saved_tensors
-        n_head, causal, kind, cols, impl, has_sel = ctx.cfg
-        lib = L.lib()
-        if dout is None:
-            dout = torch.zeros_like(out)
-        dout = dout.to(out.dtype)
-        if dout.stride() != out.stride():
-            dout = dout.contiguous()
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        bp = L.AttnBwdParams()
-        export_buf = probs if probs.numel() else None
-        if dexport is not None:
-            dexport = dexport.float().contiguous()
-        _fill_params(bp.fwd, q, k, v, out, lse, n_head, causal, kind if dexport is not None else L.EXPORT_NONE, cols,
-                     head_sel if has_sel else None, export_buf, impl)
-        if dexport is not None and kind == L.EXPORT_LOGITS:
-            bp.fwd.export_buf = dexport.data_ptr()  # logits export: only the gradient is needed (non-null marker)
-        bp.dout = dout.data_ptr()
-        bp.d_export = 0 if dexport is None else dexport.data_ptr()
-        bp.dq, bp.dk, bp.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
-        # dq/dk/dv must share the strides of q/k/v
-        assert dq.stride() == q.stride() and dk.stride() == k.stride() and dv.stride() == v.stride()
-        nbytes = C.c_size_t()
-        L.check(lib.aga_attn_bwd_workspace_bytes(C.byref(bp), C.byref(nbytes)), "aga_attn_bwd_workspace_bytes")
-        ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
-        flops = 10.0 * q.shape[0] * n_head * q.shape[1] * k.shape[1] * 64 * (0.5 if causal else 1.0)
-        tm = _Timed(f"attn_bwd_{_impl_name(q, causal, kind, impl, bwd=True)}_{q.shape[1]}x{k.shape[1]}", flops, q.device)
-        L.check(lib.aga_attn_bwd(C.byref(bp), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_bwd")
-        tm.done(q.device)
+        # gradients share the strides of q / k / v (strided inputs were made dense by _prep or are dense slices' parents)
+        dq, dk, dv = (torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device) for t in (q, k, v))
+        _attn_backward(q, k, v, out, lse, head_sel, probs, ctx.cfg, dout, dexport, dq, dk, dv)
         return dq, dk, dv, None, None, None, None, None, None
+
+
+class _AttnPackedFn(torch.autograd.Function):
+    """Attention on ONE packed projection output.  ``n_q`` = 1: x is (B,T,3D) = [q | k | v] (self-attention after a
+    single fused QKV GEMM); ``n_q`` = 0: x is (B,Tk,2D) = [k | v] and q comes separately (cross-attention).  The kernels
+    read the column slices in place (they take token / batch strides) and the backward writes dq / dk / dv straight into
+    one packed gradient, so the projection's backward is a single GEMM with no gradient-accumulation adds."""
+
+    @staticmethod
+    def forward(ctx, q, x, n_head, causal, kind, cols, head_sel, impl):
+        _require_cuda(x, "packed projection")
+        if x.dtype not in _DTYPES:
+            raise L.AgaError(f"attention supports fp32 and bf16, got {x.dtype}")
+        if not x.is_contiguous():
+            x = x.contiguous()
+        D = n_head * 64
+        if q is None:
+            qv, kv, vv = x[..., :D], x[..., D:2 * D], x[..., 2 * D:]
+        else:
+            qv, kv, vv = _prep(q.to(x.dtype)), x[..., :D], x[..., D:]
+        out, lse, export_buf = _attn_forward(qv, kv, vv, n_head, causal, kind, cols, head_sel, impl)
+        _save(ctx, (qv if q is not None else torch.empty(0), x), out, lse, head_sel, export_buf, n_head, causal, kind, cols, impl)
+        ctx.packed_q = q is None
+        return out, lse, export_buf
+
+    @staticmethod
+    def backward(ctx, dout, _dlse, dexport):
+        qs, x, out, lse, head_sel, probs = ctx.saved_tensors
+        D = ctx.cfg[0] * 64
+        dx = torch.empty_like(x)
+        if ctx.packed_q:
+            q, k, v = x[..., :D], x[..., D:2 * D], x[..., 2 * D:]
+            dq, dk, dv = dx[..., :D], dx[..., D:2 * D], dx[..., 2 * D:]
+        else:
+            q, k, v = qs, x[..., :D], x[..., D:]
+            dq = torch.empty_strided(q.shape, q.stride(), dtype=q.dtype, device=q.device)
+            dk, dv = dx[..., :D], dx[..., D:]
+        _attn_backward(q, k, v, out, lse, head_sel, probs, ctx.cfg, dout, dexport, dq, dk, dv)
+        return (None if ctx.packed_q else dq), dx, None, None, None, None, None, None
 
 
 def qkv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int, causal: bool = False,
@@ -294,6 +345,21 @@ def qkv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int
         head_sel = head_sel.to(device=q.device, dtype=torch.uint8).contiguous()
     empty_cols = export_cols if export_cols is not None else (0, 0)
     return _AttnFn.apply(q, k, v, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl])
+
+
+def qkv_attention_packed(x: torch.Tensor, n_head: int, q: Optional[torch.Tensor] = None, causal: bool = False,
+                         export: Optional[str] = None, export_cols: Optional[Tuple[int, int]] = None,
+                         head_sel: Optional[torch.Tensor] = None, impl: str = "auto"):
+    """``qkv_attention`` on a packed projection: x = [q | k | v] (B,T,3D), or x = [k | v] (B,Tk,2D) with ``q`` given.
+    Same results as :func:`qkv_attention` on the three column slices; one packed gradient comes back."""
+    kind = _KINDS[export]
+    Tk = x.shape[1]
+    if kind != L.EXPORT_NONE and export_cols is None:
+        export_cols = (0, Tk)
+    if head_sel is not None:
+        head_sel = head_sel.to(device=x.device, dtype=torch.uint8).contiguous()
+    empty_cols = export_cols if export_cols is not None else (0, 0)
+    return _AttnPackedFn.apply(q, x, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl])
 
 
 # ------------------------------------------------------------------------------------------------

@@ -124,6 +124,8 @@ class MultiHeadAttention(nn.Module):
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
                 kv_cache: Optional[dict] = None):
+        if kv_cache is None and x.is_cuda and self._frozen():
+            return self._forward_packed(x, xa, mask)
         q = self.query(x)
         if kv_cache is None or xa is None or self.key not in kv_cache:
             src = x if xa is None else xa
@@ -135,6 +137,40 @@ class MultiHeadAttention(nn.Module):
             k, v = kv_cache[self.key], kv_cache[self.value]
         wv, second = self.qkv_attention(q, k, v, mask)
         return self.out(wv), second
+
+    # ---- frozen projections (the --freeze_param adapter policy): one [q|k|v] (or [k|v]) GEMM, attention on the packed
+    #      result, one packed gradient -> one dgrad GEMM.  Same arithmetic as three F.linear calls on row blocks of
+    #      the concatenated weight.
+    def _frozen(self) -> bool:
+        return not any(p.requires_grad for p in (self.query.weight, self.key.weight, self.value.weight))
+
+    def _packed_weights(self, dtype: torch.dtype, with_q: bool):
+        mods = ([self.query] if with_q else []) + [self.key, self.value]
+        sig = (dtype, with_q) + tuple((m.weight._version, m.weight.data_ptr(), 0 if m.bias is None else m.bias._version)
+                                      for m in mods)
+        c = self.__dict__.get("_packed_cache", {}).get(with_q)
+        if c is None or c[0] != sig:
+            w = torch.cat([m.weight.detach() for m in mods], dim=0).to(dtype)
+            b = torch.cat([torch.zeros_like(m.weight[:, 0]) if m.bias is None else m.bias.detach() for m in mods]).to(dtype)
+            c = (sig, w, b)
+            self.__dict__.setdefault("_packed_cache", {})[with_q] = c
+        return c[1], c[2]
+
+    def _forward_packed(self, x: Tensor, xa: Optional[Tensor], mask: Optional[Tensor]):
+        kind, cols = self.export if self.export is not None else (None, None)
+        if xa is None:
+            w, b = self._packed_weights(x.dtype, True)
+            qkv = F.linear(x, w, b)
+            causal = mask is not None
+            out, _lse, second = ops.qkv_attention_packed(qkv, self.n_head, causal=causal, export=kind, export_cols=cols,
+                                                         head_sel=self.head_sel, impl=self.impl)
+        else:
+            w, b = self._packed_weights(x.dtype, False)
+            q = self.query(x)
+            kv = F.linear(xa.to(x.dtype), w, b)
+            out, _lse, second = ops.qkv_attention_packed(kv, self.n_head, q=q, causal=False, export=kind, export_cols=cols,
+                                                         head_sel=self.head_sel, impl=self.impl)
+        return self.out(out), second
 
     def qkv_attention(self, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor] = None):
         # The only mask the reference ever passes is TextDecoder.mask = triu(-inf) (whisper/model.py:322,103),

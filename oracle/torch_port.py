@@ -56,6 +56,16 @@ def qkv_attention(q, k, v, n_head, causal=False, export=None, export_cols=None, 
     return out, None, second
 
 
+def qkv_attention_packed(x, n_head, q=None, causal=False, export=None, export_cols=None, head_sel=None, impl="auto"):
+    """The same attention on a packed [q|k|v] (or [k|v] + q) projection: slices, then the reference op sequence."""
+    D = n_head * 64
+    if q is None:
+        q, k, v = x[..., :D], x[..., D:2 * D], x[..., 2 * D:]
+    else:
+        k, v = x[..., :D], x[..., D:]
+    return qkv_attention(q.contiguous(), k.contiguous(), v.contiguous(), n_head, causal, export, export_cols, head_sel, impl)
+
+
 def attention_pattern(tokens, lid_table, c=0.6):
     """espnet2/asr/espnet_model.py:236-275: a Python loop per utterance (the tokenizer strings are replaced by the
     LID table, the per-token loop and the host round trip are kept)."""
@@ -104,11 +114,12 @@ def patched_ops():
     """Route the mirror modules' hot-path calls to the eager port (CPU baseline / eager-GPU comparator only)."""
     import aga_b200
     from aga_b200 import ops
-    saved = {n: getattr(ops, n) for n in ("log_mel_spectrogram", "qkv_attention", "attention_pattern", "guided_loss",
+    saved = {n: getattr(ops, n) for n in ("log_mel_spectrogram", "qkv_attention", "qkv_attention_packed", "attention_pattern", "guided_loss",
                                           "head_vote", "layer_norm", "adapter_layer_norm")}
     try:
         ops.log_mel_spectrogram = log_mel_spectrogram
         ops.qkv_attention = qkv_attention
+        ops.qkv_attention_packed = qkv_attention_packed
         ops.attention_pattern = attention_pattern
         ops.guided_loss = guided_loss
         ops.head_vote = head_vote
