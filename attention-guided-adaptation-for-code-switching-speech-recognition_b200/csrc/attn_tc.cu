@@ -441,47 +441,56 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
 
 namespace {
 // =============================================================================================== backward
-// One CTA = one 128-key tile (K_j, V_j resident in smem) of one (batch, head); it walks the 128-row query tiles.
+// PERSISTENT kernel: one CTA per SM walks work items (batch, head, 128-key tile); for each item K_j, V_j sit in smem
+// and the CTA streams the 128-row query tiles of that (batch, head) past them.  All rings and barriers run on a
+// CTA-global tile counter: the next item's K_j (double-buffered: the current one is read until the item's last dQ GEMM),
+// V_j, first (Q, dO) tiles, S^T and dP^T are in flight while the current item's last tiles drain — no per-item
+// prologue / epilogue / launch gap (they were 28 % of a one-item CTA).
+//
 // The score tiles are computed TRANSPOSED (keys in the TMEM lanes, queries along the columns), so that P^T and
 // dS^T — the M x K operands of the dV and dK GEMMs — never leave tensor memory.  Each query tile is handled as two
-// independent 64-query halves g = 0, 1 (one softmax warpgroup each):
+// independent 64-query halves g = 0, 1:
 //   S^T_g  = K_j Q_ig^T       cols [64g, 64g+64)          SS, both K-major, N = 64
 //   dP^T_g = V_j dO_ig^T      cols [128+64g, 128+64g+64)  SS, both K-major, N = 64
-//   dV_j  += P^T_g dO_ig      [256,320)   A = P^T_g  (TMEM, bf16 pairs over the first 32 S^T_g columns), B = dO rows (MN-major)
-//   dK_j  += dS^T_g Q_ig      [320,384)   A = dS^T_g (TMEM, bf16 pairs over the first 32 dP^T_g columns), B = Q rows (MN-major)
+//   dV_j  += P^T_g dO_ig      [256,320)   A = P^T_g  (TMEM, bf16 pairs written over the S^T_g columns), B = dO rows (MN-major)
+//   dK_j  += dS^T_g Q_ig      [320,384)   A = dS^T_g (TMEM, bf16 pairs written over the dP^T_g columns), B = Q rows (MN-major)
 //   dQ_i   = dS K_j           [384,448)   A = dS^T rows in smem read as an MN-major operand (both halves), B = K_j (MN-major)
-// Softmax warpgroup g (lane = key): phase 1  P = exp2(S c - lse[q]) -> TMEM  (MUFU-bound);  phase 2
-// dS = P (dP - delta[q]) -> TMEM + one 128-byte swizzled smem row per thread (FMA / LSU-bound).  The two warpgroups
-// share each SM sub-partition, so their phase 1s are forced to ALTERNATE with a pair of named barriers: warpgroup 1
-// runs half a tile behind warpgroup 0 and every phase 1 has the MUFU to itself while the other warpgroup is in
-// phase 2.  lse / delta are per COLUMN here and are broadcast-read from small double-buffered smem tables.
-// 4 drain warps move dQ_i from TMEM into a swizzled fp32 staging buffer (one 32-column half at a time) and add
-// it to the global accumulator with cp.reduce.async.bulk; the accumulator is tile-major
-// (b, h, q-tile, column half, 128 rows, 32) so that every bulk reduction is contiguous.
+// Warp roles (768 threads):
+//   0-15  softmax: half g = warp >> 3, 32-column slice sub = (warp >> 2) & 1, lane quadrant warp & 3 (lane = key).
+//         phase 1  P = exp2(S c - lse[q]) -> TMEM (MUFU);  phase 2  dS = P (dP - delta[q]) -> TMEM + one swizzled smem row
+//         chunk per thread (FMA / LSU).  The two halves alternate their phase 1 (a pair of named barriers), so half 1
+//         runs half a tile behind half 0.  At the end of an item half 0's warps store dV_j, half 1's warps dK_j.
+//   16-19 dQ drain: TMEM -> swizzled fp32 staging -> cp.reduce.async.bulk add into the tile-major global accumulator
+//         (b, h, q-tile, column half, 128 rows, 32).
+//   20    TMA producer: K_j, V_j per item; (Q_i, dO_i, lse/delta rows) per tile.
+//   21,22 MMA streams of halves 0, 1 (S^T, dV, dP^T, dK);  23  MMA stream of dQ.  One in-order issuer per stream:
+//         every "softmax event -> group of MMAs" costs a few hundred cycles of wait + descriptor set-up.
 // Rows/keys past the tensor ends are zero-filled by TMA, which makes their contributions exactly zero.
 constexpr int kBwdThreads = 768;
-constexpr int kBwdSoftmaxWarps = 16;  // 2 halves x 2 column slices x 4 lane quadrants
-constexpr int kBwdDrainWarp0 = 16;    // 4 warps
+constexpr int kBwdSoftmaxWarps = 16;
+constexpr int kBwdDrainWarp0 = 16;
 constexpr int kBwdTmaWarp = 20;
-constexpr int kBwdMmaWarp = 21;  // warps 21, 22: the S / dV / dP / dK streams of query halves 0, 1; warp 23: the dQ stream
+constexpr int kBwdMmaWarp = 21;
 constexpr uint32_t kColBS = 0, kColBdP = 128, kColBdV = 256, kColBdK = 320, kColBdQ = 384;
 constexpr int kPanelBytes = kBlockM * 128;             // 128 rows x 64 bf16
 constexpr int kDqStageBytes = kBlockM * 32 * 4;        // one 32-column half of a dQ tile, fp32: 16 KiB
-constexpr int kBwdStages = 3;  // (Q_i, dO_i) ring: the TMA of tile i+2 is in flight while tile i is being processed
+constexpr int kBwdStages = 3;                          // (Q_i, dO_i, stats) ring: a tile's TMA is issued two tiles ahead
 
 struct BwdSmem {
-  uint64_t kv_full;
+  uint64_t k_full[2], k_empty[2], v_full, v_empty;
   uint64_t qdo_full[kBwdStages], qdo_empty[kBwdStages];
-  uint64_t s_full[2], dp_full[2], p_ready[2], ds_ready[2], ds_free[2], dq_full, dq_empty, dv_init, dk_init;
+  uint64_t s_full[2], dp_full[2], p_ready[2], ds_ready[2], ds_free[2], dq_full, dq_empty;
+  uint64_t dv_init, dk_init, dv_final, dk_final, dk_read;
   uint32_t tmem_base;
-  alignas(16) float stats[kBwdStages][2][kBlockM];  // per stage: lse * log2(e) | delta of the 128 queries (bulk-copied with Q, dO)
+  alignas(16) float stats[kBwdStages][2][kBlockM];  // per stage: lse * log2(e) | delta of the 128 queries
 };
-// K, V | kBwdStages x (Q, dO) | 2 x dS^T (2 panels each) | dQ staging
-constexpr size_t kBwdSmemBytes = 1024 + size_t(2 + 2 * kBwdStages) * kTileBytes + 4 * size_t(kPanelBytes) + kDqStageBytes + sizeof(BwdSmem);
+// 2 x K, V | kBwdStages x (Q, dO) | dS^T panels: half 0 double-buffered, half 1 single | dQ staging
+constexpr size_t kBwdSmemBytes = 1024 + size_t(3 + 2 * kBwdStages) * kTileBytes + 3 * size_t(kPanelBytes) + kDqStageBytes + sizeof(BwdSmem);
 static_assert(kBwdSmemBytes <= 227 * 1024, "backward kernel exceeds the 227 KiB shared-memory limit");
 
 struct BwdArgs {
   int B, H, Tq, Tk;
+  int n_items;      // B * H * ceil(Tk / 128)
   int64_t k_sb, k_st, v_sb, v_st;
   const float* stats;  // (B, H, ceil(Tq/128), 2, 128) fp32: lse * log2(e) | delta per query tile, zero past Tq
   float* dq_accum;  // (B, H, ceil(Tq/128), 2, 128, 32) fp32, zero-initialised, 16-byte chunks XOR-swizzled with (row & 7)
@@ -507,8 +516,20 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssr
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 8 column-chunks of 8 bf16 from 32 fp32 TMEM values, scaled, to one 64-byte row segment
+__device__ __forceinline__ void store_row_chunk(__nv_bfloat16* dst, const uint32_t (&v)[32], float scale) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * q4 + 2 * e]) * scale, __uint_as_float(v[8 * q4 + 2 * e + 1]) * scale);
+      w[e] = *reinterpret_cast<uint32_t*>(&hb);
+    }
+    *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -516,22 +537,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                    const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + kTileBytes;
+  uint8_t* sK = smem;                            // 2 item buffers
+  uint8_t* sV = sK + 2 * kTileBytes;
   uint8_t* sQ = sV + kTileBytes;                 // kBwdStages stages
   uint8_t* sdO = sQ + kBwdStages * kTileBytes;   // kBwdStages stages
-  uint8_t* sdS = sdO + kBwdStages * kTileBytes;  // 2 buffers x 2 panels: [key][queries 0..63], [key][queries 64..127]
-  uint8_t* sdQ = sdS + 4 * kPanelBytes;          // fp32 staging, 4 warps x (32 rows x 128 B)
+  // dS^T rows [key][64 queries]: half 0's panel is double-buffered (its tile c+1 is written while dQ(c) still waits for
+  // half 1), half 1's is not (dQ(c) is issued as soon as half 1 has written tile c): [half 0, c even][half 0, c odd][half 1]
+  uint8_t* sdS = sdO + kBwdStages * kTileBytes;
+  uint8_t* sdQ = sdS + 3 * kPanelBytes;          // fp32 staging, 4 warps x (32 rows x 128 B)
   BwdSmem* sb = reinterpret_cast<BwdSmem*>(sdQ + kDqStageBytes);
 
   CTA_LOG(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int key0 = kt * kBlockN;
   const int n_qt = (a.Tq + kBlockM - 1) / kBlockM;
+  const int n_kt = (a.Tk + kBlockN - 1) / kBlockN;
+  // work items of this CTA: w = blockIdx.x + it * gridDim.x;  item w = ((b * H + h) * n_kt + kt)
+  const int first_item = blockIdx.x, item_step = gridDim.x;
+  const int my_items = first_item < a.n_items ? (a.n_items - first_item + item_step - 1) / item_step : 0;
+  const int total_tiles = my_items * n_qt;  // tiles this CTA processes (the global tile counter c runs over them)
 
   if (threadIdx.x == 0) {
-    mbar_init(&sb->kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sb->k_full[s], 1);
+      mbar_init(&sb->k_empty[s], 3);  // commits of the three MMA streams after their last read of K_j
+    }
+    mbar_init(&sb->v_full, 1);
+    mbar_init(&sb->v_empty, 2);  // commits of the two half streams after the item's last dP^T
     for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(&sb->qdo_full[s], 1);
       mbar_init(&sb->qdo_empty[s], 2);  // one tcgen05.commit per half stream
@@ -539,7 +570,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int g = 0; g < 2; ++g) {
       mbar_init(&sb->s_full[g], 1);
       mbar_init(&sb->dp_full[g], 1);
-      mbar_init(&sb->p_ready[g], 8);   // one arrival per warp of the half's two warpgroups
+      mbar_init(&sb->p_ready[g], 8);   // one arrival per warp of the half
       mbar_init(&sb->ds_ready[g], 8);
       mbar_init(&sb->ds_free[g], 1);   // indexed by dS^T buffer
     }
@@ -547,6 +578,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_init(&sb->dq_empty, 4);
     mbar_init(&sb->dv_init, 1);
     mbar_init(&sb->dk_init, 1);
+    mbar_init(&sb->dv_final, 2);
+    mbar_init(&sb->dk_final, 2);
+    mbar_init(&sb->dk_read, 8);
     fence_barrier_init();
   }
   if (warp == kBwdMmaWarp) {
@@ -563,121 +597,168 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
+  auto decode = [&](int it, int& kt, int& h, int& b) {
+    const int w = first_item + it * item_step;
+    kt = w % n_kt;
+    const int bh = w / n_kt;
+    h = bh % a.H;
+    b = bh / a.H;
+  };
 
   if (warp == kBwdTmaWarp) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(&sb->kv_full, 2 * kTileBytes);
-      tma_load_4d(sK, &map_k, &sb->kv_full, 0, h, key0, b);
-      tma_load_4d(sV, &map_v, &sb->kv_full, 0, h, key0, b);
-    }
-    for (int i = 0; i < n_qt; ++i) {
-      const int s = i % kBwdStages;
-      const uint32_t ph = (i / kBwdStages) & 1;
-      mbar_wait(&sb->qdo_empty[s], ph ^ 1);
+    // ============================== TMA producer ==============================
+    // per item: K_j (the buffer item it-2 used), V_j (free since the previous item's last dP^T), then the (Q, dO) tiles
+    int c = 0;
+    auto load_qdo = [&](int i, int h, int b) {
+      const int s = c % kBwdStages;
+      mbar_wait(&sb->qdo_empty[s], ((c / kBwdStages) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&sb->qdo_full[s], 2 * kTileBytes + 2 * kBlockM * 4);
         bulk_load(sb->stats[s], a.stats + ((int64_t(b) * a.H + h) * n_qt + i) * (2 * kBlockM), 2 * kBlockM * 4, &sb->qdo_full[s]);
         tma_load_4d(sQ + s * kTileBytes, &map_q, &sb->qdo_full[s], 0, h, i * kBlockM, b);
         tma_load_4d(sdO + s * kTileBytes, &map_do, &sb->qdo_full[s], 0, h, i * kBlockM, b);
       }
+      ++c;
+    };
+    for (int it = 0; it < my_items; ++it) {
+      int kt, h, b;
+      decode(it, kt, h, b);
+      const int kb = it & 1;
+      mbar_wait(&sb->k_empty[kb], ((it >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sb->k_full[kb], kTileBytes);
+        tma_load_4d(sK + kb * kTileBytes, &map_k, &sb->k_full[kb], 0, h, kt * kBlockN, b);
+      }
+      // the waits are taken in the order in which they clear: ring slots of the item's first two tiles (freed by tiles
+      // n-3, n-2 of the previous item), then V (freed when the previous item's last dP^T was issued, during its tile
+      // n-1), then the remaining ring slots
+      const int pre = n_qt < 2 ? n_qt : 2;
+      for (int i = 0; i < pre; ++i) load_qdo(i, h, b);
+      mbar_wait(&sb->v_empty, (it & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sb->v_full, kTileBytes);
+        tma_load_4d(sV, &map_v, &sb->v_full, 0, h, kt * kBlockN, b);
+      }
+      for (int i = pre; i < n_qt; ++i) load_qdo(i, h, b);
     }
   } else if (warp == kBwdMmaWarp || warp == kBwdMmaWarp + 1) {
     // ============================== MMA stream of query half g ==============================
-    // One issuing warp per half (and one more for dQ): every "softmax event -> group of 4 MMAs" costs a few hundred
-    // cycles of barrier wait + descriptor set-up in the issuing thread, and a single in-order issuer for all ten
-    // groups of a tile was the critical path of the kernel (and made half 1's events wait behind half 0's).
     const int g = warp - kBwdMmaWarp;
     constexpr uint32_t idesc_nt = make_idesc_bf16(kBlockN, 64, 0, 0);        // S^T_g, dP^T_g: A and B K-major, N = 64
     constexpr uint32_t idesc_ts = make_idesc_bf16(kBlockN, kHeadDim, 0, 1);  // dV, dK: A in TMEM, B MN-major
-    const uint64_t dK_d = make_smem_desc_sw128(smem_u32(sK));
-    const uint64_t dV_d = make_smem_desc_sw128(smem_u32(sV));
     const uint32_t t_sg = tmem + kColBS + g * 64, t_dpg = tmem + kColBdP + g * 64;
     TL_DECL((lane == 0 && g == 0) ? 0 : -1);
     // query half g of a 128-row tile = rows 64g .. 64g+63 = byte offset 64 * 128 (a multiple of the 1024-byte swizzle atom)
-    auto q_desc = [&](int i) { return make_smem_desc_sw128(smem_u32(sQ + (i % kBwdStages) * kTileBytes + g * 8192)); };
-    auto do_desc = [&](int i) { return make_smem_desc_sw128(smem_u32(sdO + (i % kBwdStages) * kTileBytes + g * 8192)); };
-    mbar_wait(&sb->kv_full, 0);
-    mbar_wait(&sb->qdo_full[0], 0);
-    tc_fence_after();
-    {
-      const uint64_t dq0 = q_desc(0), ddo0 = do_desc(0);
+    auto q_desc = [&](int c) { return make_smem_desc_sw128(smem_u32(sQ + (c % kBwdStages) * kTileBytes + g * 8192)); };
+    auto do_desc = [&](int c) { return make_smem_desc_sw128(smem_u32(sdO + (c % kBwdStages) * kTileBytes + g * 8192)); };
+    const uint64_t dv = make_smem_desc_sw128(smem_u32(sV));
+    auto issue_s = [&](int c, int it) {  // S^T_g(c) = K(it) Q_g(c)^T
+      const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + (it & 1) * kTileBytes)), dq = q_desc(c);
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_sg, dK_d + uint64_t(kk * 2), dq0 + uint64_t(kk * 2), idesc_nt, kk > 0);
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_sg, dk + uint64_t(kk * 2), dq + uint64_t(kk * 2), idesc_nt, kk > 0);
         tc_commit(&sb->s_full[g]);
+      }
+      __syncwarp();
+    };
+    auto issue_dp = [&](int c, bool last_of_item) {  // dP^T_g(c) = V dO_g(c)^T
+      const uint64_t ddo = do_desc(c);
+      if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_dpg, dV_d + uint64_t(kk * 2), ddo0 + uint64_t(kk * 2), idesc_nt, kk > 0);
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_dpg, dv + uint64_t(kk * 2), ddo + uint64_t(kk * 2), idesc_nt, kk > 0);
         tc_commit(&sb->dp_full[g]);
+        if (last_of_item) tc_commit(&sb->v_empty);  // this stream's last read of V_j
       }
       __syncwarp();
+    };
+    if (my_items > 0) {
+      mbar_wait(&sb->k_full[0], 0);
+      mbar_wait(&sb->v_full, 0);
+      mbar_wait(&sb->qdo_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_dp(0, n_qt == 1);
     }
-    for (int i = 0; i < n_qt; ++i) {
-      const uint32_t par = i & 1;
-      const bool more = i + 1 < n_qt;
-      const uint64_t dq_i = q_desc(i), ddo_i = do_desc(i), dq_n = q_desc(i + 1), ddo_n = do_desc(i + 1);
-      // ---- phase 1 of half g done: dV += P^T_g dO_g, then S^T_g(i+1) over the same columns (in-order tensor pipe)
-      TL(10);
-      mbar_wait(&sb->p_ready[g], par);
-      if (more) mbar_wait(&sb->qdo_full[(i + 1) % kBwdStages], ((i + 1) / kBwdStages) & 1);
-      if (i == 0 && g == 1) mbar_wait(&sb->dv_init, 0);  // half 0's first (overwriting) dV MMA has executed
-      TL(11);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          mma_ts(tmem + kColBdV, t_sg + (kk >> 1) * 32 + (kk & 1) * 8, ddo_i + uint64_t(kk * 128), idesc_ts,
-                 (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
-        if (i == 0 && g == 0) tc_commit(&sb->dv_init);
+    int c = 0;
+    for (int it = 0; it < my_items; ++it) {
+      for (int i = 0; i < n_qt; ++i, ++c) {
+        const uint32_t par = c & 1;
+        const bool last = i == n_qt - 1;
+        const bool more = c + 1 < total_tiles;
+        const int it_next = last ? it + 1 : it;            // item of tile c + 1
+        const bool next_last = last ? n_qt == 1 : i + 2 == n_qt;  // tile c + 1 is the last tile of its item
+        const uint64_t dq_c = q_desc(c), ddo_c = do_desc(c);
+        // ---- phase 1 of half g done: dV += P^T_g dO_g, then S^T_g(c+1) over the same columns (in-order tensor pipe)
+        TL(10);
+        mbar_wait(&sb->p_ready[g], par);
         if (more) {
-#pragma unroll
-          for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_sg, dK_d + uint64_t(kk * 2), dq_n + uint64_t(kk * 2), idesc_nt, kk > 0);
-          tc_commit(&sb->s_full[g]);
+          mbar_wait(&sb->qdo_full[(c + 1) % kBwdStages], ((c + 1) / kBwdStages) & 1);
+          if (last) mbar_wait(&sb->k_full[it_next & 1], (it_next >> 1) & 1);
         }
-      }
-      __syncwarp();
-      // ---- phase 2 of half g done: dK += dS^T_g Q_g, then dP^T_g(i+1) over the same columns
-      TL(12);
-      mbar_wait(&sb->ds_ready[g], par);
-      if (i == 0 && g == 1) mbar_wait(&sb->dk_init, 0);
-      TL(13);
-      tc_fence_after();
-      if (elect_one()) {
+        if (i == 0 && g == 1) mbar_wait(&sb->dv_init, it & 1);  // half 0's overwriting dV MMA of this item has executed
+        TL(11);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          mma_ts(tmem + kColBdK, t_dpg + (kk >> 1) * 32 + (kk & 1) * 8, dq_i + uint64_t(kk * 128), idesc_ts,
-                 (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
-        if (i == 0 && g == 0) tc_commit(&sb->dk_init);
-        tc_commit(&sb->qdo_empty[i % kBwdStages]);  // this half's last read of (Q_i, dO_i)
-        if (more) {
-#pragma unroll
-          for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(t_dpg, dV_d + uint64_t(kk * 2), ddo_n + uint64_t(kk * 2), idesc_nt, kk > 0);
-          tc_commit(&sb->dp_full[g]);
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ts(tmem + kColBdV, t_sg + (kk >> 1) * 32 + (kk & 1) * 8, ddo_c + uint64_t(kk * 128), idesc_ts,
+                   (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
+          if (i == 0 && g == 0) tc_commit(&sb->dv_init);
+          if (last) tc_commit(&sb->dv_final);
         }
+        __syncwarp();
+        if (more) issue_s(c + 1, it_next);
+        // ---- phase 2 of half g done: dK += dS^T_g Q_g, then dP^T_g(c+1) over the same columns
+        TL(12);
+        mbar_wait(&sb->ds_ready[g], par);
+        if (i == 0 && g == 1) mbar_wait(&sb->dk_init, it & 1);
+        if (i == 0 && g == 0 && it > 0) mbar_wait(&sb->dk_read, (it - 1) & 1);  // half 1's warps have read dK of item it-1
+        if (more && last) mbar_wait(&sb->v_full, it_next & 1);
+        TL(13);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ts(tmem + kColBdK, t_dpg + (kk >> 1) * 32 + (kk & 1) * 8, dq_c + uint64_t(kk * 128), idesc_ts,
+                   (i > 0 || g > 0 || kk > 0) ? 1u : 0u);
+          if (i == 0 && g == 0) tc_commit(&sb->dk_init);
+          tc_commit(&sb->qdo_empty[c % kBwdStages]);  // this half's last read of (Q, dO) of tile c
+          if (last) {
+            tc_commit(&sb->dk_final);
+            tc_commit(&sb->k_empty[it & 1]);  // this stream's last read of K_j
+          }
+        }
+        __syncwarp();
+        if (more) issue_dp(c + 1, next_last);
+        TL(14);
       }
-      __syncwarp();
-      TL(14);
     }
     TL_END();
   } else if (warp == kBwdMmaWarp + 2) {
-    // ============================== dQ stream: dQ_i = dS K_j once both halves of dS^T(i) are in smem ====================
+    // ============================== dQ stream: dQ(c) = dS K_j once both halves of dS^T(c) are in smem ====================
     constexpr uint32_t idesc_tn = make_idesc_bf16(kBlockM, kHeadDim, 1, 1);  // A and B MN-major
-    const uint64_t dK_d = make_smem_desc_sw128(smem_u32(sK));
-    mbar_wait(&sb->kv_full, 0);
-    for (int i = 0; i < n_qt; ++i) {
-      const uint32_t par = i & 1;
-      const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(sdS + par * 2 * kPanelBytes), kPanelBytes);
-      mbar_wait(&sb->ds_ready[0], par);
-      mbar_wait(&sb->ds_ready[1], par);
-      if (i > 0) mbar_wait(&sb->dq_empty, (i - 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
+    int c = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const uint64_t dK_d = make_smem_desc_sw128(smem_u32(sK + (it & 1) * kTileBytes));
+      mbar_wait(&sb->k_full[it & 1], (it >> 1) & 1);
+      for (int i = 0; i < n_qt; ++i, ++c) {
+        const uint32_t par = c & 1;
+        // A = [half 0 panel of buffer par | half 1 panel]: LBO = distance between the two 64-query panels
+        const uint64_t dS_mn = make_smem_desc_sw128_mn(smem_u32(sdS + par * kPanelBytes), (2 - par) * kPanelBytes);
+        mbar_wait(&sb->ds_ready[0], par);
+        mbar_wait(&sb->ds_ready[1], par);
+        if (c > 0) mbar_wait(&sb->dq_empty, (c - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 16; ++kk)  // contraction over 128 keys: 16 key rows = 2048 bytes in both operands
-          mma_ss(tmem + kColBdQ, dS_mn + uint64_t(kk * 128), dK_d + uint64_t(kk * 128), idesc_tn, kk > 0);
-        tc_commit(&sb->dq_full);
-        tc_commit(&sb->ds_free[par]);
+          for (int kk = 0; kk < kBlockN / 16; ++kk)  // contraction over 128 keys: 16 key rows = 2048 bytes in both operands
+            mma_ss(tmem + kColBdQ, dS_mn + uint64_t(kk * 128), dK_d + uint64_t(kk * 128), idesc_tn, kk > 0);
+          tc_commit(&sb->dq_full);
+          tc_commit(&sb->ds_free[par]);
+          if (i == n_qt - 1) tc_commit(&sb->k_empty[it & 1]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp < kBwdSoftmaxWarps) {
     // ============================== P^T / dS^T producers ==============================
@@ -690,167 +771,174 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t t_s = tmem + (lane_base << 16) + kColBS + g * 64 + sub * 32;
     const uint32_t t_dp = tmem + (lane_base << 16) + kColBdP + g * 64 + sub * 32;
     const uint32_t stats0 = smem_u32(sb->stats[0][0]) + (g * 64 + sub * 32) * 4;  // this slice's 32 queries of stage 0's lse row
-    const uint32_t ds_base = smem_u32(sdS + g * kPanelBytes + r * 128);
+    const uint32_t ds_base = smem_u32(sdS + g * 2 * kPanelBytes + r * 128);  // half 0: buffers 0, 1; half 1: the third panel
 #ifndef AGA_BWD_NO_TOKEN
-    if (g == 1) named_bar_arrive(4, 512);  // half 0 may run the first phase 1
+    if (g == 1 && total_tiles > 0) named_bar_arrive(4, 512);  // half 0 may run the first phase 1
 #endif
     TL_DECL(((warp & 7) == 0 && lane == 0) ? 1 + g : -1);
-    for (int i = 0; i < n_qt; ++i) {
-      const uint32_t par = i & 1;
-      TL(20);
-      const int stage = i % kBwdStages;
-      const uint32_t lse4 = stats0 + stage * (2 * kBlockM * 4), del4 = lse4 + kBlockM * 4;
-      mbar_wait(&sb->qdo_full[stage], (i / kBwdStages) & 1);  // the tile's lse / delta rows have landed (long ago)
-      TL(26);
-      mbar_wait(&sb->s_full[g], par);
-      TL(21);
-      tc_fence_after();
-      uint32_t pk[16];
-      {
-        uint32_t sv[32];
-        tmem_ld32(t_s, sv);
-        tmem_wait_ld();
-        // ---- phase 1 (MUFU): wait for the other half to leave its phase 1
+    int c = 0;
+    for (int it = 0; it < my_items; ++it) {
+      for (int i = 0; i < n_qt; ++i, ++c) {
+        const uint32_t par = c & 1;
+        TL(20);
+        const int stage = c % kBwdStages;
+        const uint32_t lse4 = stats0 + stage * (2 * kBlockM * 4), del4 = lse4 + kBlockM * 4;
+        mbar_wait(&sb->qdo_full[stage], (c / kBwdStages) & 1);  // the tile's lse / delta rows have landed (long ago)
+        TL(26);
+        mbar_wait(&sb->s_full[g], par);
+        TL(21);
+        tc_fence_after();
+        uint32_t pk[16];
+        {
+          uint32_t sv[32];
+          tmem_ld32(t_s, sv);
+          tmem_wait_ld();
+          // ---- phase 1 (MUFU): wait for the other half to leave its phase 1
 #ifndef AGA_BWD_NO_TOKEN
-        const float sc = named_bar_sync_dep(4 + g, 512, kScaleLog2);
+          const float sc = named_bar_sync_dep(4 + g, 512, kScaleLog2);
 #else
-        const float sc = kScaleLog2;
+          const float sc = kScaleLog2;
 #endif
-        TL(22);
-        if (i == 0) CTA_MARK(5);
-        const float2 sc2 = make_float2(sc, sc);
-        float chk = 0.f;
+          TL(22);
+          if (c == 0) CTA_MARK(5);
+          const float2 sc2 = make_float2(sc, sc);
+          float chk = 0.f;
 #pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) {
-          const float4 L = lds128f(lse4 + e4 * 16);
-          const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sv[4 * e4 + 0]), __uint_as_float(sv[4 * e4 + 1])), sc2,
-                                       make_float2(-L.x, -L.y));
-          const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sv[4 * e4 + 2]), __uint_as_float(sv[4 * e4 + 3])), sc2,
-                                       make_float2(-L.z, -L.w));
-          const float p0 = ex2(x0.x), p1 = ex2(x0.y), p2 = ex2(x1.x), p3 = ex2(x1.y);
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
-          pk[2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
-          pk[2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-          chk = __uint_as_float(pk[2 * e4] ^ pk[2 * e4 + 1] ^ __float_as_uint(chk));
-        }
-        // hand the MUFU to the other half (the value threaded through depends on every exponential above)
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 L = lds128f(lse4 + e4 * 16);
+            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sv[4 * e4 + 0]), __uint_as_float(sv[4 * e4 + 1])), sc2,
+                                         make_float2(-L.x, -L.y));
+            const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sv[4 * e4 + 2]), __uint_as_float(sv[4 * e4 + 3])), sc2,
+                                         make_float2(-L.z, -L.w));
+            const float p0 = ex2(x0.x), p1 = ex2(x0.y), p2 = ex2(x1.x), p3 = ex2(x1.y);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
+            pk[2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            chk = __uint_as_float(pk[2 * e4] ^ pk[2 * e4 + 1] ^ __float_as_uint(chk));
+          }
+          // hand the MUFU to the other half (the value threaded through depends on every exponential above)
 #ifndef AGA_BWD_NO_TOKEN
-        if (!(g == 1 && i == n_qt - 1)) pk[15] ^= __float_as_uint(named_bar_arrive_dep(5 - g, 512, chk)) ^ __float_as_uint(chk);
+          if (!(g == 1 && c == total_tiles - 1)) pk[15] ^= __float_as_uint(named_bar_arrive_dep(5 - g, 512, chk)) ^ __float_as_uint(chk);
 #endif
-      }
-      tmem_st16(t_s, pk);  // 32 queries as bf16 pairs over the first 16 of this slice's S^T columns
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sb->p_ready[g]);
-      TL(23);
-      // ---- phase 2 (FMA / LSU)
-      const uint32_t dsrow = ds_base + par * 2 * kPanelBytes;
-      mbar_wait(&sb->dp_full[g], par);
-      if (i >= 2) mbar_wait(&sb->ds_free[par], ((i >> 1) - 1) & 1);  // dQ(i-2) has consumed this dS^T buffer
-      TL(24);
-      tc_fence_after();
-      uint32_t dd[16];
-      {
-        uint32_t dv[32];
-        tmem_ld32(t_dp, dv);
-        tmem_wait_ld();
+        }
+        tmem_st16(t_s, pk);  // 32 queries as bf16 pairs over the first 16 of this slice's S^T columns
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->p_ready[g]);
+        TL(23);
+        // ---- phase 2 (FMA / LSU)
+        const uint32_t dsrow = ds_base + (g == 0 ? par * kPanelBytes : 0);
+        mbar_wait(&sb->dp_full[g], par);
+        // the panel about to be written has been consumed: half 0 (double-buffered) by dQ(c-2), half 1 by dQ(c-1)
+        if (g == 0) {
+          if (c >= 2) mbar_wait(&sb->ds_free[par], ((c >> 1) - 1) & 1);
+        } else if (c >= 1) {
+          mbar_wait(&sb->ds_free[(c - 1) & 1], ((c - 1) >> 1) & 1);
+        }
+        TL(24);
+        tc_fence_after();
+        uint32_t dd[16];
+        {
+          uint32_t dv[32];
+          tmem_ld32(t_dp, dv);
+          tmem_wait_ld();
 #pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) {
-          const float4 D = lds128f(del4 + e4 * 16);
-          const uint32_t w0 = pk[2 * e4], w1 = pk[2 * e4 + 1];
-          const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(dv[4 * e4 + 0]), __uint_as_float(dv[4 * e4 + 1])),
-                                       make_float2(-D.x, -D.y));
-          const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(dv[4 * e4 + 2]), __uint_as_float(dv[4 * e4 + 3])),
-                                       make_float2(-D.z, -D.w));
-          const float2 d0 = __fmul2_rn(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), a0);
-          const float2 d1 = __fmul2_rn(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), a1);
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(d0.x, d0.y), h1 = __floats2bfloat162_rn(d1.x, d1.y);
-          dd[2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
-          dd[2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 D = lds128f(del4 + e4 * 16);
+            const uint32_t w0 = pk[2 * e4], w1 = pk[2 * e4 + 1];
+            const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(dv[4 * e4 + 0]), __uint_as_float(dv[4 * e4 + 1])),
+                                         make_float2(-D.x, -D.y));
+            const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(dv[4 * e4 + 2]), __uint_as_float(dv[4 * e4 + 3])),
+                                         make_float2(-D.z, -D.w));
+            const float2 d0 = __fmul2_rn(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), a0);
+            const float2 d1 = __fmul2_rn(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), a1);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(d0.x, d0.y), h1 = __floats2bfloat162_rn(d1.x, d1.y);
+            dd[2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
+            dd[2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+        }
+        tmem_st16(t_dp, dd);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)  // 16-byte chunk sub*4 + q4 = queries 32 sub + 8 q4 .. + 7, XOR-swizzled with (row & 7)
+          sts128(dsrow + (((sub * 4 + q4) ^ (r & 7)) * 16), dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+        fence_proxy_async_smem();
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->ds_ready[g]);
+        TL(25);
+      }
+      // ---- item done for this half: half 0's warps store dV_j (final after both streams' last dV MMA), half 1's warps
+      //      dK_j.  Half 0 reads dV before its next p_ready arrival (which gates the next item's overwriting dV MMA);
+      //      half 1 signals dk_read, which gates the next item's overwriting dK MMA.
+      {
+        int kt, h, b;
+        decode(it, kt, h, b);
+        const int key = kt * kBlockN + r;
+        mbar_wait(g == 0 ? &sb->dv_final : &sb->dk_final, it & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem + (lane_base << 16) + (g == 0 ? kColBdV : kColBdK) + sub * 32, v);
+        tmem_wait_ld();
+        if (g == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sb->dk_read);
+        }
+        if (key < a.Tk) {
+          __nv_bfloat16* dst = (g == 0 ? a.dv + int64_t(b) * a.v_sb + int64_t(key) * a.v_st
+                                       : a.dk + int64_t(b) * a.k_sb + int64_t(key) * a.k_st) + h * kHeadDim + sub * 32;
+          store_row_chunk(dst, v, g == 0 ? 1.0f : 0.125f);
         }
       }
-      tmem_st16(t_dp, dd);
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4)  // 16-byte chunk sub*4 + q4 = queries 32 sub + 8 q4 .. + 7, XOR-swizzled with (row & 7)
-        sts128(dsrow + (((sub * 4 + q4) ^ (r & 7)) * 16), dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
-      fence_proxy_async_smem();
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sb->ds_ready[g]);
-      TL(25);
     }
     CTA_MARK(6);
     TL_END();
-    // ---- dK_j / dV_j: final once both halves' last dK MMAs have completed (their commits on the last (Q, dO) stage);
-    //      the 16 softmax warps store one 32-column chunk each while the drain warps finish the last dQ tile
-    mbar_wait(&sb->qdo_empty[(n_qt - 1) % kBwdStages], ((n_qt - 1) / kBwdStages) & 1);
-    tc_fence_after();
-    {
-      const int chunk = g * 2 + sub;  // 0, 1: dV columns 0-31, 32-63;  2, 3: dK
-      const bool is_dk = chunk >= 2;
-      const int key = key0 + r;
-      uint32_t v[32];
-      tmem_ld32(tmem + (lane_base << 16) + (is_dk ? kColBdK : kColBdV) + (chunk & 1) * 32, v);
-      tmem_wait_ld();
-      if (key < a.Tk) {
-        const float scale = is_dk ? 0.125f : 1.0f;
-        __nv_bfloat16* dst = (is_dk ? a.dk + int64_t(b) * a.k_sb + int64_t(key) * a.k_st
-                                    : a.dv + int64_t(b) * a.v_sb + int64_t(key) * a.v_st) + h * kHeadDim + (chunk & 1) * 32;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * q4 + 2 * e]) * scale,
-                                                      __uint_as_float(v[8 * q4 + 2 * e + 1]) * scale);
-            w[e] = *reinterpret_cast<uint32_t*>(&hb);
-          }
-          *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-    }
   } else if (warp < kBwdTmaWarp) {
-    // ============================== dQ drain, then dK / dV store ==============================
+    // ============================== dQ drain ==============================
     const int w4 = warp & 3;
     const uint32_t lane_base = uint32_t(w4 * 32);
-    const int r = int(lane_base) + lane;
     const uint32_t t_dq = tmem + (lane_base << 16) + kColBdQ;
     uint8_t* stage = sdQ + w4 * (32 * 128);  // this warp's 32 rows x 32 fp32
     const uint32_t my_row = smem_u32(stage + lane * 128);
-    // tile (b, h, i) = 2 halves x (128 rows x 32 floats); this warp owns rows [32 w4, 32 w4 + 32) of each half
-    float* gdst = a.dq_accum + (int64_t(b) * a.H + h) * n_qt * (kBlockM * kHeadDim) + lane_base * 32;
     TL_DECL((warp == kBwdDrainWarp0 && lane == 0) ? 3 : -1);
-    for (int i = 0; i < n_qt; ++i) {
-      TL(30);
-      mbar_wait(&sb->dq_full, i & 1);
-      TL(31);
-      tc_fence_after();
-      uint32_t lo[32], hi[32];
-      tmem_ld32(t_dq, lo);
-      tmem_ld32(t_dq + 32, hi);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sb->dq_empty);
-      float* gtile = gdst + int64_t(i) * (kBlockM * kHeadDim);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (lane == 0) bulk_wait_read0();  // the previous bulk reduction has finished reading the staging rows
+    int c = 0;
+    for (int it = 0; it < my_items; ++it) {
+      int kt, h, b;
+      decode(it, kt, h, b);
+      // tile (b, h, i) = 2 halves x (128 rows x 32 floats); this warp owns rows [32 w4, 32 w4 + 32) of each half
+      float* gdst = a.dq_accum + (int64_t(b) * a.H + h) * n_qt * (kBlockM * kHeadDim) + lane_base * 32;
+      for (int i = 0; i < n_qt; ++i, ++c) {
+        TL(30);
+        mbar_wait(&sb->dq_full, c & 1);
+        TL(31);
+        tc_fence_after();
+        uint32_t lo[32], hi[32];
+        tmem_ld32(t_dq, lo);
+        tmem_ld32(t_dq + 32, hi);
+        tmem_wait_ld();
+        tc_fence_before();
         __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->dq_empty);
+        float* gtile = gdst + int64_t(i) * (kBlockM * kHeadDim);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t* v = half ? hi : lo;
-          sts128(my_row + ((e ^ (lane & 7)) * 16), v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
+        for (int half = 0; half < 2; ++half) {
+          if (lane == 0) bulk_wait_read0();  // the previous bulk reduction has finished reading the staging rows
+          __syncwarp();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t* v = half ? hi : lo;
+            sts128(my_row + ((e ^ (lane & 7)) * 16), v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
 #ifndef AGA_BWD_NO_RED
-        if (lane == 0) bulk_reduce_add_f32(gtile + half * (kBlockM * 32), stage, 32 * 128);
+          if (lane == 0) bulk_reduce_add_f32(gtile + half * (kBlockM * 32), stage, 32 * 128);
 #endif
+        }
+        TL(32);
       }
-      TL(32);
     }
     if (lane == 0) bulk_wait_read0();  // the staging rows must outlive the last bulk reduction's reads; the adds themselves
                                        // complete asynchronously (kernel completion orders them before the convert kernel)
@@ -957,10 +1045,17 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
   if ((st = make_map(&mk, p.k, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, kBlockN)) != AGA_OK) return st;
   if ((st = make_map(&mv, p.v, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, kBlockN)) != AGA_OK) return st;
   if ((st = make_map(&mdo, bp.dout, p.B, p.H, p.Tq, p.o_stride_b, p.o_stride_t, kBlockM)) != AGA_OK) return st;
-  BwdArgs a{p.B, p.H, p.Tq, p.Tk, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, stats, dq_acc,
+  const int n_kt = (p.Tk + kBlockN - 1) / kBlockN;
+  const int n_items = p.B * p.H * n_kt;
+  BwdArgs a{p.B, p.H, p.Tq, p.Tk, n_items, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, stats, dq_acc,
             static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv)};
   AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBwdSmemBytes)));
-  dim3 grid((p.Tk + kBlockN - 1) / kBlockN, p.H, p.B);
+  static const int n_sm = []() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const unsigned grid = unsigned(std::min(n_items, n_sm));  // persistent: one CTA per SM walks the items
   attn_bwd_tc_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(mq, mk, mv, mdo, a);
   AGA_AFTER_LAUNCH();
   const int64_t total8 = int64_t(p.B) * p.Tq * p.H * (kHeadDim / 8);

@@ -22,6 +22,12 @@ def dump(buf, roles, max_rows=70):
             rows.append((clk, r, tag))
     rows.sort()
     t0 = rows[0][0]
+    # per-role period of the first tag of its loop body (20 for the softmax roles): tile periods over the whole CTA
+    for r in roles:
+        first = [c for c, rr, t in rows if rr == r and t in (20, 30)]
+        if len(first) > 2:
+            d = [b - a for a, b in zip(first, first[1:])]
+            print(f"role{r}: {len(first)} loop iterations; periods: " + " ".join(str(x) for x in d[:60]))
     prev = {}
     for clk, r, tag in rows[:max_rows]:
         d = clk - prev.get(r, clk)
@@ -42,14 +48,14 @@ def main():
         out, _, _ = A.qkv_attention(q, k, v, H)
         torch.cuda.synchronize()
         lib.aga_debug_set_timeline(C.c_void_p(0))
-        rows = dump(buf, [0, 1, 2, 3], 170)
+        rows = dump(buf, [0, 1, 2, 3], 560)
     else:
         out.backward(do, retain_graph=True)
         lib.aga_debug_set_timeline(C.c_void_p(buf.data_ptr()))
         out.backward(do)
         torch.cuda.synchronize()
         lib.aga_debug_set_timeline(C.c_void_p(0))
-        rows = dump(buf, [0, 1, 2, 3], 170)
+        rows = dump(buf, [0, 1, 2, 3], 560)
 
 if __name__ == "__main__":
     main()
