@@ -66,8 +66,7 @@ class OpenAIWhisperEncoder(torch.nn.Module):
     def whisper_encode(self, input: torch.Tensor, ilens: torch.Tensor = None):
         """whisper_encoder.py:137-222 (no side network)."""
         enc = self.encoders
-        x = F.gelu(enc.conv1(input))
-        x = F.gelu(enc.conv2(x)).permute(0, 2, 1)
+        x = enc.stem(input)  # conv1 + GELU + conv2 + GELU, token-major
         n_frames, max_pos = x.size(1), enc.positional_embedding.size(0)
         if n_frames <= max_pos:
             x = (x + enc.positional_embedding[:n_frames, :]).to(x.dtype)

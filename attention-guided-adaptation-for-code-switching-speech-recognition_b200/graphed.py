@@ -41,9 +41,11 @@ class GraphedTrainStep:
                 self._update()
 
     def _fwd_bwd(self):
+        self.bucket.begin_step()
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             loss, stats, _ = self.model(*self.static_in)
         loss.backward()
+        self.bucket.gather_()
         return loss.detach(), {k: v for k, v in stats.items() if v is not None}
 
     def _reduce(self):
@@ -54,7 +56,6 @@ class GraphedTrainStep:
     def _update(self):
         self.bucket.clip_grad_norm_(self.max_grad_norm)
         self.opt.step()
-        self.bucket.zero_()
 
     def __call__(self, batch: Sequence[torch.Tensor]) -> torch.Tensor:
         for dst, src in zip(self.static_in, batch):

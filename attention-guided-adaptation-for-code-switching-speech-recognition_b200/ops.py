@@ -432,11 +432,43 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
     return _LayerNormFn.apply(x, weight, bias, float(eps))
 
 
+def cast_trainable(p: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """``p.detach().to(dtype)``; served from the per-step low-precision shadow when the parameter has a fresh one
+    (``parallel.FlatGradBucket.begin_step`` refreshes all of them with one multi-tensor copy)."""
+    if p.dtype == dtype:
+        return p.detach()
+    sh = getattr(p, "_aga_shadow", None)
+    if sh is not None and sh[0] == p._version and sh[1].dtype == dtype and sh[1].device == p.device:
+        return sh[1]
+    return p.detach().to(dtype)
+
+
+def _wgrad(a_t: torch.Tensor, b: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """a_t @ b with the result in the PARAMETER's dtype straight out of the GEMM (fp32 accumulators are written as they
+    are: no bf16 rounding of the weight gradient and no cast kernel)."""
+    if dtype == a_t.dtype:
+        return a_t @ b
+    return torch.mm(a_t, b, out_dtype=dtype)
+
+
+def gelu_bwd_colsum(dg: torch.Tensor, h: torch.Tensor):
+    """(dg * gelu'(h), column sums of that product) in one pass — at::gelu_backward + sum(0) of the Adapter backward."""
+    _require_cuda(dg, "dg")
+    rows, cols = h.shape
+    dg = dg if dg.is_contiguous() else dg.contiguous()
+    dh = torch.empty_like(h)
+    colsum = torch.empty(cols, dtype=torch.float32, device=h.device)
+    L.check(L.lib().aga_gelu_bwd_colsum(_ptr(dg), _ptr(h), _DTYPES[h.dtype], rows, cols, _ptr(dh), _ptr(colsum),
+                                        _stream_ptr(h.device)), "aga_gelu_bwd_colsum")
+    return dh, colsum
+
+
 class _AdapterLayerNormFn(torch.autograd.Function):
     """LN(x + W2 gelu(W1 x + b1) + b2): the Adapter (whisper/model.py:181-194) and the post-LayerNorm that replaces x
     (whisper/model.py:234-236, 244-246) as ONE autograd node.  The two small GEMMs stay cuBLAS; the residual add is
-    folded into the LayerNorm kernel, the gradient of b2 falls out of the LayerNorm backward (column sums of dx), and
-    dx = dx_ln + dh1 W1 is one addmm — three full-size elementwise / reduction passes fewer per adapter."""
+    folded into the LayerNorm kernel, the gradient of b2 falls out of the LayerNorm backward (column sums of dx), the
+    GELU backward and the gradient of b1 are one kernel, the weight gradients leave their GEMMs in fp32, and
+    dx = dx_ln + dh1 W1 is one addmm."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, gamma, beta, eps):
@@ -446,10 +478,10 @@ class _AdapterLayerNormFn(torch.autograd.Function):
         D = x.shape[-1]
         x2 = _rows(x, D)
         dt = x2.dtype
-        w1c, w2c = w1.detach().to(dt), w2.detach().to(dt)
-        h1 = torch.addmm(b1.detach().to(dt), x2, w1c.t())
+        w1c, w2c = cast_trainable(w1, dt), cast_trainable(w2, dt)
+        h1 = torch.addmm(cast_trainable(b1, dt), x2, w1c.t())
         g = torch.nn.functional.gelu(h1)
-        y = torch.addmm(b2.detach().to(dt), g, w2c.t())
+        y = torch.addmm(cast_trainable(b2, dt), g, w2c.t())
         g32 = gamma.detach().float().contiguous()
         be32 = beta.detach().float().contiguous()
         z, s, mean, rstd = _ln_fwd(x2, y, g32, be32, eps, True)
@@ -462,17 +494,15 @@ class _AdapterLayerNormFn(torch.autograd.Function):
     def backward(ctx, dz):
         x2, h1, g, s, mean, rstd, w1c, w2c, g32 = ctx.saved_tensors
         rows, D = x2.shape
+        dts = ctx.param_dtypes
         dz2 = _rows(dz.to(x2.dtype), D)
         ds, dgamma, dbeta, db2 = _ln_bwd(dz2, s, g32, mean, rstd, True, need_dxsum=True)
         dg = ds @ w2c                                  # (rows, bottleneck)
-        dw2 = ds.t() @ g                               # (D, bottleneck)
-        dh1 = torch.ops.aten.gelu_backward(dg, h1)
-        db1 = dh1.sum(0, dtype=torch.float32)
-        dw1 = dh1.t() @ x2                             # (bottleneck, D)
+        dw2 = _wgrad(ds.t(), g, dts[2])                # (D, bottleneck)
+        dh1, db1 = gelu_bwd_colsum(dg, h1)
+        dw1 = _wgrad(dh1.t(), x2, dts[0])              # (bottleneck, D)
         dx = torch.addmm(ds, dh1, w1c)                 # the residual branch's gradient rides the GEMM's beta = 1
-        dts = ctx.param_dtypes
-        return (dx.view(ctx.shape), dw1.to(dts[0]), db1.to(dts[1]), dw2.to(dts[2]), db2.to(dts[3]), dgamma.to(dts[4]),
-                dbeta.to(dts[5]), None)
+        return (dx.view(ctx.shape), dw1, db1.to(dts[1]), dw2, db2.to(dts[3]), dgamma.to(dts[4]), dbeta.to(dts[5]), None)
 
 
 def adapter_layer_norm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,

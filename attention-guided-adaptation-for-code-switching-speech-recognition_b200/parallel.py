@@ -19,19 +19,32 @@ import torch.distributed as dist
 class FlatGradBucket:
     """Contiguous gradient storage for the trainable parameters + its all-reduce."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None,
+                 shadow_dtype: Optional[torch.dtype] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             if p.dtype != torch.float32:
                 raise ValueError("trainable parameters are kept in fp32 (AMP master weights)")
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            self.views.append(self.flat[off: off + p.numel()].view_as(p))
+            p.grad = self.views[-1]
             off += p.numel()
+        # low-precision shadows of the trainable parameters (what autocast would re-cast on every use), refreshed by ONE
+        # multi-tensor copy per step instead of one cast kernel per parameter per use (ops.cast_trainable reads them)
+        self.shadow_flat = None
+        self.shadow_views: List[torch.Tensor] = []
+        if shadow_dtype is not None and dev.type == "cuda":
+            self.shadow_flat = torch.empty(self.numel, dtype=shadow_dtype, device=dev)
+            off = 0
+            for p in self.params:
+                self.shadow_views.append(self.shadow_flat[off: off + p.numel()].view_as(p))
+                off += p.numel()
         self.group = process_group
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._work = None
@@ -42,6 +55,35 @@ class FlatGradBucket:
 
     def zero_(self) -> None:
         self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def begin_step(self) -> None:
+        """Call before the forward pass of a (non-accumulating) step: drops ``p.grad`` so that autograd ASSIGNS this
+        step's gradients instead of launching one ``add_`` per parameter into the zeroed views, and refreshes the
+        low-precision parameter shadows.  ``gather_()`` after backward brings the gradients into the flat buffer."""
+        for p in self.params:
+            p.grad = None
+        if self.shadow_flat is not None:
+            with torch.no_grad():
+                torch._foreach_copy_(self.shadow_views, [p.detach() for p in self.params])
+            for p, v in zip(self.params, self.shadow_views):
+                p._aga_shadow = (p._version, v)
+
+    def gather_(self) -> None:
+        """p.grad (whatever autograd produced) -> the flat buffer, with one multi-tensor copy; p.grad become views again."""
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g)
+                dst.append(v)
+            p.grad = v
+        if src:
+            with torch.no_grad():
+                torch._foreach_copy_(dst, src)
 
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1

@@ -250,9 +250,44 @@ class AudioEncoder(nn.Module):
         self.ln_post = LayerNorm(n_state)
         self.n_layer = n_layer
 
+    def _stem_weights(self, dtype: torch.dtype):
+        """conv1 / conv2 kernels as GEMM operands: (D, n_mels*3) with columns (c, k), (D, 3*D) with columns (k, c)."""
+        w1, w2 = self.conv1.weight, self.conv2.weight
+        sig = (dtype, w1._version, w1.data_ptr(), w2._version, w2.data_ptr(), self.conv1.bias._version, self.conv2.bias._version)
+        c = self.__dict__.get("_stem_cache")
+        frozen = not (w1.requires_grad or w2.requires_grad or self.conv1.bias.requires_grad or self.conv2.bias.requires_grad)
+        if c is not None and c[0] == sig and (frozen or not torch.is_grad_enabled()):
+            return c[1]
+        ws = (w1.reshape(w1.shape[0], -1).to(dtype), self.conv1.bias.to(dtype),
+              w2.permute(0, 2, 1).reshape(w2.shape[0], -1).to(dtype), self.conv2.bias.to(dtype))
+        if frozen or not torch.is_grad_enabled():
+            ws = tuple(t.detach() for t in ws)
+            self.__dict__["_stem_cache"] = (sig, ws)
+        return ws
+
+    def stem(self, x: Tensor) -> Tensor:
+        """gelu(conv2(gelu(conv1(x)))).permute(0, 2, 1) (whisper/model.py:277-279): (B, n_mels, T) -> (B, T', D).
+
+        On a CUDA device both convolutions run as ONE cuBLAS GEMM each on token-major activations (k=3 windows are
+        gathered once; conv2's stride-2 windows are three row-strided slices): cuDNN serves these shapes with a
+        legacy sm_75 implicit-GEMM kernel that is 8x slower, and the token-major result needs no permute."""
+        if not x.is_cuda:
+            x = F.gelu(self.conv1(x))
+            return F.gelu(self.conv2(x)).permute(0, 2, 1)
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        w1, b1, w2, b2 = self._stem_weights(dt)
+        B, C, T = x.shape
+        cols = F.pad(x.to(dt), (1, 1)).unfold(2, 3, 1).permute(0, 2, 1, 3).reshape(B, T, C * 3)
+        with torch.autocast("cuda", enabled=False):
+            h = F.gelu(F.linear(cols, w1, b1))                                   # (B, T, D)
+            T2 = (T - 1) // 2 + 1
+            hp = F.pad(h, (0, 0, 1, 1))                                          # zero rows at t = -1 and t = T
+            span = 2 * (T2 - 1) + 1
+            cols2 = torch.cat([hp[:, k: k + span: 2] for k in range(3)], dim=-1)  # (B, T2, 3 D), columns (k, c)
+            return F.gelu(F.linear(cols2, w2, b2))
+
     def forward(self, x: Tensor) -> Tensor:
-        x = F.gelu(self.conv1(x))
-        x = F.gelu(self.conv2(x)).permute(0, 2, 1)
+        x = self.stem(x)
         assert x.shape[1:] == self.positional_embedding.shape, "incorrect audio shape"
         x = (x + self.positional_embedding).to(x.dtype)
         for block in self.blocks:

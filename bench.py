@@ -198,7 +198,7 @@ def main():
     torch.manual_seed(2022)
     model = build_model(args.model, dev)
     params = [p for p in model.parameters() if p.requires_grad]
-    bucket = FlatGradBucket(params)
+    bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16)
     opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01, fused=True,
                             capturable=not args.no_graph)
 
@@ -210,14 +210,15 @@ def main():
     model.static_shapes = True  # synthetic batches are already cut to the longest target: no host syncs in the step
 
     def eager_step(batch):
+        bucket.begin_step()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss, stats, weight = model(*batch)
         loss.backward()
+        bucket.gather_()
         bucket.all_reduce_mean_async()
         bucket.wait()
         bucket.clip_grad_norm_(1.0)
         opt.step()
-        bucket.zero_()
         return loss
 
     if args.no_graph:

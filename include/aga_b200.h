@@ -176,6 +176,14 @@ AGA_API int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t 
                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
                       void* stream);
 
+/* Backward of the Adapter's GELU fused with the bias gradient of its first Linear (W/model.py:181-194,
+ * Adapter.model = Linear -> GELU -> Linear).  dh = dg * gelu'(h) (exact erf form, fp32 math,
+ * rounded to dtype) and colsum[c] = sum_rows dh[r, c] (of the rounded values), in one pass.
+ *   dg, h, dh : (rows, cols) contiguous, dtype AGA_F32 or AGA_BF16, 16-byte aligned; cols a multiple of 16 B / sizeof(dtype)
+ *   colsum    : (cols) fp32, OVERWRITTEN */
+AGA_API int aga_gelu_bwd_colsum(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh, float* colsum,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

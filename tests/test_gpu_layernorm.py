@@ -104,3 +104,46 @@ def test_adapter_layer_norm_matches_reference_expression(A, dtype, tol, shape, D
     for a, b in zip(g1, g2):
         assert a.dtype == torch.float32
         torch.testing.assert_close(a, b, rtol=tol, atol=tol * float(b.abs().max()))
+
+
+@pytest.mark.parametrize("dtype,rows,cols", [(torch.float32, 1000, 96), (torch.bfloat16, 24000, 192), (torch.bfloat16, 333, 256),
+                                             (torch.bfloat16, 7, 320), (torch.float32, 5, 192)])
+def test_gelu_bwd_colsum_matches_aten(A, dtype, rows, cols):
+    """dh = dg * gelu'(h) and its column sums (the Adapter's first-bias gradient, whisper/model.py:181-194) in one pass."""
+    from aga_b200 import ops
+    g = torch.Generator().manual_seed(rows + cols)
+    h = (2.0 * torch.randn(rows, cols, generator=g)).to(dtype).cuda()
+    dg = torch.randn(rows, cols, generator=g).to(dtype).cuda()
+    dh, colsum = ops.gelu_bwd_colsum(dg, h)
+    ref = torch.ops.aten.gelu_backward(dg, h)
+    # fp32 oracle of the exact (erf) derivative
+    x64 = h.double()
+    exact = dg.double() * (0.5 * (1 + torch.erf(x64 / 2 ** 0.5)) + x64 * torch.exp(-0.5 * x64 * x64) / (2 * np.pi) ** 0.5)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    torch.testing.assert_close(dh.double(), exact, rtol=tol, atol=tol)
+    torch.testing.assert_close(dh.float(), ref.float(), rtol=tol, atol=tol)
+    torch.testing.assert_close(colsum, dh.float().sum(0), rtol=1e-4, atol=1e-3)
+
+
+def test_conv_stem_gemm_matches_conv1d(A):
+    """AudioEncoder.stem (two GEMMs on token-major activations) == gelu(conv2(gelu(conv1(x)))).permute(0,2,1)
+    (whisper/model.py:277-279)."""
+    from aga_b200 import whisper_model as W
+    enc = W.AudioEncoder(80, 1500, 384, 6, 1).cuda()
+    W.seeded_init_(enc, 1)
+    for T in (3000, 261, 100):
+        x = torch.randn(2, 80, T, generator=torch.Generator().manual_seed(T)).cuda()
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            ref = F.gelu(F.conv1d(F.gelu(F.conv1d(x, enc.conv1.weight, enc.conv1.bias, padding=1)), enc.conv2.weight,
+                                  enc.conv2.bias, stride=2, padding=1)).permute(0, 2, 1)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        got = enc.stem(x)
+        assert got.shape == ref.shape
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got16 = enc.stem(x)
+        assert got16.dtype == torch.bfloat16
+        torch.testing.assert_close(got16.float(), ref, rtol=2e-2, atol=2e-2)

@@ -43,6 +43,16 @@ def _worker(rank, world, port, q):
         assert model[2].bias.grad.data_ptr() == bucket.flat[-4:].data_ptr()
         norm = bucket.clip_grad_norm_(1e-3)
         assert torch.linalg.vector_norm(bucket.flat) <= 1e-3 + 1e-6 and norm > 0
+        # assign-then-gather step protocol: same flat contents as accumulating into zeroed views
+        bucket.zero_()
+        model(x).pow(2).mean().backward()
+        ref = bucket.flat.clone()
+        bucket.begin_step()
+        assert all(p.grad is None for p in bucket.params)
+        model(x).pow(2).mean().backward()
+        assert model[2].bias.grad.data_ptr() != bucket.flat[-4:].data_ptr()
+        bucket.gather_()
+        assert torch.equal(bucket.flat, ref) and model[2].bias.grad.data_ptr() == bucket.flat[-4:].data_ptr()
         stats = all_reduce_stats({"loss": loss.detach(), "acc": torch.tensor(float(rank)), "cer": None},
                                  torch.tensor(float(x.shape[0])))
         assert stats["cer"] is None and abs(float(stats["acc"]) - 0.5) < 1e-6

@@ -11,16 +11,17 @@ def main():
     model = bench.build_model("small", dev)
     from aga_b200.parallel import FlatGradBucket
     params = [p for p in model.parameters() if p.requires_grad]
-    bucket = FlatGradBucket(params)
+    bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16)
     opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01, fused=True)
     data = tuple(t.to(dev) for t in bench.synthetic_batch(16, 64, 2022))
     def step():
+        bucket.begin_step()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss, stats, w = model(*data, static_text=True)
         loss.backward()
+        bucket.gather_()
         bucket.clip_grad_norm_(1.0)
         opt.step()
-        bucket.zero_()
     for _ in range(3): step()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
