@@ -1015,6 +1015,363 @@ attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restr
   }
 }
 
+
+// =============================================================================================== backward, Tq <= 128
+// Decoder cross attention (Tq = text length <= 128, Tk = 1500): one query tile, so the roles of the persistent kernel
+// are swapped — Q, dO and the row statistics stay RESIDENT (per-thread scalars: lane = query row) and the CTA streams a
+// chunk of key tiles past them.  dV_j and dK_j are complete after one tile (no accumulation across tiles: they are
+// drained and stored as bf16 directly), dQ accumulates in TMEM over the chunk and is added once into the fp32
+// accumulator (a few chunk-CTAs per (batch, head) keep 148 SMs busy).  No per-item pipeline restart: with the
+// persistent kernel every tile was an item boundary (97 us per call, 120 TFLOP/s).
+//   S  = Q K_j^T      cols [0,128)     SS, both K-major, N = 128
+//   dP = dO V_j^T     cols [128,256)   SS, both K-major, N = 128
+//   softmax warps (lane = query, 32 keys each): P = exp2(S c - lse), dS = P (dP - delta) -> bf16 rows [query][key] in
+//   two 64-key swizzled smem panels each
+//   dV_j = P^T dO     [256,320)   A = P panels read MN-major (M = keys), B = dO rows (MN-major)
+//   dK_j = dS^T Q     [320,384)   A = dS panels read MN-major,           B = Q rows (MN-major)
+//   dQ  += dS K_j     [384,448)   A = dS panels read K-major,           B = K_j rows (MN-major)
+// Warps: 0-15 softmax (quadrant = warp & 3, key slice = warp >> 2), 16 TMA, 17 MMA, 18-21 drain (dV_j, dK_j per tile,
+// dQ at the end).  The drain warps never store to global memory themselves: a lane-per-row store of 16-byte pieces
+// costs one L1 transaction per lane per instruction (4000 cycles per tile, and it starves the tensor core's own
+// shared-memory operand reads).  Rows go to swizzled staging tiles and leave through the TMA unit (tile stores for
+// dV_j / dK_j, which also clips keys past Tk; a bulk reduce-add for dQ).
+constexpr int kQrSoftmaxWarps = 16;
+constexpr int kQrTmaWarp = 16, kQrMmaWarp = 17, kQrDrainWarp0 = 18;
+constexpr int kQrThreads = 22 * 32;
+constexpr uint32_t kColQS = 0, kColQdP = 128, kColQdV = 256, kColQdK = 320, kColQdQ = 384;
+constexpr int kQrKStages = 3;  // K_j stays until dQ(j) has run, two tiles after its load: a third buffer keeps TMA ahead
+
+struct QrSmem {
+  uint64_t qdo_full, k_full[kQrKStages], k_empty[kQrKStages], v_full[2], v_empty[2];
+  uint64_t s_full, dp_full, s_free, dp_free, p_ready, pds_free, dvk_full, dvk_free, dq_full;
+  uint32_t tmem_base;
+};
+// Q, dO | 3 x K, 2 x V | P panels (2) | dS panels (2) | dV, dK staging (bf16 rows; reused as fp32 dQ staging at the end)
+constexpr size_t kQrSmemBytes = 1024 + size_t(2 + kQrKStages + 2) * kTileBytes + 4 * size_t(kPanelBytes) + 2 * size_t(kTileBytes) + sizeof(QrSmem);
+static_assert(kQrSmemBytes <= 227 * 1024, "q-resident backward kernel exceeds the shared-memory limit");
+
+struct QrArgs {
+  int B, H, Tq, Tk;
+  int tiles_per_cta;  // key tiles per chunk
+  const float* stats;  // (B, H, 1, 2, 128): lse * log2(e) | delta, zero past Tq
+  float* dq_accum;     // (B, H, 1, 2, 128, 32) fp32, zero-initialised, chunk-swizzled like the persistent kernel's
+};
+
+// one 128-byte bf16 row (64 values, scaled) from two 32-column TMEM loads into a SWIZZLE_128B staging row
+__device__ __forceinline__ void stage_row_bf16(uint32_t row_addr, int row, const uint32_t (&lo)[32], const uint32_t (&hi)[32], float scale) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t* v = c < 4 ? lo : hi;
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * (c & 3) + 2 * e]) * scale, __uint_as_float(v[8 * (c & 3) + 2 * e + 1]) * scale);
+      w[e] = *reinterpret_cast<uint32_t*>(&hb);
+    }
+    sts128(row_addr + uint32_t((c ^ (row & 7)) * 16), w[0], w[1], w[2], w[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kQrThreads, 1)
+attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                        const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                        const __grid_constant__ CUtensorMap map_dk, const __grid_constant__ CUtensorMap map_dv,
+                        const QrArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + kTileBytes;
+  uint8_t* sK = sdO + kTileBytes;       // kQrKStages stages
+  uint8_t* sV = sK + kQrKStages * kTileBytes;  // 2 stages
+  uint8_t* sP = sV + 2 * kTileBytes;    // 2 panels: keys [0,64), [64,128)
+  uint8_t* sdS = sP + 2 * kPanelBytes;  // 2 panels
+  uint8_t* sStage = sdS + 2 * kPanelBytes;  // dV rows | dK rows (32 rows = 4 KiB per drain warp each)
+  QrSmem* sb = reinterpret_cast<QrSmem*>(sStage + 2 * kTileBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_kt = (a.Tk + kBlockN - 1) / kBlockN;
+  const int kt0 = blockIdx.x * a.tiles_per_cta;
+  const int n_my = min(a.tiles_per_cta, n_kt - kt0);  // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sb->qdo_full, 1);
+    for (int s = 0; s < kQrKStages; ++s) {
+      mbar_init(&sb->k_full[s], 1);
+      mbar_init(&sb->k_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sb->v_full[s], 1);
+      mbar_init(&sb->v_empty[s], 1);
+    }
+    mbar_init(&sb->s_full, 1);
+    mbar_init(&sb->dp_full, 1);
+    mbar_init(&sb->s_free, kQrSoftmaxWarps);
+    mbar_init(&sb->dp_free, kQrSoftmaxWarps);
+    mbar_init(&sb->p_ready, kQrSoftmaxWarps);
+    mbar_init(&sb->pds_free, 1);
+    mbar_init(&sb->dvk_full, 1);
+    mbar_init(&sb->dvk_free, 4);
+    mbar_init(&sb->dq_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kQrMmaWarp) {
+    tmem_alloc(&sb->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == kQrTmaWarp && lane == 0) {
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_k);
+    prefetch_tensormap(&map_v);
+    prefetch_tensormap(&map_do);
+    prefetch_tensormap(&map_dk);
+    prefetch_tensormap(&map_dv);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sb->tmem_base;
+
+  if (warp == kQrTmaWarp) {
+    // ============================== TMA producer ==============================
+    TL_DECL(lane == 0 ? 3 : -1);
+    TL(40);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&sb->qdo_full, 2 * kTileBytes);
+      tma_load_4d(sQ, &map_q, &sb->qdo_full, 0, h, 0, b);
+      tma_load_4d(sdO, &map_do, &sb->qdo_full, 0, h, 0, b);
+    }
+    for (int jj = 0; jj < n_my; ++jj) {
+      const int s = jj & 1, sk = jj % kQrKStages;
+      const uint32_t ph = (jj >> 1) & 1;
+      mbar_wait(&sb->k_empty[sk], ((jj / kQrKStages) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sb->k_full[sk], kTileBytes);
+        tma_load_4d(sK + sk * kTileBytes, &map_k, &sb->k_full[sk], 0, h, (kt0 + jj) * kBlockN, b);
+      }
+      mbar_wait(&sb->v_empty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sb->v_full[s], kTileBytes);
+        tma_load_4d(sV + s * kTileBytes, &map_v, &sb->v_full[s], 0, h, (kt0 + jj) * kBlockN, b);
+      }
+      TL(42);
+    }
+    TL_END();
+  } else if (warp == kQrMmaWarp) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc_s = make_idesc_bf16(kBlockM, kBlockN, 0, 0);    // S, dP: A and B K-major, N = 128
+    constexpr uint32_t idesc_mn = make_idesc_bf16(kBlockN, kHeadDim, 1, 1);  // dV, dK: A and B MN-major
+    constexpr uint32_t idesc_dq = make_idesc_bf16(kBlockM, kHeadDim, 0, 1);  // dQ: A K-major, B MN-major
+    const uint64_t dQd = make_smem_desc_sw128(smem_u32(sQ)), ddO = make_smem_desc_sw128(smem_u32(sdO));
+    const uint64_t aP = make_smem_desc_sw128_mn(smem_u32(sP), kPanelBytes);
+    const uint64_t adS = make_smem_desc_sw128_mn(smem_u32(sdS), kPanelBytes);
+    auto issue_s = [&](int jj) {
+      const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + (jj % kQrKStages) * kTileBytes));
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(tmem + kColQS, dQd + uint64_t(kk * 2), dk + uint64_t(kk * 2), idesc_s, kk > 0);
+        tc_commit(&sb->s_full);
+      }
+      __syncwarp();
+    };
+    auto issue_dp = [&](int jj) {
+      const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + (jj & 1) * kTileBytes));
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(tmem + kColQdP, ddO + uint64_t(kk * 2), dv + uint64_t(kk * 2), idesc_s, kk > 0);
+        tc_commit(&sb->dp_full);
+        tc_commit(&sb->v_empty[jj & 1]);
+      }
+      __syncwarp();
+    };
+    TL_DECL(lane == 0 ? 0 : -1);
+    TL(9);
+    mbar_wait(&sb->qdo_full, 0);
+    mbar_wait(&sb->k_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    mbar_wait(&sb->v_full[0], 0);
+    tc_fence_after();
+    issue_dp(0);
+    for (int jj = 0; jj < n_my; ++jj) {
+      const uint32_t par = jj & 1;
+      TL(10);
+      if (jj + 1 < n_my) {
+        const uint32_t ph1 = ((jj + 1) >> 1) & 1;
+        mbar_wait(&sb->k_full[(jj + 1) % kQrKStages], ((jj + 1) / kQrKStages) & 1);
+        mbar_wait(&sb->s_free, par);
+        tc_fence_after();
+        issue_s(jj + 1);
+        TL(11);
+        mbar_wait(&sb->v_full[(jj + 1) & 1], ph1);
+        mbar_wait(&sb->dp_free, par);
+        tc_fence_after();
+        issue_dp(jj + 1);
+        TL(12);
+      }
+      mbar_wait(&sb->p_ready, par);
+      if (jj > 0) mbar_wait(&sb->dvk_free, (jj - 1) & 1);
+      TL(13);
+      tc_fence_after();
+      const uint64_t dkm = make_smem_desc_sw128(smem_u32(sK + (jj % kQrKStages) * kTileBytes));
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kBlockM / 16; ++kk)  // contraction over the 128 queries: 16 rows = 2048 bytes in both operands
+          mma_ss(tmem + kColQdV, aP + uint64_t(kk * 128), ddO + uint64_t(kk * 128), idesc_mn, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < kBlockM / 16; ++kk)
+          mma_ss(tmem + kColQdK, adS + uint64_t(kk * 128), dQd + uint64_t(kk * 128), idesc_mn, kk > 0);
+        tc_commit(&sb->dvk_full);
+#pragma unroll
+        for (int kk = 0; kk < kBlockN / 16; ++kk) {  // contraction over the 128 keys: 4 k-steps per 64-key panel
+          const uint64_t ads_k = make_smem_desc_sw128(smem_u32(sdS + (kk >> 2) * kPanelBytes)) + uint64_t((kk & 3) * 2);
+          mma_ss(tmem + kColQdQ, ads_k, dkm + uint64_t(kk * 128), idesc_dq, (jj > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&sb->pds_free);
+        tc_commit(&sb->k_empty[jj % kQrKStages]);
+        if (jj == n_my - 1) tc_commit(&sb->dq_full);
+      }
+      __syncwarp();
+      TL(14);
+    }
+    TL_END();
+  } else if (warp < kQrSoftmaxWarps) {
+    // ============================== P / dS producers ==============================
+    const int quad = warp & 3, cs = warp >> 2;
+    const uint32_t lane_base = uint32_t(quad * 32);
+    const int row = int(lane_base) + lane;  // query row
+    const float* st = a.stats + (int64_t(b) * a.H + h) * (2 * kBlockM);
+    const float neg_lse = -st[row], delta = st[kBlockM + row];
+    const uint32_t t_s = tmem + (lane_base << 16) + kColQS + cs * 32;
+    const uint32_t t_dp = tmem + (lane_base << 16) + kColQdP + cs * 32;
+    const uint32_t p_row = smem_u32(sP + (cs >> 1) * kPanelBytes + row * 128);
+    const uint32_t ds_row = smem_u32(sdS + (cs >> 1) * kPanelBytes + row * 128);
+    const float2 sc2 = make_float2(kScaleLog2, kScaleLog2), nl2 = make_float2(neg_lse, neg_lse);
+    const float2 nd2 = make_float2(-delta, -delta);
+    TL_DECL((warp == 0 && lane == 0) ? 1 : -1);
+    TL(19);
+    for (int jj = 0; jj < n_my; ++jj) {
+      const uint32_t par = jj & 1;
+      uint32_t pk[16], dd[16];
+      TL(20);
+      mbar_wait(&sb->s_full, par);
+      TL(21);
+      tc_fence_after();
+      {
+        uint32_t sv[32];
+        tmem_ld32(t_s, sv);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->s_free);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nl2);
+          __nv_bfloat162 hb = __floats2bfloat162_rn(ex2(x.x), ex2(x.y));
+          pk[i] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+      }
+      TL(23);
+      mbar_wait(&sb->dp_full, par);
+      tc_fence_after();
+      {
+        uint32_t dv[32];
+        tmem_ld32(t_dp, dv);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->dp_free);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 t = __fadd2_rn(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), nd2);
+          const float2 d = __fmul2_rn(make_float2(__uint_as_float(pk[i] << 16), __uint_as_float(pk[i] & 0xffff0000u)), t);
+          __nv_bfloat162 hb = __floats2bfloat162_rn(d.x, d.y);
+          dd[i] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+      }
+      TL(25);
+      if (jj > 0) mbar_wait(&sb->pds_free, (jj - 1) & 1);  // the previous tile's GEMMs have read the panels
+      TL(26);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {  // 16-byte chunk (cs & 1) * 4 + q4 of the 128-byte row, XOR-swizzled with (row & 7)
+        const uint32_t off = uint32_t((((cs & 1) * 4 + q4) ^ (row & 7)) * 16);
+        sts128(p_row + off, pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        sts128(ds_row + off, dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->p_ready);
+      TL(27);
+    }
+    TL_END();
+  } else if (warp >= kQrDrainWarp0) {
+    // ============================== drain: dV_j, dK_j per tile; dQ at the end ==============================
+    const int w4 = warp & 3;
+    const uint32_t lane_base = uint32_t(w4 * 32);
+    const int r = int(lane_base) + lane;
+    const uint32_t t_base = tmem + (lane_base << 16);
+    uint8_t* st_dv = sStage + w4 * (32 * 128);               // this warp's 32 rows of the dV staging tile
+    uint8_t* st_dk = sStage + kTileBytes + w4 * (32 * 128);
+    const uint32_t row_dv = smem_u32(st_dv + lane * 128), row_dk = smem_u32(st_dk + lane * 128);
+    TL_DECL((warp == kQrDrainWarp0 && lane == 0) ? 2 : -1);
+    for (int jj = 0; jj < n_my; ++jj) {
+      TL(30);
+      const int key0 = (kt0 + jj) * kBlockN + int(lane_base);
+      mbar_wait(&sb->dvk_full, jj & 1);
+      TL(31);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld32(t_base + kColQdV, v0);
+      tmem_ld32(t_base + kColQdV + 32, v1);
+      tmem_wait_ld();
+      if (lane == 0) bulk_wait_group_read0();  // the previous tile's stores have read the staging rows
+      __syncwarp();
+      stage_row_bf16(row_dv, r, v0, v1, 1.0f);
+      tmem_ld32(t_base + kColQdK, v0);
+      tmem_ld32(t_base + kColQdK + 32, v1);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->dvk_free);
+      stage_row_bf16(row_dk, r, v0, v1, 0.125f);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&map_dv, st_dv, 0, h, key0, b);
+        tma_store_4d(&map_dk, st_dk, 0, h, key0, b);
+        bulk_commit_group();
+      }
+      TL(32);
+    }
+    // dQ: this warp's 32 rows of the (b, h) tile, two 32-column fp32 halves, staged (16-byte chunks XOR-swizzled with
+    // the row, the accumulator's own layout) and added with one bulk reduction each
+    mbar_wait(&sb->dq_full, 0);
+    TL(33);
+    tc_fence_after();
+    float* gtile = a.dq_accum + (int64_t(b) * a.H + h) * (kBlockM * kHeadDim) + lane_base * 32;
+    if (lane == 0) bulk_wait_group_read0();
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld32(t_base + kColQdQ + half * 32, v);
+      tmem_wait_ld();
+      const uint32_t my_row = half ? row_dk : row_dv;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sts128(my_row + ((e ^ (lane & 7)) * 16), v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_reduce_add_f32(gtile + half * (kBlockM * 32), half ? st_dk : st_dv, 32 * 128);
+    }
+    if (lane == 0) bulk_wait_group_read0();
+    TL(34);
+    TL_END();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kQrMmaWarp) tmem_dealloc(tmem, kTmemCols);
+}
+
 }  // namespace
 
 bool attn_tc_bwd_supported(const aga_attn_params& p) { return attn_tc_supported(p); }
@@ -1046,18 +1403,36 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
   if ((st = make_map(&mv, p.v, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, kBlockN)) != AGA_OK) return st;
   if ((st = make_map(&mdo, bp.dout, p.B, p.H, p.Tq, p.o_stride_b, p.o_stride_t, kBlockM)) != AGA_OK) return st;
   const int n_kt = (p.Tk + kBlockN - 1) / kBlockN;
-  const int n_items = p.B * p.H * n_kt;
-  BwdArgs a{p.B, p.H, p.Tq, p.Tk, n_items, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, stats, dq_acc,
-            static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv)};
-  AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBwdSmemBytes)));
   static const int n_sm = []() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n > 0 ? n : 148;
   }();
+#ifndef AGA_BWD_NO_QRES
+  if (n_qt == 1) {
+    // one query tile (decoder cross attention): Q-resident kernel, ~4 waves of chunk-CTAs
+    const int64_t tiles = int64_t(p.B) * p.H * n_kt;
+    int per = int((tiles + int64_t(n_sm) * 4 - 1) / (int64_t(n_sm) * 4));
+    per = std::max(1, std::min(per, n_kt));
+    const int n_chunks = (n_kt + per - 1) / per;
+    QrArgs qa{p.B, p.H, p.Tq, p.Tk, per, stats, dq_acc};
+    CUtensorMap mdk, mdv;  // 32-row boxes: one store per drain warp
+    if ((st = make_map(&mdk, bp.dk, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, 32)) != AGA_OK) return st;
+    if ((st = make_map(&mdv, bp.dv, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, 32)) != AGA_OK) return st;
+    AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_qres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kQrSmemBytes)));
+    attn_bwd_tc_qres_kernel<<<dim3(n_chunks, p.H, p.B), kQrThreads, kQrSmemBytes, s>>>(mq, mk, mv, mdo, mdk, mdv, qa);
+    AGA_AFTER_LAUNCH();
+  } else
+#endif
+  {
+  const int n_items = p.B * p.H * n_kt;
+  BwdArgs a{p.B, p.H, p.Tq, p.Tk, n_items, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, stats, dq_acc,
+            static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv)};
+  AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBwdSmemBytes)));
   const unsigned grid = unsigned(std::min(n_items, n_sm));  // persistent: one CTA per SM walks the items
   attn_bwd_tc_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(mq, mk, mv, mdo, a);
   AGA_AFTER_LAUNCH();
+  }
   const int64_t total8 = int64_t(p.B) * p.Tq * p.H * (kHeadDim / 8);
   const unsigned gx = unsigned(std::min<int64_t>((total8 + 255) / 256, 148 * 16));
   attn_bwd_dq_convert_kernel<<<gx ? gx : 1, 256, 0, s>>>(dq_acc, static_cast<__nv_bfloat16*>(bp.dq), p.q_stride_b,

@@ -71,7 +71,9 @@ def test_tc_full_size_properties(A):
 
 @pytest.mark.parametrize("B,H,Tq,Tk,amp", [
     (1, 1, 128, 128, 1.0), (1, 1, 1, 1, 1.0), (1, 2, 257, 129, 1.0), (2, 3, 300, 200, 1.0), (1, 2, 64, 1500, 1.0),
-    (1, 2, 1500, 1500, 1.0), (1, 2, 512, 640, 3.0)])
+    (1, 2, 1500, 1500, 1.0), (1, 2, 512, 640, 3.0),
+    # one query tile -> the Q-resident kernel (decoder cross attention): ragged rows / keys, several chunk CTAs
+    (2, 3, 100, 1500, 1.0), (1, 2, 128, 700, 2.0), (3, 2, 5, 64, 1.0), (16, 12, 64, 1500, 1.0), (1, 1, 33, 129, 1.0)])
 def test_tc_backward_vs_oracle(A, B, H, Tq, Tk, amp):
     """dQ/dK/dV of the 5-GEMM tcgen05 backward (dQ via fp32 red.add accumulation) vs the fp64 oracle: 2e-2 of the
     gradient's scale (north-star bf16 tolerance)."""

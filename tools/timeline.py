@@ -39,7 +39,9 @@ def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
     B, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (2, 2)  # 16 12 = every SM busy
     T = 1500
-    q, k, v = (torch.randn(B, T, H * 64, device="cuda").bfloat16().requires_grad_() for _ in range(3))
+    Tq = 64 if which == "cross" else T  # "cross": the Q-resident backward kernel (decoder cross attention)
+    q = torch.randn(B, Tq, H * 64, device="cuda").bfloat16().requires_grad_()
+    k, v = (torch.randn(B, T, H * 64, device="cuda").bfloat16().requires_grad_() for _ in range(2))
     buf = torch.zeros(8 * 4096, dtype=torch.int64, device="cuda")
     out, _, _ = A.qkv_attention(q, k, v, H)  # warm
     do = torch.randn_like(out)
