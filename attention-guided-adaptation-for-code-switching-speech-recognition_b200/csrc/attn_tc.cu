@@ -114,10 +114,28 @@ struct FwdArgs {
   float* lse;
 };
 
+// 32 fp32 TMEM columns (scaled) -> the bf16 half `half` (64 bytes) of a 128-byte row of a SWIZZLE_128B staging tile
+__device__ __forceinline__ void stage_half_row_bf16(uint32_t row_addr, int row, int half, const uint32_t (&v)[32], float scale) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 2 * e]) * scale, __uint_as_float(v[8 * c + 2 * e + 1]) * scale);
+      w[e] = *reinterpret_cast<uint32_t*>(&hb);
+    }
+    sts128(row_addr + uint32_t(((half * 4 + c) ^ (row & 7)) * 16), w[0], w[1], w[2], w[3]);
+  }
+}
+__device__ __forceinline__ void stage_row_bf16(uint32_t row_addr, int row, const uint32_t (&lo)[32], const uint32_t (&hi)[32], float scale) {
+  stage_half_row_bf16(row_addr, row, 0, lo, scale);
+  stage_half_row_bf16(row_addr, row, 1, hi, scale);
+}
+
 template <int NT>
 __global__ void __launch_bounds__(FwdCfg<NT>::kThreads, NT == 1 ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                   const __grid_constant__ CUtensorMap map_v, const FwdArgs a) {
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using Cfg = FwdCfg<NT>;
@@ -159,6 +177,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     prefetch_tensormap(&map_q);
     prefetch_tensormap(&map_k);
     prefetch_tensormap(&map_v);
+    prefetch_tensormap(&map_o);
   }
   tc_fence_before();
   __syncthreads();
@@ -349,28 +368,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       CTA_MARK(6);
       TL_END();
-      // ---- epilogue: O / l -> bf16 -> global ; lse
+      // ---- epilogue: O / l -> bf16 rows staged in this tile's Q buffer (its last S GEMM is long done) -> one TMA tile
+      //      store per warp (rows past Tq are clipped).  A lane-per-row store of 16-byte pieces costs one L1 transaction per
+      //      lane per instruction and was 7 % of the CTA's lifetime.
       mbar_wait(&sb->pv_done[t], (n_kt - 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l;
-      __nv_bfloat16* orow = a.out + int64_t(b) * a.o_sb + int64_t(row) * a.o_st + h * kHeadDim;
+      {
+        uint8_t* stage = sQ + t * kTileBytes + (warp & 3) * (32 * 128);
 #pragma unroll 1
-      for (int c = 0; c < kHeadDim / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_o + c * 32, r);
-        tmem_wait_ld();
-        if (row < a.Tq) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 2 * e]) * inv,
-                                                        __uint_as_float(r[8 * i + 2 * e + 1]) * inv);
-              w[e] = *reinterpret_cast<uint32_t*>(&hb);
-            }
-            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
+        for (int c = 0; c < kHeadDim / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_o + c * 32, r);
+          tmem_wait_ld();
+          stage_half_row_bf16(smem_u32(stage + lane * 128), lane, c, r, inv);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&map_o, stage, 0, h, row0 + t * kBlockM + int(lane_base), b);
+          bulk_commit_group();
+          bulk_wait_group_read0();  // the staging rows must outlive the store's reads (the CTA exits next)
         }
       }
       if (row < a.Tq && a.lse) a.lse[(int64_t(b) * a.H + h) * a.Tq + row] = (m_used + log2f(l)) * kLn2;
@@ -425,6 +443,8 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
   if ((st = make_map(&mq, p.q, p.B, p.H, p.Tq, p.q_stride_b, p.q_stride_t, kBlockM)) != AGA_OK) return st;
   if ((st = make_map(&mk, p.k, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, kBlockN)) != AGA_OK) return st;
   if ((st = make_map(&mv, p.v, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, kBlockN)) != AGA_OK) return st;
+  CUtensorMap mo;  // 32-row boxes: one store per softmax warp
+  if ((st = make_map(&mo, p.out, p.B, p.H, p.Tq, p.o_stride_b, p.o_stride_t, 32)) != AGA_OK) return st;
   FwdArgs a{p.B, p.H, p.Tq, p.Tk, p.o_stride_b, p.o_stride_t, static_cast<__nv_bfloat16*>(p.out), p.lse};
 #ifdef AGA_FWD_TWO_TILES  // one CTA per SM, two query tiles sharing each K/V tile
   constexpr int NT = 2;
@@ -434,7 +454,7 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
   AGA_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     int(FwdCfg<NT>::kSmemBytes)));
   dim3 grid((p.Tq + NT * kBlockM - 1) / (NT * kBlockM), p.H, p.B);
-  attn_fwd_tc_kernel<NT><<<grid, FwdCfg<NT>::kThreads, FwdCfg<NT>::kSmemBytes, s>>>(mq, mk, mv, a);
+  attn_fwd_tc_kernel<NT><<<grid, FwdCfg<NT>::kThreads, FwdCfg<NT>::kSmemBytes, s>>>(mq, mk, mv, mo, a);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }
@@ -534,6 +554,7 @@ __device__ __forceinline__ void store_row_chunk(__nv_bfloat16* dst, const uint32
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                   const __grid_constant__ CUtensorMap map_dk, const __grid_constant__ CUtensorMap map_dv,
                    const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -592,6 +613,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     prefetch_tensormap(&map_k);
     prefetch_tensormap(&map_v);
     prefetch_tensormap(&map_do);
+    prefetch_tensormap(&map_dk);
+    prefetch_tensormap(&map_dv);
   }
   tc_fence_before();
   __syncthreads();
@@ -775,6 +798,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #ifndef AGA_BWD_NO_TOKEN
     if (g == 1 && total_tiles > 0) named_bar_arrive(4, 512);  // half 0 may run the first phase 1
 #endif
+    const bool issuer = (warp & 7) == 0 && lane == 0;  // issues this half's dV_j / dK_j tile stores
     TL_DECL(((warp & 7) == 0 && lane == 0) ? 1 + g : -1);
     int c = 0;
     for (int it = 0; it < my_items; ++it) {
@@ -859,6 +883,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           }
         }
         tmem_st16(t_dp, dd);
+        if (i == 0 && it > 0) {  // this panel staged the previous item's dV_j / dK_j: its tile store must have read it
+          if (issuer) bulk_wait_group_read0();
+          named_bar_sync(6 + g, 256);
+        }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)  // 16-byte chunk sub*4 + q4 = queries 32 sub + 8 q4 .. + 7, XOR-swizzled with (row & 7)
           sts128(dsrow + (((sub * 4 + q4) ^ (r & 7)) * 16), dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
@@ -869,13 +897,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0) mbar_arrive(&sb->ds_ready[g]);
         TL(25);
       }
-      // ---- item done for this half: half 0's warps store dV_j (final after both streams' last dV MMA), half 1's warps
+      // ---- item done for this half: half 0's warps hand out dV_j (final after both streams' last dV MMA), half 1's warps
       //      dK_j.  Half 0 reads dV before its next p_ready arrival (which gates the next item's overwriting dV MMA);
-      //      half 1 signals dk_read, which gates the next item's overwriting dK MMA.
+      //      half 1 signals dk_read, which gates the next item's overwriting dK MMA.  The rows are staged (bf16, swizzled)
+      //      in the dS^T panel this half writes NEXT — free once the dQ GEMM that read it is done, the very wait the next
+      //      tile's phase 2 takes — and leave as one TMA tile store per half (keys past Tk are clipped).  Lane-per-row
+      //      global stores cost one L1 transaction per lane per instruction and starved the tensor core's operand reads:
+      //      the item boundary was 4800 cycles longer than a tile.
       {
         int kt, h, b;
         decode(it, kt, h, b);
-        const int key = kt * kBlockN + r;
         mbar_wait(g == 0 ? &sb->dv_final : &sb->dk_final, it & 1);
         tc_fence_after();
         uint32_t v[32];
@@ -886,13 +917,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&sb->dk_read);
         }
-        if (key < a.Tk) {
-          __nv_bfloat16* dst = (g == 0 ? a.dv + int64_t(b) * a.v_sb + int64_t(key) * a.v_st
-                                       : a.dk + int64_t(b) * a.k_sb + int64_t(key) * a.k_st) + h * kHeadDim + sub * 32;
-          store_row_chunk(dst, v, g == 0 ? 1.0f : 0.125f);
+        if (g == 0) {
+          if (c >= 2) mbar_wait(&sb->ds_free[c & 1], ((c >> 1) - 1) & 1);
+        } else if (c >= 1) {
+          mbar_wait(&sb->ds_free[(c - 1) & 1], ((c - 1) >> 1) & 1);
+        }
+        uint8_t* panel = sdS + (g == 0 ? (c & 1) : 2) * kPanelBytes;
+        stage_half_row_bf16(smem_u32(panel + r * 128), r, sub, v, g == 0 ? 1.0f : 0.125f);
+        fence_proxy_async_smem();
+        named_bar_sync(6 + g, 256);
+        if (issuer) {
+          tma_store_4d(g == 0 ? &map_dv : &map_dk, panel, 0, h, kt * kBlockN, b);
+          bulk_commit_group();
         }
       }
     }
+    if (issuer) bulk_wait_group_read0();
     CTA_MARK(6);
     TL_END();
   } else if (warp < kBwdTmaWarp) {
@@ -1056,21 +1096,6 @@ struct QrArgs {
   const float* stats;  // (B, H, 1, 2, 128): lse * log2(e) | delta, zero past Tq
   float* dq_accum;     // (B, H, 1, 2, 128, 32) fp32, zero-initialised, chunk-swizzled like the persistent kernel's
 };
-
-// one 128-byte bf16 row (64 values, scaled) from two 32-column TMEM loads into a SWIZZLE_128B staging row
-__device__ __forceinline__ void stage_row_bf16(uint32_t row_addr, int row, const uint32_t (&lo)[32], const uint32_t (&hi)[32], float scale) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t* v = c < 4 ? lo : hi;
-    uint32_t w[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * (c & 3) + 2 * e]) * scale, __uint_as_float(v[8 * (c & 3) + 2 * e + 1]) * scale);
-      w[e] = *reinterpret_cast<uint32_t*>(&hb);
-    }
-    sts128(row_addr + uint32_t((c ^ (row & 7)) * 16), w[0], w[1], w[2], w[3]);
-  }
-}
 
 __global__ void __launch_bounds__(kQrThreads, 1)
 attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -1430,7 +1455,10 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
             static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv)};
   AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBwdSmemBytes)));
   const unsigned grid = unsigned(std::min(n_items, n_sm));  // persistent: one CTA per SM walks the items
-  attn_bwd_tc_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(mq, mk, mv, mdo, a);
+  CUtensorMap mdk, mdv;
+  if ((st = make_map(&mdk, bp.dk, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, kBlockN)) != AGA_OK) return st;
+  if ((st = make_map(&mdv, bp.dv, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, kBlockN)) != AGA_OK) return st;
+  attn_bwd_tc_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(mq, mk, mv, mdo, mdk, mdv, a);
   AGA_AFTER_LAUNCH();
   }
   const int64_t total8 = int64_t(p.B) * p.Tq * p.H * (kHeadDim / 8);
