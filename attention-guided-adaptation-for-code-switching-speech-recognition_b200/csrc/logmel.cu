@@ -4,13 +4,16 @@
 //   torch.stft(center, reflect, hann 400, hop 160) -> drop last frame -> |.|^2 -> mel_80 @ P ->
 //   log10(clamp 1e-10) -> max(x, utt_max - 8) -> (x + 4) / 4
 // as two kernels:
-//   1. logmel_frames_kernel: one CTA per 32 consecutive frames of one utterance.  The CTA stages the
-//      5360 samples its frames cover ONCE into shared memory with 128-bit loads (each HBM sample is
-//      read once, the 2.5x frame overlap is served from smem), then per frame runs a 400-point real DFT
+//   1. logmel_frames_kernel: PERSISTENT CTAs (two per SM) walk blocks of 32 consecutive frames of one utterance;
+//      the constant tables (window, twiddles, filter bands) are loaded once per CTA and the NEXT block's samples
+//      are fetched into registers with 128-bit loads while the current block is transformed (HBM latency off
+//      the critical path; it was 30 % of the stall samples).  A block's 5360 samples sit in shared memory ONCE
+//      (each HBM sample is read once, the 2.5x frame overlap is served from smem); per frame a 400-point real DFT
 //      factored 400 = 16 x 25 (16 real 25-point DFTs with constant roots in registers, W_400 twiddles,
 //      13 complex 16-point FFTs; the other 12 residues follow from Hermitian symmetry), the power
-//      spectrum, the banded mel projection and log10; it stores the un-normalised log-mel tile with
-//      128-byte coalesced rows and folds the per-utterance maximum into one atomicMax per warp.
+//      spectrum (kept [bin][frame], frame fastest, so that the projection reads it conflict-free), the banded mel
+//      projection and log10 (MUFU lg2); it stores the un-normalised log-mel tile with 128-byte coalesced rows and
+//      folds the per-utterance maximum into one atomicMax per warp.
 //   2. logmel_normalise_kernel: max(x, m_b - 8), (x + 4)/4 in place (the tile is L2-resident).
 // Algorithmic HBM bytes per utterance: N*4 read + n_mels*(N/160)*4 written.
 #include "aga_common.cuh"
@@ -41,7 +44,9 @@ constexpr int kSampSmemAl = (kSampSmem + 3) / 4 * 4;
 constexpr int kXchK1Stride = 36;                    // floats: 16 complex + 4 pad (conflict-free LDS.128)
 constexpr int kXchFrameStride = 13 * kXchK1Stride;  // 468
 constexpr int kXchSmem = kFramesPerPass * kXchFrameStride;
-constexpr int kPowSmem = kFramesPerCta * kNfreq;
+constexpr int kPowStride = kFramesPerCta + 1;  // [bin][frame]: odd stride -> stage 2's strided bins and the projection's rows are conflict-free
+constexpr int kPowSmem = (kNfreq * kPowStride + 3) / 4 * 4;  // keeps the tables behind it 16-byte aligned
+constexpr int kStageVecs = (kChunk / 4 + kThreads - 1) / kThreads;  // float4 per thread of a block's samples (6)
 constexpr int kTwSmem = 13 * 16 * 2;
 constexpr int kSmemFloats = kSampSmemAl + kXchSmem + kPowSmem + kNfft + kTwSmem + 3 * kMaxMels + kWSmem;
 constexpr size_t kSmemBytes = size_t(kSmemFloats) * 4;
@@ -112,7 +117,7 @@ __device__ __forceinline__ float load_sample_reflect(const float* __restrict__ r
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-logmel_frames_kernel(const float* __restrict__ audio, int64_t N, int64_t ld, int F,
+logmel_frames_kernel(const float* __restrict__ audio, int64_t N, int64_t ld, int F, int n_fblocks, int n_blocks,
                      const unsigned char* __restrict__ packed, int n_mels, float* __restrict__ out,
                      uint32_t* __restrict__ maxkey) {
   extern __shared__ __align__(16) float smem[];
@@ -125,17 +130,15 @@ logmel_frames_kernel(const float* __restrict__ audio, int64_t N, int64_t ld, int
   float* s_fw = reinterpret_cast<float*>(s_fst + 3 * kMaxMels);
 
   const int tid = threadIdx.x;
-  const int b = blockIdx.y;
-  const int f0 = blockIdx.x * kFramesPerCta;
-  const float* arow = audio + int64_t(b) * ld;
 
-  // ---- filter bands -> smem
+  // ---- constant tables -> smem, once per (persistent) CTA
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(packed);
   const int* g_start = reinterpret_cast<const int*>(packed + sizeof(PackedHeader));
   const int* g_count = g_start + n_mels;
   const int* g_off = g_count + n_mels;
   const float* g_w = reinterpret_cast<const float*>(g_off + n_mels);
   const int total_w = hdr->total;
+  const bool w_in_smem = total_w <= kWSmem;  // every stock filterbank (391 / 394 weights); dense custom ones read global
   for (int i = tid; i < n_mels; i += kThreads) {
     s_fst[i] = g_start[i];
     s_fst[kMaxMels + i] = g_count[i];
@@ -145,110 +148,139 @@ logmel_frames_kernel(const float* __restrict__ audio, int64_t N, int64_t ld, int
   for (int i = tid; i < kNfft; i += kThreads) s_win[i] = k_hann400[i];
   for (int i = tid; i < kTwSmem; i += kThreads) s_tw[i] = k_tw400[i];
 
-  // ---- stage the CTA's samples once (128-bit loads where the chunk is interior and aligned)
-  {
+  // samples of one block as kStageVecs float4 per thread (128-bit loads where the chunk is interior and aligned)
+  auto fetch = [&](int blk, float4 (&val)[kStageVecs]) {
+    const int b = blk / n_fblocks, f0 = (blk - b * n_fblocks) * kFramesPerCta;
+    const float* arow = audio + int64_t(b) * ld;
     const int64_t g0 = int64_t(f0) * kHop - kNfft / 2;  // multiple of 8 samples
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(arow) & 15) == 0);
-    for (int c = tid; c < kChunk / 4; c += kThreads) {
-      const int s = 4 * c;
-      const int64_t g = g0 + s;
-      float4 val;
-      if (vec_ok && g >= 0 && g + 3 < N) {
-        val = __ldg(reinterpret_cast<const float4*>(arow + g));
+#pragma unroll
+    for (int u = 0; u < kStageVecs; ++u) {
+      const int c = tid + u * kThreads;
+      const int64_t g = g0 + 4 * c;
+      if (c >= kChunk / 4) {
+        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (vec_ok && g >= 0 && g + 3 < N) {
+        val[u] = __ldg(reinterpret_cast<const float4*>(arow + g));
       } else {
-        val.x = load_sample_reflect(arow, g, N);
-        val.y = load_sample_reflect(arow, g + 1, N);
-        val.z = load_sample_reflect(arow, g + 2, N);
-        val.w = load_sample_reflect(arow, g + 3, N);
+        val[u].x = load_sample_reflect(arow, g, N);
+        val[u].y = load_sample_reflect(arow, g + 1, N);
+        val[u].z = load_sample_reflect(arow, g + 2, N);
+        val[u].w = load_sample_reflect(arow, g + 3, N);
       }
-      *reinterpret_cast<float4*>(s_samp + pad_idx(s)) = val;
     }
-  }
-  __syncthreads();
+  };
 
   const int slot = tid & 15;
   const int fpass = tid >> 4;  // frame within the pass
-#pragma unroll 1
-  for (int pass = 0; pass < kFramesPerCta / kFramesPerPass; ++pass) {
-    const int fl = pass * kFramesPerPass + fpass;
-    // ---- stage 1: thread (frame, n2) — real 25-point DFT over n1 of x[16*n1 + n2], outputs k1 = 0..12
-    {
-      const int n2 = slot;
-      const float* sp = s_samp + fl * (kHop + 16) + n2;
-      float x[25];
+  const int lane = tid & 31, warp = tid >> 5;
+  float4 nxt[kStageVecs];
+  int blk = blockIdx.x;
+  if (blk < n_blocks) fetch(blk, nxt);
+
+  for (; blk < n_blocks; blk += gridDim.x) {
+    const int b = blk / n_fblocks, f0 = (blk - b * n_fblocks) * kFramesPerCta;
+    // ---- this block's samples: registers -> smem; then the next block's loads go out and fly during the transforms
 #pragma unroll
-      for (int n1 = 0; n1 < 25; ++n1) {
-        const int j = 16 * n1;
-        x[n1] = sp[j + 16 * (n1 / 10)] * s_win[j + n2];
-      }
-      float a[13], bb[13];
-#pragma unroll
-      for (int j = 1; j <= 12; ++j) {
-        a[j] = x[j] + x[25 - j];
-        bb[j] = x[j] - x[25 - j];
-      }
-      float2* xrow = reinterpret_cast<float2*>(s_xch + fpass * kXchFrameStride) + n2;
-      static_for<0, 13>([&](auto k1c) {
-        constexpr int k1 = decltype(k1c)::value;
-        float re = x[0], im = 0.0f;
-        static_for<1, 13>([&](auto jc) {
-          constexpr int j = decltype(jc)::value;
-          constexpr int m = (j * k1) % 25;
-          constexpr float cr = kC25[m], nsi = -kS25[m];
-          re = fmaf(a[j], cr, re);
-          im = fmaf(bb[j], nsi, im);
-        });
-        const float2 tw = reinterpret_cast<const float2*>(s_tw)[k1 * 16 + n2];
-        xrow[k1 * (kXchK1Stride / 2)] = make_float2(re * tw.x - im * tw.y, re * tw.y + im * tw.x);
-      });
+    for (int u = 0; u < kStageVecs; ++u) {
+      const int c = tid + u * kThreads;
+      if (c < kChunk / 4) *reinterpret_cast<float4*>(s_samp + pad_idx(4 * c)) = nxt[u];
     }
     __syncthreads();
-    // ---- stage 2: thread (frame, k1 < 13) — 16-point FFT over n2; bins k1 + 25*k2 and their mirrors
-    if (slot < 13) {
-      const int k1 = slot;
-      const float4* src = reinterpret_cast<const float4*>(s_xch + fpass * kXchFrameStride + k1 * kXchK1Stride);
-      float2 v[16];
+    if (blk + int(gridDim.x) < n_blocks) fetch(blk + gridDim.x, nxt);
+
+#pragma unroll 1
+    for (int pass = 0; pass < kFramesPerCta / kFramesPerPass; ++pass) {
+      const int fl = pass * kFramesPerPass + fpass;
+      // ---- stage 1: thread (frame, n2) — real 25-point DFT over n1 of x[16*n1 + n2], outputs k1 = 0..12
+      {
+        const int n2 = slot;
+        const float* sp = s_samp + fl * (kHop + 16) + n2;
+        float x[25];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 t = src[i];
-        v[2 * i] = make_float2(t.x, t.y);
-        v[2 * i + 1] = make_float2(t.z, t.w);
+        for (int n1 = 0; n1 < 25; ++n1) {
+          const int j = 16 * n1;
+          x[n1] = sp[j + 16 * (n1 / 10)] * s_win[j + n2];
+        }
+        float a[13], bb[13];
+#pragma unroll
+        for (int j = 1; j <= 12; ++j) {
+          a[j] = x[j] + x[25 - j];
+          bb[j] = x[j] - x[25 - j];
+        }
+        float2* xrow = reinterpret_cast<float2*>(s_xch + fpass * kXchFrameStride) + n2;
+        static_for<0, 13>([&](auto k1c) {
+          constexpr int k1 = decltype(k1c)::value;
+          float re = x[0], im = 0.0f;
+          static_for<1, 13>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr int m = (j * k1) % 25;
+            constexpr float cr = kC25[m], nsi = -kS25[m];
+            re = fmaf(a[j], cr, re);
+            im = fmaf(bb[j], nsi, im);
+          });
+          const float2 tw = reinterpret_cast<const float2*>(s_tw)[k1 * 16 + n2];
+          xrow[k1 * (kXchK1Stride / 2)] = make_float2(re * tw.x - im * tw.y, re * tw.y + im * tw.x);
+        });
       }
-      fft16(v);
-      float* prow = s_pow + fl * kNfreq;
+      __syncthreads();
+      // ---- stage 2: thread (frame, k1 < 13) — 16-point FFT over n2; bins k1 + 25*k2 and their mirrors
+      if (slot < 13) {
+        const int k1 = slot;
+        const float4* src = reinterpret_cast<const float4*>(s_xch + fpass * kXchFrameStride + k1 * kXchK1Stride);
+        float2 v[16];
 #pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) {
-        const float p = v[k2].x * v[k2].x + v[k2].y * v[k2].y;
-        if (k2 < 8) {
-          prow[k1 + 25 * k2] = p;
-        } else if (k1 > 0 || k2 == 8) {
-          prow[kNfft - k1 - 25 * k2] = p;  // |X[400-k]| = |X[k]|
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = src[i];
+          v[2 * i] = make_float2(t.x, t.y);
+          v[2 * i + 1] = make_float2(t.z, t.w);
+        }
+        fft16(v);
+        float* pcol = s_pow + fl;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const float p = v[k2].x * v[k2].x + v[k2].y * v[k2].y;
+          if (k2 < 8) {
+            pcol[(k1 + 25 * k2) * kPowStride] = p;
+          } else if (k1 > 0 || k2 == 8) {
+            pcol[(kNfft - k1 - 25 * k2) * kPowStride] = p;  // |X[400-k]| = |X[k]|
+          }
         }
       }
+      __syncthreads();
     }
+
+    // ---- mel projection + log10; lane = frame (coalesced 128-byte rows), warp strides over mel bins
+    const int f = f0 + lane;
+    const float* pcol = s_pow + lane;
+    float vmax = -INFINITY;
+    for (int m = warp; m < n_mels; m += kThreads / 32) {
+      const int st = s_fst[m], cnt = s_fst[kMaxMels + m], off = s_fst[2 * kMaxMels + m];
+      const float* pp = pcol + st * kPowStride;
+      float acc0 = 0.0f, acc1 = 0.0f;
+      if (w_in_smem) {
+        const float* wp = s_fw + off;
+        int i = 0;
+        for (; i + 1 < cnt; i += 2) {
+          acc0 = fmaf(wp[i], pp[i * kPowStride], acc0);
+          acc1 = fmaf(wp[i + 1], pp[(i + 1) * kPowStride], acc1);
+        }
+        if (i < cnt) acc0 = fmaf(wp[i], pp[i * kPowStride], acc0);
+      } else {
+        for (int i = 0; i < cnt; ++i) acc0 = fmaf(__ldg(g_w + off + i), pp[i * kPowStride], acc0);
+      }
+      const float v = __log2f(fmaxf(acc0 + acc1, 1e-10f)) * 0.30102999566398120f;  // log10 via MUFU lg2 (abs error < 1e-7)
+      if (f < F) {
+        out[(int64_t(b) * n_mels + m) * F + f] = v;
+        vmax = fmaxf(vmax, v);
+      }
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0 && vmax > -INFINITY) atomicMax(maxkey + b, float_to_key(vmax));
+    // s_samp / s_pow of this block are dead once every warp is here; the next iteration's first barrier orders the
+    // sample stores against stage 1, this one orders them against the projection's reads of s_pow (next stage 2)
     __syncthreads();
   }
-
-  // ---- mel projection + log10; lane = frame (coalesced 128-byte rows), warp strides over mel bins
-  const int lane = tid & 31, warp = tid >> 5;
-  const int f = f0 + lane;
-  const float* prow = s_pow + lane * kNfreq;
-  float vmax = -INFINITY;
-  for (int m = warp; m < n_mels; m += kThreads / 32) {
-    const int st = s_fst[m], cnt = s_fst[kMaxMels + m], off = s_fst[2 * kMaxMels + m];
-    float acc = 0.0f;
-    for (int i = 0; i < cnt; ++i) {
-      const float w = (off + i < kWSmem) ? s_fw[off + i] : __ldg(g_w + off + i);
-      acc = fmaf(w, prow[st + i], acc);
-    }
-    const float v = log10f(fmaxf(acc, 1e-10f));
-    if (f < F) {
-      out[(int64_t(b) * n_mels + m) * F + f] = v;
-      vmax = fmaxf(vmax, v);
-    }
-  }
-  vmax = warp_max(vmax);
-  if (lane == 0 && vmax > -INFINITY) atomicMax(maxkey + b, float_to_key(vmax));
 }
 
 __global__ void __launch_bounds__(256)
@@ -357,9 +389,18 @@ extern "C" int aga_logmel_fwd(const float* audio, int64_t B, int64_t N, int64_t 
   uint32_t* maxkey = static_cast<uint32_t*>(workspace);
   AGA_CUDA_TRY(cudaMemsetAsync(maxkey, 0, size_t(B) * sizeof(uint32_t), s));
   AGA_CUDA_TRY(cudaFuncSetAttribute(logmel_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
-  dim3 grid(unsigned((F + kFramesPerCta - 1) / kFramesPerCta), unsigned(B));
+  const int64_t n_fblocks = (F + kFramesPerCta - 1) / kFramesPerCta;
+  const int64_t n_blocks = n_fblocks * B;
+  if (n_blocks > INT32_MAX) return AGA_ERR_UNSUPPORTED;
+  static const int n_sm = []() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const unsigned grid = unsigned(std::min<int64_t>(n_blocks, 2 * int64_t(n_sm)));  // persistent: two resident CTAs per SM
   logmel_frames_kernel<<<grid, kThreads, kSmemBytes, s>>>(
-      audio, N, ld, int(F), static_cast<const unsigned char*>(packed_filters), n_mels, out, maxkey);
+      audio, N, ld, int(F), int(n_fblocks), int(n_blocks), static_cast<const unsigned char*>(packed_filters), n_mels, out,
+      maxkey);
   AGA_AFTER_LAUNCH();
   const int64_t per_utt = int64_t(n_mels) * F;
   const int vec = (per_utt % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);

@@ -157,7 +157,7 @@ class OpenAIWhisperDecoder(torch.nn.Module):
             if self.whisper_cs and layer >= self.src_layer:
                 attention_scores.append(attention_map)
         x = dec.ln(x)
-        logits = (x @ dec.token_embedding.weight.to(x.dtype).t()).float()
+        logits = dec.vocab_logits(x)
         if self.whisper_cs:
             return logits, torch.stack(attention_scores)
         return logits, attention_scores
@@ -186,7 +186,7 @@ class OpenAIWhisperDecoder(torch.nn.Module):
         if return_maps:
             self.att_map = maps
         x = dec.ln(x)
-        y = (x[:, -1] @ dec.token_embedding.weight.to(x.dtype).t()).float()
+        y = dec.vocab_logits(x[:, -1])
         return torch.log_softmax(y, dim=-1), None
 
     def score(self, ys, state, x):

@@ -319,7 +319,27 @@ class TextDecoder(nn.Module):
         for block in self.blocks:
             x, _ = block(x, xa, mask=self.mask, kv_cache=kv_cache)
         x = self.ln(x)
-        return (x @ cast_param(self, "_emb_cast", self.token_embedding.weight, x.dtype).t()).float()
+        return self.vocab_logits(x)
+
+    def vocab_logits(self, x: Tensor) -> Tensor:
+        """``(x @ token_embedding.weight.T).float()`` (whisper/model.py:343-345).
+
+        n_vocab = 51865 is odd: with a leading dimension that is not a multiple of 16 bytes cuBLAS has no TMA / vector
+        path and falls back to a legacy sm_75 kernel (650 us forward, 550 us backward at B*T = 1024, 8x slower than the
+        aligned GEMM).  A frozen embedding is therefore multiplied as a copy padded with zero rows to a multiple of 64;
+        the extra logit columns are sliced away before anyone sees them (their gradient is zero)."""
+        w = self.token_embedding.weight
+        n_vocab = w.shape[0]
+        pad = (-n_vocab) % 64
+        if not x.is_cuda or pad == 0 or (w.requires_grad and torch.is_grad_enabled()):
+            return (x @ cast_param(self, "_emb_cast", w, x.dtype).t()).float()
+        c = self.__dict__.get("_emb_pad")
+        if c is None or c[0] != (w._version, w.data_ptr(), x.dtype):
+            wp = torch.zeros(n_vocab + pad, w.shape[1], dtype=x.dtype, device=w.device)
+            wp[:n_vocab] = w.detach()
+            c = ((w._version, w.data_ptr(), x.dtype), wp)
+            self.__dict__["_emb_pad"] = c
+        return F.linear(x, c[1])[..., :n_vocab].float()
 
 
 class Whisper(nn.Module):
