@@ -112,6 +112,10 @@ struct FwdArgs {
   int64_t o_sb, o_st;
   __nv_bfloat16* out;
   float* lse;
+  int causal;                  // key j visible to query i iff j <= i (Tq == Tk): key tiles above the diagonal are skipped
+  int export_lo, export_hi;    // exported key columns [lo, hi) of the scaled, masked logits (decoder self attention)
+  float* export_buf;           // (B, H, Tq, hi - lo) fp32 or nullptr
+  const uint8_t* head_sel;     // (H) or nullptr: heads whose columns are exported
 };
 
 // 32 fp32 TMEM columns (scaled) -> the bf16 half `half` (64 bytes) of a 128-byte row of a SWIZZLE_128B staging tile
@@ -150,7 +154,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row0 = qt * NT * kBlockM;
-  const int n_kt = (a.Tk + kBlockN - 1) / kBlockN;
+  const int n_kt_all = (a.Tk + kBlockN - 1) / kBlockN;
+  const int n_kt = a.causal ? min(n_kt_all, (row0 + NT * kBlockM - 1) / kBlockN + 1) : n_kt_all;
   const bool active_b = NT == 2 && row0 + kBlockM < a.Tq;  // tile B exists and holds at least one valid row
 
   if (threadIdx.x == 0) {
@@ -273,6 +278,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const uint32_t t_p = tmem + (lane_base << 16) + kColP + t * 64;
       float m_used = -INFINITY, l = 0.f;
       TL_DECL((lane == 0 && (warp & 3) == 0) ? 1 + t : -1);
+      const int W = a.export_hi - a.export_lo;
+      float* erow = (a.export_buf && (a.head_sel == nullptr || a.head_sel[h] != 0) && row < a.Tq)
+                        ? a.export_buf + ((int64_t(b) * a.H + h) * a.Tq + row) * W - a.export_lo : nullptr;
 
       // The two warpgroups share each SM sub-partition's MUFU.  Their exp2 phases are forced to ALTERNATE with a pair
       // of named barriers (id 2: "A may start its exp2 phase", id 3: "B may start"): while one warpgroup runs its
@@ -297,13 +305,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&sb->s_free[t]);
         TL(22);
-        const int valid = a.Tk - j * kBlockN;  // keys of this tile that exist (>= 128 except on the last tile)
+        int valid = a.Tk - j * kBlockN;  // keys of this tile this row may see (>= 128 except on the last / diagonal tile)
+        if (a.causal) valid = min(valid, row - j * kBlockN + 1);
         if (valid < kBlockN) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;  // -inf: exp2 -> 0
+        }
+        if (erow != nullptr && j * kBlockN < a.export_hi && (j + 1) * kBlockN > a.export_lo) {
+          // side buffer of the guided loss: scaled, masked logits of the selected key columns (whisper/model.py:103,
+          // what the reference returns as `qk`), written straight from the S registers
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int key = j * kBlockN + c * 32 + i;
+              if (key >= a.export_lo && key < a.export_hi) erow[key] = __uint_as_float(sr[c][i]) * 0.125f;
+            }
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -430,8 +450,15 @@ int make_map(CUtensorMap* map, const void* base, int B, int H, int T, int64_t st
 
 }  // namespace
 
+// exported columns are written from registers with fully unrolled, predicated stores: a narrow window only
+// (the guided loss reads key columns 1:3); full maps and probability export stay on the CUDA-core path
+constexpr int kMaxExportCols = 16;
+
 bool attn_tc_supported(const aga_attn_params& p) {
-  if (p.dtype != AGA_BF16 || p.causal || p.export_kind != AGA_EXPORT_NONE) return false;
+  if (p.dtype != AGA_BF16) return false;
+  if (p.export_kind != AGA_EXPORT_NONE &&
+      (p.export_kind != AGA_EXPORT_LOGITS || p.export_hi - p.export_lo > kMaxExportCols))
+    return false;
   // TMA: global strides are multiples of 16 bytes (validated by the caller) and below 2^40 bytes
   return get_encode_fn() != nullptr;
 }
@@ -445,7 +472,10 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
   if ((st = make_map(&mv, p.v, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, kBlockN)) != AGA_OK) return st;
   CUtensorMap mo;  // 32-row boxes: one store per softmax warp
   if ((st = make_map(&mo, p.out, p.B, p.H, p.Tq, p.o_stride_b, p.o_stride_t, 32)) != AGA_OK) return st;
-  FwdArgs a{p.B, p.H, p.Tq, p.Tk, p.o_stride_b, p.o_stride_t, static_cast<__nv_bfloat16*>(p.out), p.lse};
+  const bool exporting = p.export_kind == AGA_EXPORT_LOGITS && p.export_buf != nullptr;
+  FwdArgs a{p.B, p.H, p.Tq, p.Tk, p.o_stride_b, p.o_stride_t, static_cast<__nv_bfloat16*>(p.out), p.lse, p.causal,
+            exporting ? p.export_lo : 0, exporting ? p.export_hi : 0, exporting ? p.export_buf : nullptr,
+            exporting ? p.head_sel : nullptr};
 #ifdef AGA_FWD_TWO_TILES  // one CTA per SM, two query tiles sharing each K/V tile
   constexpr int NT = 2;
 #else                     // two independent single-tile CTAs per SM (measured faster: see DESIGN.md)
@@ -1093,6 +1123,10 @@ static_assert(kQrSmemBytes <= 227 * 1024, "q-resident backward kernel exceeds th
 struct QrArgs {
   int B, H, Tq, Tk;
   int tiles_per_cta;  // key tiles per chunk
+  int causal;                 // Tq == Tk <= 128: one key tile, keys above the diagonal masked
+  int export_lo, export_hi;   // columns [lo, hi) whose scaled logits were exported; d_export is their gradient
+  const float* d_export;      // (B, H, Tq, hi - lo) fp32 or nullptr
+  const uint8_t* head_sel;    // (H) or nullptr
   const float* stats;  // (B, H, 1, 2, 128): lse * log2(e) | delta, zero past Tq
   float* dq_accum;     // (B, H, 1, 2, 128, 32) fp32, zero-initialised, chunk-swizzled like the persistent kernel's
 };
@@ -1273,6 +1307,9 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     const uint32_t ds_row = smem_u32(sdS + (cs >> 1) * kPanelBytes + row * 128);
     const float2 sc2 = make_float2(kScaleLog2, kScaleLog2), nl2 = make_float2(neg_lse, neg_lse);
     const float2 nd2 = make_float2(-delta, -delta);
+    const int W = a.export_hi - a.export_lo;
+    const float* grow = (a.d_export && (a.head_sel == nullptr || a.head_sel[h] != 0) && row < a.Tq)
+                            ? a.d_export + ((int64_t(b) * a.H + h) * a.Tq + row) * W - a.export_lo : nullptr;
     TL_DECL((warp == 0 && lane == 0) ? 1 : -1);
     TL(19);
     for (int jj = 0; jj < n_my; ++jj) {
@@ -1289,6 +1326,14 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sb->s_free);
+        if (a.causal) {  // key > query: -inf -> P = 0
+          const int vis = row - ((kt0 + jj) * kBlockN + cs * 32) + 1;  // keys of this 32-column slice the row may see
+          if (vis < 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i >= vis) sv[i] = 0xff800000u;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nl2);
@@ -1309,7 +1354,13 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 t = __fadd2_rn(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), nd2);
-          const float2 d = __fmul2_rn(make_float2(__uint_as_float(pk[i] << 16), __uint_as_float(pk[i] & 0xffff0000u)), t);
+          float2 d = __fmul2_rn(make_float2(__uint_as_float(pk[i] << 16), __uint_as_float(pk[i] & 0xffff0000u)), t);
+          if (grow != nullptr) {  // gradient of the exported (scaled, masked) logits adds to dS on the visible entries
+            const int key = (kt0 + jj) * kBlockN + cs * 32 + 2 * i;
+            const int lim = a.causal ? min(a.export_hi, row + 1) : a.export_hi;
+            if (key >= a.export_lo && key < lim) d.x += grow[key];
+            if (key + 1 >= a.export_lo && key + 1 < lim) d.y += grow[key + 1];
+          }
           __nv_bfloat162 hb = __floats2bfloat162_rn(d.x, d.y);
           dd[i] = *reinterpret_cast<uint32_t*>(&hb);
         }
@@ -1399,7 +1450,16 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 
 }  // namespace
 
-bool attn_tc_bwd_supported(const aga_attn_params& p) { return attn_tc_supported(p); }
+// causal masking and the gradient of the exported columns exist in the one-query-tile kernel only (Tq <= 128: the
+// decoder self attention of a training step); longer causal sequences take the CUDA-core path
+bool attn_tc_bwd_supported(const aga_attn_params& p) {
+  if (!attn_tc_supported(p)) return false;
+  if ((p.causal || p.export_kind != AGA_EXPORT_NONE) && p.Tq > kBlockM) return false;
+#ifdef AGA_BWD_NO_QRES
+  if (p.causal || p.export_kind != AGA_EXPORT_NONE) return false;
+#endif
+  return true;
+}
 
 size_t attn_tc_bwd_workspace(const aga_attn_params& p) {
   const size_t n_qt = size_t(p.Tq + kBlockM - 1) / kBlockM;
@@ -1440,7 +1500,9 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
     int per = int((tiles + int64_t(n_sm) * 4 - 1) / (int64_t(n_sm) * 4));
     per = std::max(1, std::min(per, n_kt));
     const int n_chunks = (n_kt + per - 1) / per;
-    QrArgs qa{p.B, p.H, p.Tq, p.Tk, per, stats, dq_acc};
+    const bool dexp = p.export_kind == AGA_EXPORT_LOGITS && bp.d_export != nullptr;
+    QrArgs qa{p.B, p.H, p.Tq, p.Tk, per, p.causal, dexp ? p.export_lo : 0, dexp ? p.export_hi : 0,
+              dexp ? bp.d_export : nullptr, dexp ? p.head_sel : nullptr, stats, dq_acc};
     CUtensorMap mdk, mdv;  // 32-row boxes: one store per drain warp
     if ((st = make_map(&mdk, bp.dk, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, 32)) != AGA_OK) return st;
     if ((st = make_map(&mdv, bp.dv, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, 32)) != AGA_OK) return st;

@@ -171,11 +171,13 @@ _KINDS = {None: L.EXPORT_NONE, "none": L.EXPORT_NONE, "logits": L.EXPORT_LOGITS,
 TC_BWD_AVAILABLE = True  # the tcgen05 backward exists (attn_tc.cu)
 
 
-def _impl_name(q, causal, kind, impl, bwd=False) -> str:
-    """Which implementation the C ABI will pick (mirrors attn_api.cu::use_tc) — for profiling tags only."""
-    tc = impl != L.ATTN_SIMT and q.dtype == torch.bfloat16 and not causal and kind == L.EXPORT_NONE
-    if bwd:
-        tc = tc and TC_BWD_AVAILABLE
+def _impl_name(q, causal, kind, impl, bwd=False, cols=(0, 0)) -> str:
+    """Which implementation the C ABI will pick (mirrors attn_tc.cu::attn_tc_supported / attn_tc_bwd_supported) — for
+    profiling tags only."""
+    narrow = kind == L.EXPORT_NONE or (kind == L.EXPORT_LOGITS and cols[1] - cols[0] <= 16)
+    tc = impl != L.ATTN_SIMT and q.dtype == torch.bfloat16 and narrow
+    if bwd and (causal or kind != L.EXPORT_NONE):
+        tc = tc and q.shape[1] <= 128
     return "tc" if tc else "simt"
 
 
@@ -223,7 +225,7 @@ def _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl):
     L.check(lib.aga_attn_fwd_workspace_bytes(C.byref(p), C.byref(nbytes)), "aga_attn_fwd_workspace_bytes")
     ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
     flops = 4.0 * B * n_head * Tq * k.shape[1] * 64 * (0.5 if causal else 1.0)
-    tm = _Timed(f"attn_fwd_{_impl_name(q, causal, kind, impl)}_{Tq}x{k.shape[1]}", flops, q.device)
+    tm = _Timed(f"attn_fwd_{_impl_name(q, causal, kind, impl, cols=cols)}_{Tq}x{k.shape[1]}", flops, q.device)
     L.check(lib.aga_attn_fwd(C.byref(p), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_fwd")
     tm.done(q.device)
     return out, lse, export_buf
@@ -254,7 +256,8 @@ def _attn_backward(q, k, v, out, lse, head_sel, probs, cfg, dout, dexport, dq, d
     L.check(lib.aga_attn_bwd_workspace_bytes(C.byref(bp), C.byref(nbytes)), "aga_attn_bwd_workspace_bytes")
     ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
     flops = 10.0 * q.shape[0] * n_head * q.shape[1] * k.shape[1] * 64 * (0.5 if causal else 1.0)
-    tm = _Timed(f"attn_bwd_{_impl_name(q, causal, kind, impl, bwd=True)}_{q.shape[1]}x{k.shape[1]}", flops, q.device)
+    tm = _Timed(f"attn_bwd_{_impl_name(q, causal, kind if dexport is not None else L.EXPORT_NONE, impl, bwd=True, cols=cols)}"
+                f"_{q.shape[1]}x{k.shape[1]}", flops, q.device)
     L.check(lib.aga_attn_bwd(C.byref(bp), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_bwd")
     tm.done(q.device)
 

@@ -106,3 +106,58 @@ def test_tc_backward_full_size_linearity(A):
         scale = float(a.float().abs().max())
         assert float((b2.float() - 2 * a.float()).abs().max()) <= 2e-2 * scale
         assert float((a2.float() - a.float()).abs().max()) <= 1e-2 * scale
+
+
+@pytest.mark.parametrize("B,H,T,cols,sel", [(2, 3, 64, (1, 3), None), (1, 2, 128, (1, 3), [1, 0]), (2, 2, 37, (0, 5), None),
+                                            (16, 12, 64, (1, 3), None), (1, 2, 300, (1, 3), None), (1, 1, 448, (120, 131), None)])
+def test_tc_causal_export_forward_vs_oracle(A, B, H, T, cols, sel):
+    """Decoder self attention on the tcgen05 path: causal mask (key tiles above the diagonal skipped) and the scaled,
+    masked logits of the selected key columns written from the S registers (whisper/model.py:103-109)."""
+    q, k, v = _mk(B, T, T, H, 1.0, seed=T + 11)
+    head_sel = None if sel is None else torch.tensor(sel, dtype=torch.uint8)
+    out, lse, slab = A.qkv_attention(q.cuda(), k.cuda(), v.cuda(), H, causal=True, export="logits", export_cols=cols,
+                                     head_sel=head_sel, impl="tcgen05")
+    ref, qk, _ = O.qkv_attention(q.float().numpy(), k.float().numpy(), v.float().numpy(), H, causal=True)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, rtol=2e-2, atol=2e-2)
+    want = qk[..., cols[0]:cols[1]]
+    got = slab.cpu().numpy()
+    for h in range(H):
+        if sel is not None and not sel[h]:
+            assert not got[:, h].any()  # unselected heads are never written (buffer starts as zeros)
+            continue
+        assert np.array_equal(np.isinf(got[:, h]), np.isinf(want[:, h]))
+        fin = np.isfinite(want[:, h])
+        np.testing.assert_allclose(got[:, h][fin], want[:, h][fin], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,H,T,cols,sel", [(2, 3, 64, (1, 3), None), (1, 2, 128, (1, 3), [0, 1]), (2, 2, 37, (0, 5), None),
+                                            (16, 12, 64, (1, 3), None)])
+def test_tc_causal_export_backward_vs_oracle(A, B, H, T, cols, sel):
+    """dQ/dK/dV of the causal one-query-tile kernel with a gradient on the exported columns (the guided loss'
+    gradient, espnet_model.py:463-530) vs the fp64 oracle, and agreement with the CUDA-core path."""
+    q, k, v = _mk(B, T, T, H, 1.0, seed=T * 5 + 1)
+    g = torch.Generator().manual_seed(3)
+    do = torch.randn(B, T, H * 64, generator=g).bfloat16()
+    dE = torch.randn(B, H, T, cols[1] - cols[0], generator=g)
+    head_sel = None if sel is None else torch.tensor(sel, dtype=torch.uint8)
+    grads = {}
+    for impl in ("tcgen05", "simt"):
+        qd, kd, vd = (x.cuda().requires_grad_() for x in (q, k, v))
+        out, _, slab = A.qkv_attention(qd, kd, vd, H, causal=True, export="logits", export_cols=cols, head_sel=head_sel,
+                                       impl=impl)
+        fin = torch.isfinite(slab)
+        loss_e = (torch.where(fin, slab, torch.zeros_like(slab)) * dE.cuda()).sum()
+        torch.autograd.backward([out, loss_e], [do.cuda(), torch.ones((), device="cuda")])
+        grads[impl] = (qd.grad, kd.grad, vd.grad)
+    d_qk = np.zeros((B, H, T, T))
+    d_qk[..., cols[0]:cols[1]] = dE.numpy()
+    if sel is not None:
+        d_qk *= np.asarray(sel, dtype=np.float64)[None, :, None, None]
+    d_qk *= np.tril(np.ones((T, T)))[None, None]
+    dq, dk, dv = O.qkv_attention_bwd(q.float().numpy(), k.float().numpy(), v.float().numpy(), H, True, do.float().numpy(),
+                                     d_qk=d_qk)
+    for name, got, alt, ref in zip(("dq", "dk", "dv"), grads["tcgen05"], grads["simt"], (dq, dk, dv)):
+        scale = max(float(np.abs(ref).max()), 1e-6)
+        np.testing.assert_allclose(got.float().cpu().numpy(), ref, rtol=2e-2, atol=2e-2 * scale, err_msg=name)
+        np.testing.assert_allclose(got.float().cpu().numpy(), alt.float().cpu().numpy(), rtol=2e-2, atol=2e-2 * scale,
+                                   err_msg=name + " vs simt")
