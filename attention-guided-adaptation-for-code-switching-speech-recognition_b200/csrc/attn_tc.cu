@@ -420,6 +420,282 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   if (warp == kMmaWarp) tmem_dealloc(tmem, Cfg::kCols);
 }
 
+// ------------------------------------------------------------------------------------------ forward, column-split softmax
+// Same pipeline as attn_fwd_tc_kernel<1> (one 128-row query tile per CTA, two CTAs per SM, same TMEM map), but every
+// 32-row group of S is shared by TWO softmax warps, 64 key columns each: 8 softmax warps per CTA, FOUR per SM
+// sub-partition.  With one warp per sub-partition and CTA, a tile's serial chain (wait S, TMEM load, row max, wait PV,
+// 128 exp2, TMEM store: 2900 cycles, of which 1024 on the MUFU) left the MUFU 30 % idle; half-rows shorten every link
+// of the chain and give the scheduler four chains per MUFU to interleave.  The two warps of a pair agree on the
+// running row maximum through a parity-double-buffered smem slot and a 64-thread named barrier per tile; the row sums
+// are combined once at the end.
+#ifndef AGA_FS_POLY
+#define AGA_FS_POLY 2  // measured on B200 (B16 H12 1500x1500): 0 -> 631, 2 -> 679, 3 -> 663 TFLOP/s
+#endif
+constexpr int kFsPolyPairs = AGA_FS_POLY;
+constexpr int kFsSoftmaxWarps = 8;
+constexpr int kFsTmaWarp = 8, kFsMmaWarp = 9;
+constexpr int kFsThreads = 10 * 32;
+constexpr int kFsStages = 2;
+struct FsSmem {
+  uint64_t q_full;
+  uint64_t k_full[kFsStages], k_empty[kFsStages], v_full[kFsStages], v_empty[kFsStages];
+  uint64_t s_full, s_free, p_ready, pv_done;
+  uint32_t tmem_base;
+  alignas(16) float xch[2][2][kBlockM];  // [tile parity][column half][row]: local row maxima (and the row sums at the end)
+};
+constexpr size_t kFsSmemBytes = 1024 + size_t(1 + 2 * kFsStages) * kTileBytes + sizeof(FsSmem);
+static_assert(2 * kFsSmemBytes <= 227 * 1024, "two CTAs per SM");
+
+__global__ void __launch_bounds__(kFsThreads, 2)
+attn_fwd_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                         const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o, const FwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t kColS = 0, kColO = 128, kColP = 192;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + kFsStages * kTileBytes;
+  FsSmem* sb = reinterpret_cast<FsSmem*>(sV + kFsStages * kTileBytes);
+
+  CTA_LOG(0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = qt * kBlockM;
+  const int n_kt_all = (a.Tk + kBlockN - 1) / kBlockN;
+  const int n_kt = a.causal ? min(n_kt_all, (row0 + kBlockM - 1) / kBlockN + 1) : n_kt_all;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sb->q_full, 1);
+    for (int s = 0; s < kFsStages; ++s) {
+      mbar_init(&sb->k_full[s], 1);
+      mbar_init(&sb->k_empty[s], 1);
+      mbar_init(&sb->v_full[s], 1);
+      mbar_init(&sb->v_empty[s], 1);
+    }
+    mbar_init(&sb->s_full, 1);
+    mbar_init(&sb->s_free, kFsSoftmaxWarps);
+    mbar_init(&sb->p_ready, kFsSoftmaxWarps);
+    mbar_init(&sb->pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kFsMmaWarp) {
+    tmem_alloc(&sb->tmem_base, 256);
+    tmem_relinquish();
+  }
+  if (warp == kFsTmaWarp && lane == 0) {
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_k);
+    prefetch_tensormap(&map_v);
+    prefetch_tensormap(&map_o);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sb->tmem_base;
+
+  if (warp == kFsTmaWarp) {
+    // ============================== TMA producer ==============================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&sb->q_full, kTileBytes);
+      tma_load_4d(sQ, &map_q, &sb->q_full, 0, h, row0, b);
+    }
+    for (int j = 0; j < n_kt; ++j) {
+      const int s = j % kFsStages;
+      const uint32_t ph = (j / kFsStages) & 1;
+      mbar_wait(&sb->k_empty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sb->k_full[s], kTileBytes);
+        tma_load_4d(sK + s * kTileBytes, &map_k, &sb->k_full[s], 0, h, j * kBlockN, b);
+      }
+      mbar_wait(&sb->v_empty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sb->v_full[s], kTileBytes);
+        tma_load_4d(sV + s * kTileBytes, &map_v, &sb->v_full[s], 0, h, j * kBlockN, b);
+      }
+    }
+  } else if (warp == kFsMmaWarp) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, kHeadDim, 0, 1);
+    const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ));
+    auto issue_s = [&](int stage) {
+      const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + stage * kTileBytes));
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) mma_ss(tmem + kColS, dq + uint64_t(kk * 2), dk + uint64_t(kk * 2), idesc_qk, kk > 0);
+        tc_commit(&sb->s_full);
+        tc_commit(&sb->k_empty[stage]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&sb->q_full, 0);
+    mbar_wait(&sb->k_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < n_kt; ++j) {
+      const int s = j % kFsStages;
+      const uint32_t ph = (j / kFsStages) & 1;
+      if (j + 1 < n_kt) {  // S(j+1) as soon as the softmax warps hold S(j) in registers
+        const int s1 = (j + 1) % kFsStages;
+        mbar_wait(&sb->k_full[s1], ((j + 1) / kFsStages) & 1);
+        mbar_wait(&sb->s_free, j & 1);
+        tc_fence_after();
+        issue_s(s1);
+      }
+      mbar_wait(&sb->v_full[s], ph);
+      mbar_wait(&sb->p_ready, j & 1);
+      tc_fence_after();
+      const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + s * kTileBytes));
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kBlockN / 16; ++kk)
+          mma_ts(tmem + kColO, tmem + kColP + kk * 8, dv + uint64_t(kk * 128), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        tc_commit(&sb->pv_done);
+        tc_commit(&sb->v_empty[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ============================== softmax / correction / epilogue: warp = (row quadrant, column half) ==============
+    const int quad = warp & 3, ch = warp >> 2;
+    const uint32_t lane_base = uint32_t(quad * 32);
+    const int rloc = int(lane_base) + lane;
+    const int row = row0 + rloc;
+    const uint32_t t_s = tmem + (lane_base << 16) + kColS + ch * 64;
+    const uint32_t t_o = tmem + (lane_base << 16) + kColO + ch * 32;  // this warp's half of the O columns
+    const uint32_t t_p = tmem + (lane_base << 16) + kColP + ch * 32;  // bf16 pairs of its 64 keys
+    const int pair_bar = 2 + quad;                                     // named barrier of the two warps sharing these rows
+    float m_used = -INFINITY, l = 0.f;
+    const int W = a.export_hi - a.export_lo;
+    float* erow = (a.export_buf && (a.head_sel == nullptr || a.head_sel[h] != 0) && row < a.Tq)
+                      ? a.export_buf + ((int64_t(b) * a.H + h) * a.Tq + row) * W - a.export_lo : nullptr;
+    if (row0 + int(lane_base) >= a.Tq) {
+      // all 32 rows of this warp (and of its pair) lie past Tq (decoder tiles: Tq = 64): only keep the MMA warp's
+      // barriers moving — no TMEM traffic, no exponentials; the PV GEMM's rows for them are never read
+      for (int j = 0; j < n_kt; ++j) {
+        mbar_wait(&sb->s_full, j & 1);
+        if (lane == 0) mbar_arrive(&sb->s_free);
+        if (j > 0) mbar_wait(&sb->pv_done, (j - 1) & 1);
+        if (lane == 0) mbar_arrive(&sb->p_ready);
+      }
+    } else {
+    for (int j = 0; j < n_kt; ++j) {
+      mbar_wait(&sb->s_full, j & 1);
+      tc_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld32(t_s, sr[0]);
+      tmem_ld32(t_s + 32, sr[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->s_free);
+      const int kbase = j * kBlockN + ch * 64;
+      int valid = a.Tk - kbase;  // keys of this 64-column slice the row may see
+      if (a.causal) valid = min(valid, row - kbase + 1);
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;  // -inf: exp2 -> 0
+      }
+      if (erow != nullptr && kbase < a.export_hi && kbase + 64 > a.export_lo) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = kbase + c * 32 + i;
+            if (key >= a.export_lo && key < a.export_hi) erow[key] = __uint_as_float(sr[c][i]) * 0.125f;
+          }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+      }
+      // ---- agree on the row maximum with the warp that holds the other 64 columns of these rows
+      float* slot = sb->xch[j & 1][0];
+      slot[ch * kBlockM + rloc] = fmaxf(mx0, mx1);
+      named_bar_sync(pair_bar, 64);
+      const float m_new = fmaxf(m_used, fmaxf(slot[rloc], slot[kBlockM + rloc]) * kScaleLog2);
+      if (j > 0) {
+        mbar_wait(&sb->pv_done, (j - 1) & 1);  // P buffer consumed and O stable
+        tc_fence_after();
+      }
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, m_new - m_used > kRescaleThreshold)) {  // same rows, same decision in both warps
+        const float alpha = ex2(m_used - m_new);
+        l *= alpha;
+        m_used = m_new;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {  // 16 columns at a time: the S row stays in registers across this rare path
+          uint32_t r[16];
+          tmem_ld16(t_o + c * 16, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st16(t_o + c * 16, r);
+        }
+      }
+      const float neg_m = -m_used;
+      float2 rs = make_float2(0.f, 0.f);
+      const float2 sc2 = make_float2(kScaleLog2, kScaleLog2), nm2 = make_float2(neg_m, neg_m);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[c][2 * i]), __uint_as_float(sr[c][2 * i + 1])), sc2, nm2);
+          // kFsPolyPairs of every 8 pairs take the FMA-pipe exp2 (tc_ptx.cuh), the rest the MUFU
+          const float2 pp = (i & 7) < kFsPolyPairs ? ex2_poly2(x) : make_float2(ex2(x.x), ex2(x.y));
+          rs = __fadd2_rn(rs, pp);
+          __nv_bfloat162 hb = __floats2bfloat162_rn(pp.x, pp.y);
+          pk[i] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        tmem_st16(t_p + c * 16, pk);
+      }
+      l += rs.x + rs.y;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->p_ready);
+    }
+    // ---- epilogue: combine the two partial row sums, O / l -> bf16 half rows staged in the dead Q buffer, one TMA tile
+    //      store per 32-row group (issued by the pair's first warp), lse
+    float* slot = sb->xch[n_kt & 1][0];
+    slot[ch * kBlockM + rloc] = l;
+    named_bar_sync(pair_bar, 64);
+    l = slot[rloc] + slot[kBlockM + rloc];
+    mbar_wait(&sb->pv_done, (n_kt - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    uint8_t* stage = sQ + quad * (32 * 128);
+    {
+      uint32_t r[32];
+      tmem_ld32(t_o, r);
+      tmem_wait_ld();
+      stage_half_row_bf16(smem_u32(stage + lane * 128), lane, ch, r, inv);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(pair_bar, 64);
+    if (ch == 0) {
+      if (lane == 0) {
+        tma_store_4d(&map_o, stage, 0, h, row0 + int(lane_base), b);
+        bulk_commit_group();
+        bulk_wait_group_read0();  // the staging rows must outlive the store's reads (the CTA exits next)
+      }
+      if (row < a.Tq && a.lse) a.lse[(int64_t(b) * a.H + h) * a.Tq + row] = (m_used + log2f(l)) * kLn2;
+    }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  CTA_LOG(1);
+  if (warp == kFsMmaWarp) tmem_dealloc(tmem, 256);
+}
+
 // ------------------------------------------------------------------------------------------ host
 PFN_cuTensorMapEncodeTiled get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
@@ -481,10 +757,17 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
 #else                     // two independent single-tile CTAs per SM (measured faster: see DESIGN.md)
   constexpr int NT = 1;
 #endif
+#ifndef AGA_FWD_NO_SPLIT  // column-split softmax: 8 softmax warps per CTA (measured faster, see the kernel's header)
+  (void)NT;
+  AGA_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFsSmemBytes)));
+  dim3 grid_s((p.Tq + kBlockM - 1) / kBlockM, p.H, p.B);
+  attn_fwd_tc_split_kernel<<<grid_s, kFsThreads, kFsSmemBytes, s>>>(mq, mk, mv, mo, a);
+#else
   AGA_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     int(FwdCfg<NT>::kSmemBytes)));
   dim3 grid((p.Tq + NT * kBlockM - 1) / (NT * kBlockM), p.H, p.B);
   attn_fwd_tc_kernel<NT><<<grid, FwdCfg<NT>::kThreads, FwdCfg<NT>::kSmemBytes, s>>>(mq, mk, mv, mo, a);
+#endif
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }
@@ -516,6 +799,10 @@ namespace {
 //   21,22 MMA streams of halves 0, 1 (S^T, dV, dP^T, dK);  23  MMA stream of dQ.  One in-order issuer per stream:
 //         every "softmax event -> group of MMAs" costs a few hundred cycles of wait + descriptor set-up.
 // Rows/keys past the tensor ends are zero-filled by TMA, which makes their contributions exactly zero.
+#ifndef AGA_BWD_POLY
+#define AGA_BWD_POLY 0
+#endif
+constexpr int kBwdPolyQuads = AGA_BWD_POLY;  // of every 4 element quads of phase 1, this many use ex2_poly2
 constexpr int kBwdThreads = 768;
 constexpr int kBwdSoftmaxWarps = 16;
 constexpr int kBwdDrainWarp0 = 16;
@@ -864,7 +1151,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                                          make_float2(-L.x, -L.y));
             const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sv[4 * e4 + 2]), __uint_as_float(sv[4 * e4 + 3])), sc2,
                                          make_float2(-L.z, -L.w));
-            const float p0 = ex2(x0.x), p1 = ex2(x0.y), p2 = ex2(x1.x), p3 = ex2(x1.y);
+            float p0, p1, p2, p3;
+            if ((e4 & 3) < kBwdPolyQuads) {  // this share of the exponentials runs on the FMA pipe instead of the MUFU
+              const float2 q0 = ex2_poly2(x0), q1 = ex2_poly2(x1);
+              p0 = q0.x, p1 = q0.y, p2 = q1.x, p3 = q1.y;
+            } else {
+              p0 = ex2(x0.x), p1 = ex2(x0.y), p2 = ex2(x1.x), p3 = ex2(x1.y);
+            }
             __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
             pk[2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
             pk[2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
@@ -1026,8 +1319,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // zero for rows past Tq.  8 lanes per row, 16-byte loads.
 __global__ void __launch_bounds__(256)
 attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int64_t o_sb, int64_t o_st,
-                      const float* __restrict__ lse, int B, int H, int Tq, int n_qt, float* __restrict__ stats) {
+                      const float* __restrict__ lse, int B, int H, int Tq, int n_qt, float* __restrict__ stats,
+                      float4* __restrict__ dq_acc4, int64_t n_acc4) {
   const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  // the fp32 dQ accumulator is cleared here as well (one launch and one pass less than a separate memset)
+  for (int64_t i = gid; i < n_acc4; i += int64_t(gridDim.x) * blockDim.x) dq_acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t row_id = gid >> 3;  // (b, h, padded t)
   const int sub = int(gid & 7);
   const int Tp = n_qt * kBlockM;
@@ -1312,6 +1608,28 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                             ? a.d_export + ((int64_t(b) * a.H + h) * a.Tq + row) * W - a.export_lo : nullptr;
     TL_DECL((warp == 0 && lane == 0) ? 1 : -1);
     TL(19);
+    if (int(lane_base) >= a.Tq) {
+      // all 32 query rows of this warp lie past Tq (Tq = 64: half of the softmax warps): their P / dS rows are zero —
+      // written once — and only the barrier protocol is kept going (no TMEM loads, no exponentials, no smem traffic)
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t off = uint32_t((((cs & 1) * 4 + q4) ^ (row & 7)) * 16);
+        sts128(p_row + off, 0u, 0u, 0u, 0u);
+        sts128(ds_row + off, 0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      for (int jj = 0; jj < n_my; ++jj) {
+        const uint32_t par = jj & 1;
+        mbar_wait(&sb->s_full, par);
+        if (lane == 0) mbar_arrive(&sb->s_free);
+        mbar_wait(&sb->dp_full, par);
+        if (lane == 0) mbar_arrive(&sb->dp_free);
+        // one arrival per phase: the live warps may still be writing tile jj-1 when dP(jj) lands
+        if (jj > 0) mbar_wait(&sb->p_ready, (jj - 1) & 1);
+        if (lane == 0) mbar_arrive(&sb->p_ready);
+      }
+    } else
     for (int jj = 0; jj < n_my; ++jj) {
       const uint32_t par = jj & 1;
       uint32_t pk[16], dd[16];
@@ -1475,11 +1793,10 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
   float* dq_acc = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) +
                                            align_up(size_t(p.B) * p.H * n_qt * 2 * kBlockM * sizeof(float), 256));
   const size_t dq_bytes = size_t(p.B) * p.H * n_qt * kBlockM * kHeadDim * sizeof(float);
-  AGA_CUDA_TRY(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   const int64_t stat_threads = int64_t(p.B) * p.H * n_qt * kBlockM * 8;
   attn_bwd_stats_kernel<<<unsigned((stat_threads + 255) / 256), 256, 0, s>>>(
       static_cast<const __nv_bfloat16*>(p.out), static_cast<const __nv_bfloat16*>(bp.dout), p.o_stride_b, p.o_stride_t,
-      p.lse, p.B, p.H, p.Tq, n_qt, stats);
+      p.lse, p.B, p.H, p.Tq, n_qt, stats, reinterpret_cast<float4*>(dq_acc), int64_t(dq_bytes / 16));
   AGA_AFTER_LAUNCH();
   CUtensorMap mq, mk, mv, mdo;
   int st;
