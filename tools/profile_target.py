@@ -11,10 +11,15 @@ def main():
     audio = (0.1 * torch.randn(B, 480000, generator=g)).cuda()
     q, k, v = (torch.randn(B, T, H * 64, generator=g).bfloat16().cuda().requires_grad_() for _ in range(3))
     do = torch.randn(B, T, H * 64, generator=g).bfloat16().cuda()
+    # decoder cross attention (Tq = 64: the one-query-tile backward kernel)
+    qc = torch.randn(B, 64, H * 64, generator=g).bfloat16().cuda().requires_grad_()
+    doc = torch.randn(B, 64, H * 64, generator=g).bfloat16().cuda()
     for _ in range(3):
         A.log_mel_spectrogram(audio)
         out, _, _ = A.qkv_attention(q, k, v, H)
         out.backward(do)
+        oc, _, _ = A.qkv_attention(qc, k, v, H)
+        oc.backward(doc)
     torch.cuda.synchronize()
     print("ok")
 
