@@ -4,7 +4,7 @@
 // four times (attn_ln, adapter_attn_ln, mlp_ln, adapter_mlp_ln; the adapter LNs are the trainable ones), and eager
 // PyTorch turns each call into an fp32 up-cast, the normalisation and a down-cast (5x the algorithmic traffic),
 // with a separate slow column reduction for the gamma/beta gradients.
-//   forward : one warp per row, the row lives in registers (D/32 values per lane, 8- or 16-byte loads),
+//   forward : one warp per row, the row lives in registers (D/32 values per lane, 16-byte loads, all issued up front),
 //             two-pass mean / variance in fp32, writes y in the input dtype and (mean, rstd) for backward.
 //   backward: persistent warps stride over rows; dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dy*gamma; each lane
 //             keeps its columns' dgamma / dbeta partial sums in registers across all its rows, one smem reduction
@@ -19,8 +19,9 @@ namespace {
 
 constexpr int kLnWarps = 8;
 
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
+// V consecutive elements of a row <-> fp32 registers; 16-byte accesses wherever the row length allows (bf16: V = 8)
+template <typename T, int V> struct Vec;
+template <> struct Vec<float, 4> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -29,7 +30,7 @@ template <> struct Vec4<float> {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
 };
-template <> struct Vec4<__nv_bfloat16> {
+template <> struct Vec<__nv_bfloat16, 4> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
     const uint2 t = *reinterpret_cast<const uint2*>(p);
     const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
@@ -44,44 +45,77 @@ template <> struct Vec4<__nv_bfloat16> {
     *reinterpret_cast<uint2*>(p) = t;
   }
 };
+template <> struct Vec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+      v[2 * e] = f.x;
+      v[2 * e + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      w[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <int V> __device__ __forceinline__ void load_f32(const float* p, float (&v)[V]) {
+#pragma unroll
+  for (int q = 0; q < V / 4; ++q) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
 
-// lane l owns columns {128*c + 4*l .. +3 : c < NC}
+// lane l owns columns {32*V*c + V*l .. + V-1 : c < NC}
 template <typename T> __device__ __forceinline__ float round_to(float v);
 template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
 template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 // residual != nullptr: normalises s = T(x + residual) (the sum is rounded to the row dtype first, as the reference's
 // `x + self.model(x)` is) and, when sum_out != nullptr, also writes s — the tensor the backward needs.
-template <typename T, int NC>
+template <typename T, int V, int NC>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, int64_t rows, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, T* __restrict__ y, T* __restrict__ sum_out,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  constexpr int D = NC * 128;
+  constexpr int D = NC * 32 * V;
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* xr = x + row * D;
-  float v[NC][4];
+  float v[NC][V];
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    Vec4<T>::load(xr + c * 128 + lane * 4, v[c]);
-    if (residual) {
-      float rv[4];
-      Vec4<T>::load(residual + row * D + c * 128 + lane * 4, rv);
+  for (int c = 0; c < NC; ++c) Vec<T, V>::load(xr + c * 32 * V + lane * V, v[c]);  // all loads in flight first
+  if (residual) {
+    float rv[NC][V];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[c][e] = round_to<T>(v[c][e] + rv[e]);
-      if (sum_out) Vec4<T>::store(sum_out + row * D + c * 128 + lane * 4, v[c]);
+    for (int c = 0; c < NC; ++c) Vec<T, V>::load(residual + row * D + c * 32 * V + lane * V, rv[c]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[c][e] = round_to<T>(v[c][e] + rv[c][e]);
+      if (sum_out) Vec<T, V>::store(sum_out + row * D + c * 32 * V + lane * V, v[c]);
     }
-    sum += (v[c][0] + v[c][1]) + (v[c][2] + v[c][3]);
   }
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int e = 0; e < V; ++e) sum += v[c][e];
   const float mean = warp_sum(sum) * (1.0f / D);
   float sq = 0.f;
 #pragma unroll
   for (int c = 0; c < NC; ++c)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < V; ++e) {
       const float d = v[c][e] - mean;
       sq = fmaf(d, d, sq);
     }
@@ -89,14 +123,12 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, in
   T* yr = y + row * D;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c * 128 + lane * 4));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c * 128 + lane * 4));
-    float o[4];
-    o[0] = fmaf((v[c][0] - mean) * rstd, g.x, b.x);
-    o[1] = fmaf((v[c][1] - mean) * rstd, g.y, b.y);
-    o[2] = fmaf((v[c][2] - mean) * rstd, g.z, b.z);
-    o[3] = fmaf((v[c][3] - mean) * rstd, g.w, b.w);
-    Vec4<T>::store(yr + c * 128 + lane * 4, o);
+    float g[V], b[V], o[V];
+    load_f32<V>(gamma + c * 32 * V + lane * V, g);
+    load_f32<V>(beta + c * 32 * V + lane * V, b);
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = fmaf((v[c][e] - mean) * rstd, g[e], b[e]);
+    Vec<T, V>::store(yr + c * 32 * V + lane * V, o);
   }
   if (lane == 0) {
     mean_out[row] = mean;
@@ -106,131 +138,133 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, in
 
 // kParamGrads == 2 additionally accumulates dxsum[c] = sum_rows dx[row, c]: when the normalised tensor is
 // x + Linear(...)(x), that column sum IS the gradient of the Linear's bias (saves a separate reduction pass).
-template <typename T, int NC, int kParamGrads>
+template <typename T, int V, int NC, int kParamGrads>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t rows, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
-  constexpr int D = NC * 128;
+  constexpr int D = NC * 32 * V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float g[NC][4];
+  float g[NC][V];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(gamma + c * 128 + lane * 4));
-    g[c][0] = t.x; g[c][1] = t.y; g[c][2] = t.z; g[c][3] = t.w;
-  }
-  float ag[NC][4], ab[NC][4], ax[kParamGrads == 2 ? NC : 1][4];
+  for (int c = 0; c < NC; ++c) load_f32<V>(gamma + c * 32 * V + lane * V, g[c]);
+  float ag[NC][V], ab[NC][V], ax[kParamGrads == 2 ? NC : 1][V];
   if (kParamGrads) {
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) ag[c][e] = ab[c][e] = 0.f;
+      for (int e = 0; e < V; ++e) ag[c][e] = ab[c][e] = 0.f;
   }
   if (kParamGrads == 2) {
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) ax[c][e] = 0.f;
+      for (int e = 0; e < V; ++e) ax[c][e] = 0.f;
   }
   const int64_t stride = int64_t(gridDim.x) * kLnWarps;
   for (int64_t row = int64_t(blockIdx.x) * kLnWarps + warp; row < rows; row += stride) {
     const float mu = mean[row], rs = rstd[row];
-    float xh[NC][4], gy[NC][4];
+    float xh[NC][V], gy[NC][V];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      float xv[4], dv[4];
-      Vec4<T>::load(x + row * D + c * 128 + lane * 4, xv);
-      Vec4<T>::load(dy + row * D + c * 128 + lane * 4, dv);
+      Vec<T, V>::load(x + row * D + c * 32 * V + lane * V, xh[c]);
+      Vec<T, V>::load(dy + row * D + c * 32 * V + lane * V, gy[c]);
+    }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        xh[c][e] = (xv[e] - mu) * rs;
-        gy[c][e] = dv[e] * g[c][e];
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float dv = gy[c][e];
+        xh[c][e] = (xh[c][e] - mu) * rs;
+        gy[c][e] = dv * g[c][e];
         s1 += gy[c][e];
         s2 = fmaf(gy[c][e], xh[c][e], s2);
         if (kParamGrads) {
-          ag[c][e] = fmaf(dv[e], xh[c][e], ag[c][e]);
-          ab[c][e] += dv[e];
+          ag[c][e] = fmaf(dv, xh[c][e], ag[c][e]);
+          ab[c][e] += dv;
         }
       }
     }
     const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      float o[4];
+      float o[V];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < V; ++e) {
         o[e] = rs * (gy[c][e] - c1 - xh[c][e] * c2);
         if (kParamGrads == 2) ax[c][e] += o[e];
       }
-      Vec4<T>::store(dx + row * D + c * 128 + lane * 4, o);
+      Vec<T, V>::store(dx + row * D + c * 32 * V + lane * V, o);
     }
   }
   if (kParamGrads) {
-    __shared__ float red[kLnWarps][128];
+    __shared__ float red[kLnWarps][32 * V];
 #pragma unroll 1
     for (int pass = 0; pass < (kParamGrads == 2 ? 3 : 2); ++pass) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         __syncthreads();
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          red[warp][lane * 4 + e] = pass == 0 ? ag[c][e] : (pass == 1 ? ab[c][e] : ax[kParamGrads == 2 ? c : 0][e]);
+        for (int e = 0; e < V; ++e)
+          red[warp][lane * V + e] = pass == 0 ? ag[c][e] : (pass == 1 ? ab[c][e] : ax[kParamGrads == 2 ? c : 0][e]);
         __syncthreads();
-        if (threadIdx.x < 128) {
+        for (int col = threadIdx.x; col < 32 * V; col += kLnWarps * 32) {
           float t = 0.f;
 #pragma unroll
-          for (int w = 0; w < kLnWarps; ++w) t += red[w][threadIdx.x];
-          atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum)) + c * 128 + threadIdx.x, t);
+          for (int w = 0; w < kLnWarps; ++w) t += red[w][col];
+          atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum)) + c * 32 * V + col, t);
         }
       }
     }
   }
 }
 
-template <typename T, int NC>
+template <typename T, int V, int NC>
 int launch_fwd(const void* x, const void* residual, int64_t rows, const float* gamma, const float* beta, float eps, void* y,
                void* sum_out, float* mean, float* rstd, cudaStream_t s) {
   const unsigned grid = unsigned((rows + kLnWarps - 1) / kLnWarps);
-  layernorm_fwd_kernel<T, NC><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(residual), rows,
-                                                              gamma, beta, eps, static_cast<T*>(y), static_cast<T*>(sum_out),
-                                                              mean, rstd);
+  layernorm_fwd_kernel<T, V, NC><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(residual), rows,
+                                                                 gamma, beta, eps, static_cast<T*>(y), static_cast<T*>(sum_out),
+                                                                 mean, rstd);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }
 
-template <typename T, int NC>
+template <typename T, int V, int NC>
 int launch_bwd(const void* dy, const void* x, int64_t rows, const float* gamma, const float* mean, const float* rstd,
                void* dx, float* dgamma, float* dbeta, float* dxsum, cudaStream_t s) {
+  constexpr int D = NC * 32 * V;
   const int64_t want = (rows + kLnWarps - 1) / kLnWarps;
   const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 4)));
   if (dgamma && dbeta) {
-    AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, NC * 128 * sizeof(float), s));
-    AGA_CUDA_TRY(cudaMemsetAsync(dbeta, 0, NC * 128 * sizeof(float), s));
+    AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, D * sizeof(float), s));
+    AGA_CUDA_TRY(cudaMemsetAsync(dbeta, 0, D * sizeof(float), s));
     if (dxsum) {
-      AGA_CUDA_TRY(cudaMemsetAsync(dxsum, 0, NC * 128 * sizeof(float), s));
-      layernorm_bwd_kernel<T, NC, 2><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
-                                                                     gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta, dxsum);
+      AGA_CUDA_TRY(cudaMemsetAsync(dxsum, 0, D * sizeof(float), s));
+      layernorm_bwd_kernel<T, V, NC, 2><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
+                                                                        gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta, dxsum);
     } else {
-      layernorm_bwd_kernel<T, NC, 1><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
-                                                                     gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta, nullptr);
+      layernorm_bwd_kernel<T, V, NC, 1><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
+                                                                        gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta, nullptr);
     }
   } else {
-    layernorm_bwd_kernel<T, NC, 0><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows, gamma,
-                                                                   mean, rstd, static_cast<T*>(dx), nullptr, nullptr, nullptr);
+    layernorm_bwd_kernel<T, V, NC, 0><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows, gamma,
+                                                                      mean, rstd, static_cast<T*>(dx), nullptr, nullptr, nullptr);
   }
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }
 
-#define AGA_LN_DISPATCH(FN, ...)                                                            \
-  switch (D / 128) {                                                                        \
-    case 3:  return bf16 ? FN<__nv_bfloat16, 3>(__VA_ARGS__)  : FN<float, 3>(__VA_ARGS__);  \
-    case 4:  return bf16 ? FN<__nv_bfloat16, 4>(__VA_ARGS__)  : FN<float, 4>(__VA_ARGS__);  \
-    case 6:  return bf16 ? FN<__nv_bfloat16, 6>(__VA_ARGS__)  : FN<float, 6>(__VA_ARGS__);  \
-    case 8:  return bf16 ? FN<__nv_bfloat16, 8>(__VA_ARGS__)  : FN<float, 8>(__VA_ARGS__);  \
-    case 10: return bf16 ? FN<__nv_bfloat16, 10>(__VA_ARGS__) : FN<float, 10>(__VA_ARGS__); \
-    default: return AGA_ERR_UNSUPPORTED;                                                    \
+// bf16 rows of 512 / 768 / 1024 / 1280 columns use 16-byte (8-element) accesses; 384 (whisper-tiny) and fp32 rows 4 elements
+#define AGA_LN_DISPATCH(FN, ...)                                                                 \
+  switch (D) {                                                                                   \
+    case 384:  return bf16 ? FN<__nv_bfloat16, 4, 3>(__VA_ARGS__) : FN<float, 4, 3>(__VA_ARGS__);  \
+    case 512:  return bf16 ? FN<__nv_bfloat16, 8, 2>(__VA_ARGS__) : FN<float, 4, 4>(__VA_ARGS__);  \
+    case 768:  return bf16 ? FN<__nv_bfloat16, 8, 3>(__VA_ARGS__) : FN<float, 4, 6>(__VA_ARGS__);  \
+    case 1024: return bf16 ? FN<__nv_bfloat16, 8, 4>(__VA_ARGS__) : FN<float, 4, 8>(__VA_ARGS__);  \
+    case 1280: return bf16 ? FN<__nv_bfloat16, 8, 5>(__VA_ARGS__) : FN<float, 4, 10>(__VA_ARGS__); \
+    default: return AGA_ERR_UNSUPPORTED;                                                         \
   }
 
 int check(const void* a, const void* b, int dtype, int64_t rows, int D) {
