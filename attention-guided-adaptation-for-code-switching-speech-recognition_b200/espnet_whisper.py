@@ -111,11 +111,12 @@ class OpenAIWhisperDecoder(torch.nn.Module):
                  whisper_model: str = "small", download_dir: Optional[str] = None, src_layer: int = 12,
                  whisper_cs: bool = False, pe_whisper: bool = False, adapter: bool = False, side_network: bool = False,
                  side_network_conf=None, c_val_attention: float = 0.6, estimate_c: bool = False,
-                 export_mode: str = "full", export_kind: str = "logits", seed: int = 0):
+                 export_mode: str = "full", export_kind: str = "logits", seed: int = 0, kv_cache: bool = False):
         super().__init__()
         _model = W.load_model(whisper_model, adapter, pe_whisper, side_network, side_network_conf,
                               download_root=download_dir, seed=seed)
         self.sidenetwork = side_network
+        self.kv_cache = kv_cache  # forward_one_step / score / batch_score keep per-hypothesis K/V states
         self.decoders = copy.deepcopy(_model.decoder)
         self.decoders.train()
         del _model
@@ -163,15 +164,23 @@ class OpenAIWhisperDecoder(torch.nn.Module):
         return logits, attention_scores
 
     def forward_one_step(self, tgt: torch.Tensor, tgt_mask: torch.Tensor, memory: torch.Tensor,
-                         cache: List[torch.Tensor] = None, side_encoder_output: torch.Tensor = None,
+                         cache: List[Any] = None, side_encoder_output: torch.Tensor = None,
                          return_maps: bool = False):
-        """whisper_decoder.py:172-244: whole-prefix recompute, last position -> log_softmax.
+        """whisper_decoder.py:172-244: whole-prefix recompute, last position -> log_softmax; returns (logp, None).
 
         The reference dumps every layer's map to the CPU each step (:230); here maps stay on the device and are
-        only produced when ``return_maps`` is set (then stored in ``self.att_map`` as a list of (n,H,t,t))."""
+        only produced when ``return_maps`` is set (then stored in ``self.att_map`` as a list of (n,H,t,t)).
+
+        With ``kv_cache=True`` (constructor) the call is incremental instead: ``cache`` is None on the first call
+        (the whole prefix is processed, the cross-attention K/V are projected once) or the state returned by the
+        previous call, a list over layers of (self K, self V, cross K, cross V) with a leading batch dimension; only
+        the last token of ``tgt`` is run and (logp, new state) is returned — O(t) per step instead of O(t^2), no
+        device->host copies.  Same logits as the recompute path."""
         dec = self.decoders
         if tgt.size(1) > 448:
             tgt = tgt[:, :448]
+        if self.kv_cache and not return_maps:
+            return self._forward_one_step_cached(tgt, memory, cache)
         x = dec.token_embedding(tgt) + dec.positional_embedding[: tgt.size(1)]
         x = self.dropout(x).to(memory.dtype)
         self._set_export(return_maps, mode="full")
@@ -189,10 +198,43 @@ class OpenAIWhisperDecoder(torch.nn.Module):
         y = dec.vocab_logits(x[:, -1])
         return torch.log_softmax(y, dim=-1), None
 
+    def _forward_one_step_cached(self, tgt: torch.Tensor, memory: torch.Tensor, cache: Optional[List[Any]]):
+        dec = self.decoders
+        t = tgt.size(1)
+        self._set_export(False)
+        if cache is None:  # prefill
+            x = dec.token_embedding(tgt) + dec.positional_embedding[:t]
+        else:
+            if cache[0][0].size(1) != t - 1:
+                raise ValueError("kv cache holds %d positions, the prefix has %d" % (cache[0][0].size(1), t))
+            x = dec.token_embedding(tgt[:, -1:]) + dec.positional_embedding[t - 1: t]
+        x = self.dropout(x).to(memory.dtype)
+        new_cache = []
+        last = len(dec.blocks) - 1
+        for layer, block in enumerate(dec.blocks):
+            x, st = block.step(x, memory, None if cache is None else cache[layer])
+            new_cache.append(st)
+            if layer < last:
+                x = self.dropout(x)
+        x = dec.ln(x[:, -1])
+        return torch.log_softmax(dec.vocab_logits(x), dim=-1), new_cache
+
     def score(self, ys, state, x):
+        if self.kv_cache and state is not None:
+            state = [tuple(t.unsqueeze(0) for t in layer) for layer in state]
         logp, state = self.forward_one_step(ys.unsqueeze(0), torch.empty(0), x.unsqueeze(0), cache=state)
+        if state is not None:
+            state = [tuple(t.squeeze(0) for t in layer) for layer in state]
         return logp.squeeze(0), state
 
     def batch_score(self, ys: torch.Tensor, states: List[Any], xs: torch.Tensor, x_enc: torch.Tensor = None):
-        logp, _ = self.forward_one_step(ys, torch.empty(0), xs, cache=None, side_encoder_output=x_enc)
-        return logp, None
+        """ESPnet's BatchScorerInterface: per-hypothesis states (no batch dimension) are stacked, run, and split again
+        (the reference keeps no state and returns None, whisper_decoder.py:246-273)."""
+        cache = None
+        if self.kv_cache and states and states[0] is not None:
+            n_layer = len(states[0])
+            cache = [tuple(torch.stack([st[layer][i] for st in states]) for i in range(4)) for layer in range(n_layer)]
+        logp, new = self.forward_one_step(ys, torch.empty(0), xs, cache=cache, side_encoder_output=x_enc)
+        if new is None:
+            return logp, None
+        return logp, [[tuple(t[b] for t in layer) for layer in new] for b in range(ys.size(0))]

@@ -172,6 +172,25 @@ class MultiHeadAttention(nn.Module):
                                                          head_sel=self.head_sel, impl=self.impl)
         return self.out(out), second
 
+    def step(self, x: Tensor, past_k: Optional[Tensor] = None, past_v: Optional[Tensor] = None,
+             cross_kv: Optional[Tuple[Tensor, Tensor]] = None):
+        """Incremental attention for KV-cached decoding (the reference recomputes the whole prefix
+        on every step, whisper_decoder.py:172-244).  Self attention (``cross_kv`` None): the keys / values of the new
+        tokens ``x`` (n, t_new, D) are appended to ``past_k`` / ``past_v`` and returned; cross attention: the K / V of
+        the encoder output, projected once, are passed in.  Same arithmetic as ``forward`` on the full prefix."""
+        q = self.query(x)
+        if cross_kv is not None:
+            k, v = cross_kv
+            out, _, _ = ops.qkv_attention(q, k, v, self.n_head, causal=False, impl=self.impl)
+            return self.out(out)
+        k, v = self.key(x), self.value(x)
+        if past_k is not None:
+            k, v = torch.cat([past_k, k], dim=1), torch.cat([past_v, v], dim=1)
+        if q.shape[1] > 1 and q.shape[1] != k.shape[1]:
+            raise ValueError("chunked prefill is not supported: feed the whole prefix first, then one token per step")
+        out, _, _ = ops.qkv_attention(q, k, v, self.n_head, causal=q.shape[1] > 1, impl=self.impl)
+        return self.out(out), k, v
+
     def qkv_attention(self, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor] = None):
         # The only mask the reference ever passes is TextDecoder.mask = triu(-inf) (whisper/model.py:322,103),
         # i.e. "mask is not None" <=> causal over equal-length q/k.
@@ -228,6 +247,24 @@ class ResidualAttentionBlock(nn.Module):
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x, second
+
+    def step(self, x: Tensor, xa: Tensor, cache: Optional[Tuple[Tensor, Tensor, Tensor, Tensor]] = None):
+        """``forward`` for the new tokens only.  ``cache`` = (self K, self V, cross K, cross V) of the prefix, or None on
+        the first call (prefill: x is the whole prefix); returns (x, updated cache)."""
+        a, k, v = self.attn.step(self.attn_ln(x), *((cache[0], cache[1]) if cache is not None else (None, None)))
+        x = x + a
+        if self.adapter_flag:
+            x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)
+        if cache is not None:
+            kc, vc = cache[2], cache[3]
+        else:
+            src = xa.to(x.dtype)
+            kc, vc = self.cross_attn.key(src), self.cross_attn.value(src)
+        x = x + self.cross_attn.step(self.cross_attn_ln(x), cross_kv=(kc, vc))
+        x = x + self.mlp(self.mlp_ln(x))
+        if self.adapter_flag:
+            x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
+        return x, (k, v, kc, vc)
 
     @staticmethod
     def _adapter_ln(adapter: "Adapter", ln: "LayerNorm", x: Tensor) -> Tensor:

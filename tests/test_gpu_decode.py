@@ -42,3 +42,52 @@ def test_greedy_decode_matches_reference(golden_dir):
     assert np.array_equal(np.isinf(maps), np.isinf(ref))
     fin = np.isfinite(ref)
     np.testing.assert_allclose(maps[fin], ref[fin], rtol=2e-3, atol=2e-3)
+
+
+def test_kv_cached_decode_matches_recompute_and_reference(golden_dir):
+    """incremental decoding (self K/V appended, cross K/V projected once) gives the reference's greedy
+    hypothesis on the bundled utterance and the recompute path's log-probabilities; batch_score / score carry the
+    per-hypothesis states ESPnet's beam search expects."""
+    import aga_b200  # noqa: F401
+    from aga_b200 import espnet_whisper as EW
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = np.load(os.path.join(golden_dir, "decode_seame.npz"))
+    enc = EW.OpenAIWhisperEncoder(whisper_model="small", adapter=True).cuda().eval()
+    dec = EW.OpenAIWhisperDecoder(51865, 768, whisper_model="small", adapter=True, whisper_cs=True, src_layer=1,
+                                  kv_cache=True).cuda().eval()
+    speech = torch.from_numpy(g["pcm"].astype(np.float32) / 32768.0)[None].cuda()
+    n_steps = len(g["token_ids"])
+    with torch.no_grad():
+        enc_out, _, _ = enc(speech, torch.tensor([41760], device="cuda"))
+        ys = torch.tensor([[50258, 50260, 50259, 50359, 50363]], device="cuda")
+        ids, logps, cache = [], [], None
+        for step in range(n_steps):
+            logp, cache = dec.forward_one_step(ys, torch.empty(0), enc_out, cache=cache)
+            assert cache[0][0].shape == (1, ys.size(1), 768) and cache[0][2].shape == (1, 131, 768)
+            nxt = int(logp[0].argmax())
+            ids.append(nxt)
+            logps.append(float(logp[0, nxt]))
+            ys = torch.cat([ys, torch.tensor([[nxt]], device="cuda")], dim=1)
+        assert ids == g["token_ids"].tolist()
+        np.testing.assert_allclose(np.array(logps), g["logp"], rtol=1e-3, atol=1e-3)
+        # the same prefix through the recompute path (kv_cache off): same distribution over the whole vocabulary
+        dec.kv_cache = False
+        ref_logp, none_state = dec.forward_one_step(ys[:, :-1], torch.empty(0), enc_out)
+        assert none_state is None
+        dec.kv_cache = True
+        torch.testing.assert_close(logp, ref_logp, rtol=1e-3, atol=1e-3)
+        # ESPnet scorer interface: two hypotheses of equal length, states stacked / split per hypothesis
+        h1, h2 = ys[0, :7], torch.cat([ys[0, :6], torch.tensor([11], device="cuda")])
+        s1 = s2 = None
+        for t in range(5, 8):
+            lp1, s1 = dec.score(h1[:t], s1, enc_out[0])
+            lp2, s2 = dec.score(h2[:t], s2, enc_out[0])
+        lpb, sb = dec.batch_score(torch.stack([h1, h2]), [None, None], enc_out.expand(2, -1, -1))
+        torch.testing.assert_close(lpb, torch.stack([lp1, lp2]), rtol=1e-3, atol=1e-3)
+        nxt = torch.stack([torch.cat([h1, lp1.argmax()[None]]), torch.cat([h2, lp2.argmax()[None]])])
+        lpc, sc = dec.batch_score(nxt, sb, enc_out.expand(2, -1, -1))  # one incremental step from the batched states
+        lpd, _ = dec.batch_score(nxt, [None, None], enc_out.expand(2, -1, -1))
+        torch.testing.assert_close(lpc, lpd, rtol=1e-3, atol=1e-3)
+        assert len(sc) == 2 and sc[0][0][0].shape == (8, 768)
