@@ -215,11 +215,17 @@ class ESPnetASRModel(torch.nn.Module):
             ys_in_pad, ys_out_pad = add_sos_eos(ys_pad, self.sos, self.eos, self.ignore_id)
         ys_in_lens = ys_pad_lens + 1
         decoder_out, att_map = self.decoder(encoder_out, encoder_out_lens, ys_in_pad, ys_in_lens)
-        loss_att = self.criterion_att(decoder_out, ys_out_pad)
+        fused = isinstance(decoder_out, ops.VocabLogits)
+        if fused:  # decoder(fused_loss=True): KL loss + accuracy straight from the padded logits, no fp32 (B,T,V) tensor
+            c = self.criterion_att
+            loss_att, acc_att = ops.ls_cross_entropy(decoder_out, ys_out_pad, c.padding_idx, c.smoothing, c.normalize_length)
+        else:
+            loss_att = self.criterion_att(decoder_out, ys_out_pad)
         loss_cs = None
         if self.is_encoder_whisper and self.cs_weight != 0:
             loss_cs = self.calculate_cs_loss(att_map, ys_in_pad, self.c_val_attention)
-        acc_att = th_accuracy(decoder_out.view(-1, self.vocab_size), ys_out_pad, ignore_label=self.ignore_id)
+        if not fused:
+            acc_att = th_accuracy(decoder_out.view(-1, self.vocab_size), ys_out_pad, ignore_label=self.ignore_id)
         return loss_att, acc_att, None, None, loss_cs
 
     def forward(self, speech: torch.Tensor, speech_lengths: torch.Tensor, text: torch.Tensor,

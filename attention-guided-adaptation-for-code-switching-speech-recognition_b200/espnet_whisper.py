@@ -111,11 +111,15 @@ class OpenAIWhisperDecoder(torch.nn.Module):
                  whisper_model: str = "small", download_dir: Optional[str] = None, src_layer: int = 12,
                  whisper_cs: bool = False, pe_whisper: bool = False, adapter: bool = False, side_network: bool = False,
                  side_network_conf=None, c_val_attention: float = 0.6, estimate_c: bool = False,
-                 export_mode: str = "full", export_kind: str = "logits", seed: int = 0, kv_cache: bool = False):
+                 export_mode: str = "full", export_kind: str = "logits", seed: int = 0, kv_cache: bool = False,
+                 fused_loss: bool = False):
         super().__init__()
         _model = W.load_model(whisper_model, adapter, pe_whisper, side_network, side_network_conf,
                               download_root=download_dir, seed=seed)
         self.sidenetwork = side_network
+        # forward() returns an ops.VocabLogits handle (padded logits in the GEMM's dtype) instead of the fp32 (B,T,V)
+        # tensor; ESPnetASRModel feeds it to the fused label-smoothing loss / accuracy
+        self.fused_loss = fused_loss
         self.kv_cache = kv_cache  # forward_one_step / score / batch_score keep per-hypothesis K/V states
         self.decoders = copy.deepcopy(_model.decoder)
         self.decoders.train()
@@ -158,7 +162,7 @@ class OpenAIWhisperDecoder(torch.nn.Module):
             if self.whisper_cs and layer >= self.src_layer:
                 attention_scores.append(attention_map)
         x = dec.ln(x)
-        logits = dec.vocab_logits(x)
+        logits = dec.vocab_logits(x, lazy=self.fused_loss)
         if self.whisper_cs:
             return logits, torch.stack(attention_scores)
         return logits, attention_scores

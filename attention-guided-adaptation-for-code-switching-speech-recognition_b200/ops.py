@@ -516,6 +516,83 @@ def adapter_layer_norm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: 
 
 
 # ------------------------------------------------------------------------------------------------
+# 8f #4. vocabulary logits -> label-smoothing KL loss + accuracy, without fp32 logits
+# ------------------------------------------------------------------------------------------------
+class VocabLogits:
+    """The decoder's logits as the aligned GEMM left them: ``padded`` (..., ld) in the activation dtype, of which the
+    first ``n_vocab`` columns are real (ld = n_vocab rounded up to 64).  ``materialize()`` gives the reference's tensor
+    ``(x @ tok_emb.T).float()`` (whisper_decoder.py:164-166); ``ops.ls_cross_entropy`` consumes the handle directly."""
+
+    def __init__(self, padded: torch.Tensor, n_vocab: int):
+        self.padded, self.n_vocab = padded, int(n_vocab)
+
+    def materialize(self) -> torch.Tensor:
+        return self.padded[..., : self.n_vocab].float()
+
+    @property
+    def shape(self):
+        return tuple(self.padded.shape[:-1]) + (self.n_vocab,)
+
+
+class _LsCeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits2, target, n_vocab, padding_idx, smoothing, denom):
+        _require_cuda(logits2, "logits")
+        rows, ld = logits2.shape
+        row_loss = torch.empty(rows, dtype=torch.float32, device=logits2.device)
+        row_lse = torch.empty(rows, dtype=torch.float32, device=logits2.device)
+        row_correct = torch.empty(rows, dtype=torch.int32, device=logits2.device)
+        L.check(L.lib().aga_ls_ce_fwd(_ptr(logits2), _DTYPES[logits2.dtype], rows, n_vocab, ld, _ptr(target), padding_idx,
+                                      float(smoothing), _ptr(row_loss), _ptr(row_lse), _ptr(row_correct),
+                                      _stream_ptr(logits2.device)), "aga_ls_ce_fwd")
+        ctx.save_for_backward(logits2, target, row_lse, denom)
+        ctx.cfg = (n_vocab, padding_idx, float(smoothing))
+        ctx.mark_non_differentiable(row_correct)
+        return row_loss.sum() / denom, row_correct
+
+    @staticmethod
+    def backward(ctx, g, _):
+        logits2, target, row_lse, denom = ctx.saved_tensors
+        n_vocab, padding_idx, smoothing = ctx.cfg
+        rows, ld = logits2.shape
+        gscale = (g.float() / denom).reshape(1).contiguous()  # upstream gradient / denominator, as a device scalar
+        dlogits = torch.empty_like(logits2)
+        L.check(L.lib().aga_ls_ce_bwd(_ptr(logits2), _DTYPES[logits2.dtype], rows, n_vocab, ld, _ptr(target), padding_idx,
+                                      smoothing, _ptr(row_lse), _ptr(gscale), 1.0, _ptr(dlogits),
+                                      _stream_ptr(logits2.device)), "aga_ls_ce_bwd")
+        return dlogits, None, None, None, None, None
+
+
+def ls_cross_entropy(logits, target: torch.Tensor, padding_idx: int, smoothing: float, normalize_length: bool = False,
+                     n_vocab: Optional[int] = None):
+    """LabelSmoothingLoss.forward (label_smoothing_loss.py:41-63) + th_accuracy (nets_utils.py:304-324) in two kernels.
+
+    ``logits``: a :class:`VocabLogits` handle or a plain (B, T, V) tensor (fp32 / bf16); ``target`` (B, T) int64 with
+    ``padding_idx`` on ignored positions.  Returns (loss, accuracy): loss = sum of the per-token KL / (batch size, or
+    the number of real tokens when ``normalize_length``)."""
+    if isinstance(logits, VocabLogits):
+        padded, n_vocab = logits.padded, logits.n_vocab
+    else:
+        padded = logits
+        n_vocab = n_vocab or logits.shape[-1]
+    if padded.dtype not in _DTYPES:
+        padded = padded.float()
+    vec = 16 // padded.element_size()
+    if padded.shape[-1] % vec != 0:  # unaligned rows (a plain 51865-wide tensor): pad once
+        padded = torch.nn.functional.pad(padded, (0, (-padded.shape[-1]) % vec))
+    batch = padded.shape[0]
+    logits2 = padded.reshape(-1, padded.shape[-1])
+    if not logits2.is_contiguous():
+        logits2 = logits2.contiguous()
+    tgt = target.reshape(-1).to(torch.int64).contiguous()
+    real = (tgt != padding_idx).sum()
+    denom = real.float() if normalize_length else torch.full((), float(batch), dtype=torch.float32, device=logits2.device)
+    loss, correct = _LsCeFn.apply(logits2, tgt, int(n_vocab), int(padding_idx), float(smoothing), denom)
+    acc = correct.sum().float() / real.float()
+    return loss, acc
+
+
+# ------------------------------------------------------------------------------------------------
 # a11 / a12 / a10
 # ------------------------------------------------------------------------------------------------
 def attention_pattern(tokens: torch.Tensor, lid_table: torch.Tensor, c: float = 0.6) -> torch.Tensor:

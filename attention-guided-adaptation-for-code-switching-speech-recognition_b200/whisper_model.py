@@ -358,8 +358,9 @@ class TextDecoder(nn.Module):
         x = self.ln(x)
         return self.vocab_logits(x)
 
-    def vocab_logits(self, x: Tensor) -> Tensor:
-        """``(x @ token_embedding.weight.T).float()`` (whisper/model.py:343-345).
+    def vocab_logits(self, x: Tensor, lazy: bool = False):
+        """``(x @ token_embedding.weight.T).float()`` (whisper/model.py:343-345); ``lazy``: an ``ops.VocabLogits`` handle
+        on the padded GEMM output instead of the fp32 tensor (consumed by ``ops.ls_cross_entropy``).
 
         n_vocab = 51865 is odd: with a leading dimension that is not a multiple of 16 bytes cuBLAS has no TMA / vector
         path and falls back to a legacy sm_75 kernel (650 us forward, 550 us backward at B*T = 1024, 8x slower than the
@@ -369,14 +370,16 @@ class TextDecoder(nn.Module):
         n_vocab = w.shape[0]
         pad = (-n_vocab) % 64
         if not x.is_cuda or pad == 0 or (w.requires_grad and torch.is_grad_enabled()):
-            return (x @ cast_param(self, "_emb_cast", w, x.dtype).t()).float()
+            full = x @ cast_param(self, "_emb_cast", w, x.dtype).t()
+            return ops.VocabLogits(full, n_vocab) if (lazy and x.is_cuda) else full.float()
         c = self.__dict__.get("_emb_pad")
         if c is None or c[0] != (w._version, w.data_ptr(), x.dtype):
             wp = torch.zeros(n_vocab + pad, w.shape[1], dtype=x.dtype, device=w.device)
             wp[:n_vocab] = w.detach()
             c = ((w._version, w.data_ptr(), x.dtype), wp)
             self.__dict__["_emb_pad"] = c
-        return F.linear(x, c[1])[..., :n_vocab].float()
+        padded = F.linear(x, c[1])
+        return ops.VocabLogits(padded, n_vocab) if lazy else padded[..., :n_vocab].float()
 
 
 class Whisper(nn.Module):

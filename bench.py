@@ -69,7 +69,7 @@ def build_model(name, device, export_mode="compact"):
     d = W.MODEL_DIMS[name]
     enc = EW.OpenAIWhisperEncoder(whisper_model=name, adapter=True)
     dec = EW.OpenAIWhisperDecoder(d.n_vocab, d.n_text_state, whisper_model=name, adapter=True, whisper_cs=True,
-                                  src_layer=1, export_mode=export_mode)
+                                  src_layer=1, export_mode=export_mode, fused_loss=str(device) != "cpu")
     toks = [str(i) for i in range(d.n_vocab)]
     toks[50258], toks[50257] = "<|startoftranscript|>", "<|endoftext|>"
     if (d.n_text_layer, d.n_text_head) == (12, 12):

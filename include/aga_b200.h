@@ -184,6 +184,23 @@ AGA_API int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t 
 AGA_API int aga_gelu_bwd_colsum(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh, float* colsum,
                         void* stream);
 
+/* Label-smoothing cross entropy + accuracy on the vocabulary logits, kept in the GEMM's dtype.
+ * Replaces `.float()` of the logits (E2/asr/decoder/whisper_decoder.py:164-166), LabelSmoothingLoss.forward
+ * (espnet/nets/pytorch_backend/transformer/label_smoothing_loss.py:41-63) and th_accuracy
+ * (espnet/nets/pytorch_backend/nets_utils.py:304-324).
+ *   logits  : (rows, ld) AGA_F32 / AGA_BF16, 16-byte aligned rows (ld a multiple of 16 B / sizeof(dtype)); columns [V, ld)
+ *             are padding of the aligned GEMM and ignored
+ *   target  : (rows) int64; rows with target == padding_idx contribute nothing
+ *   fwd     : row_loss[r] = KL(smoothed one-hot || softmax) (0 for ignored rows), row_lse[r] = log-sum-exp,
+ *             row_correct[r] = 1 iff arg-max (lowest index) == target (0 for ignored rows)
+ *   bwd     : dlogits = (*gscale) * inv_denom * (softmax - smoothed one-hot), zero in padding columns / ignored rows;
+ *             gscale = device scalar with the upstream gradient (NULL = 1) */
+AGA_API int aga_ls_ce_fwd(const void* logits, int dtype, int64_t rows, int V, int64_t ld, const int64_t* target,
+                  int64_t padding_idx, float smoothing, float* row_loss, float* row_lse, int32_t* row_correct, void* stream);
+AGA_API int aga_ls_ce_bwd(const void* logits, int dtype, int64_t rows, int V, int64_t ld, const int64_t* target,
+                  int64_t padding_idx, float smoothing, const float* row_lse, const float* gscale, float inv_denom,
+                  void* dlogits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
