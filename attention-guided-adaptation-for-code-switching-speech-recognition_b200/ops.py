@@ -516,6 +516,65 @@ def adapter_layer_norm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: 
 
 
 # ------------------------------------------------------------------------------------------------
+# 8f #2. Linear with the residual add folded into the GEMM
+# ------------------------------------------------------------------------------------------------
+_LR_WORKSPACE = {}
+
+
+def _lr_workspace(device) -> torch.Tensor:
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _LR_WORKSPACE.get(key)
+    if ws is None:
+        n = C.c_size_t()
+        L.check(L.lib().aga_linear_residual_workspace_bytes(C.byref(n)), "aga_linear_residual_workspace_bytes")
+        ws = _LR_WORKSPACE[key] = torch.empty(n.value, dtype=torch.uint8, device=device)
+    return ws
+
+
+class _LinearResidualFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, residual):
+        N, K = w.shape
+        x2 = x.reshape(-1, K)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        r2 = residual.reshape(-1, N)
+        r2 = r2 if r2.is_contiguous() else r2.contiguous()
+        wc = w if w.is_contiguous() else w.contiguous()
+        out = torch.empty_like(r2)
+        ws = _lr_workspace(x.device)
+        st = L.lib().aga_linear_residual(_ptr(x2), _ptr(wc), _ptr(b), _ptr(r2), _ptr(out), _DTYPES[x2.dtype], x2.shape[0], N, K,
+                                         _ptr(ws), ws.numel(), _stream_ptr(x.device))
+        if st == -2:  # AGA_ERR_UNSUPPORTED: no cuBLASLt in the process / unaligned operands -> the two-kernel form
+            out = torch.addmm(r2, x2, wc.t()) if b is None else torch.addmm(b, x2, wc.t()) + r2
+        else:
+            L.check(st, "aga_linear_residual")
+        ctx.save_for_backward(x2 if ctx.needs_input_grad[1] else torch.empty(0), wc)
+        ctx.shapes = (x.shape, residual.shape)
+        return out.view(residual.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, wc = ctx.saved_tensors
+        N, K = wc.shape
+        d2 = dout.reshape(-1, N)
+        dx = (d2 @ wc).view(ctx.shapes[0]) if ctx.needs_input_grad[0] else None
+        dw = (d2.t() @ x2) if ctx.needs_input_grad[1] else None
+        db = d2.sum(0) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, (dout if ctx.needs_input_grad[3] else None)
+
+
+def linear_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor) -> torch.Tensor:
+    """``residual + F.linear(x, weight, bias)`` in one GEMM (cuBLASLt reads the residual as C with beta = 1 and applies the
+    bias in the epilogue): the `x = x + self.attn(...)` / `x = x + self.mlp(...)` adds of ResidualAttentionBlock.forward
+    (whisper/model.py:231-242) without their own pass over the activations.  x, weight, bias, residual share one dtype
+    (fp32 or bf16)."""
+    _require_cuda(x, "x")
+    if not (x.dtype == weight.dtype == residual.dtype and (bias is None or bias.dtype == x.dtype)) or x.dtype not in _DTYPES:
+        raise L.AgaError("linear_residual needs x, weight, bias and residual in one dtype (fp32 or bf16)")
+    return _LinearResidualFn.apply(x, weight, bias, residual)
+
+
+# ------------------------------------------------------------------------------------------------
 # 8f #4. vocabulary logits -> label-smoothing KL loss + accuracy, without fp32 logits
 # ------------------------------------------------------------------------------------------------
 class VocabLogits:

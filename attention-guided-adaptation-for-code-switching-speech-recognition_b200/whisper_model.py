@@ -85,6 +85,18 @@ class Linear(nn.Linear):
         return F.linear(x, cast_param(self, "_w_cast", self.weight, x.dtype), cast_param(self, "_b_cast", self.bias, x.dtype))
 
 
+def linear_plus_residual(lin: "Linear", x: Tensor, residual: Tensor) -> Tensor:
+    """``residual + lin(x)``; for a frozen Linear on a CUDA device the add rides the GEMM (ops.linear_residual)."""
+    frozen = not (lin.weight.requires_grad or (lin.bias is not None and lin.bias.requires_grad))
+    if not (x.is_cuda and frozen):
+        return residual + lin(x)
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    if dt not in (torch.float32, torch.bfloat16):
+        return residual + lin(x)
+    return ops.linear_residual(x.to(dt), cast_param(lin, "_w_cast", lin.weight, dt), cast_param(lin, "_b_cast", lin.bias, dt),
+                               residual.to(dt))
+
+
 class Conv1d(nn.Conv1d):
     def _conv_forward(self, x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
         return super()._conv_forward(x, cast_param(self, "_w_cast", weight, x.dtype),
@@ -123,9 +135,11 @@ class MultiHeadAttention(nn.Module):
         self.impl = "auto"
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
-                kv_cache: Optional[dict] = None):
+                kv_cache: Optional[dict] = None, residual: Optional[Tensor] = None):
+        """``residual``: when given, the first return value is ``residual + out`` (the block's `x = x + attn(...)`, with
+        the add folded into the output projection's GEMM)."""
         if kv_cache is None and x.is_cuda and self._frozen():
-            return self._forward_packed(x, xa, mask)
+            return self._forward_packed(x, xa, mask, residual)
         q = self.query(x)
         if kv_cache is None or xa is None or self.key not in kv_cache:
             src = x if xa is None else xa
@@ -136,7 +150,7 @@ class MultiHeadAttention(nn.Module):
         else:
             k, v = kv_cache[self.key], kv_cache[self.value]
         wv, second = self.qkv_attention(q, k, v, mask)
-        return self.out(wv), second
+        return (self.out(wv) if residual is None else linear_plus_residual(self.out, wv, residual)), second
 
     # ---- frozen projections (the --freeze_param adapter policy): one [q|k|v] (or [k|v]) GEMM, attention on the packed
     #      result, one packed gradient -> one dgrad GEMM.  Same arithmetic as three F.linear calls on row blocks of
@@ -156,7 +170,7 @@ class MultiHeadAttention(nn.Module):
             self.__dict__.setdefault("_packed_cache", {})[with_q] = c
         return c[1], c[2]
 
-    def _forward_packed(self, x: Tensor, xa: Optional[Tensor], mask: Optional[Tensor]):
+    def _forward_packed(self, x: Tensor, xa: Optional[Tensor], mask: Optional[Tensor], residual: Optional[Tensor] = None):
         kind, cols = self.export if self.export is not None else (None, None)
         if xa is None:
             w, b = self._packed_weights(x.dtype, True)
@@ -170,7 +184,7 @@ class MultiHeadAttention(nn.Module):
             kv = F.linear(xa.to(x.dtype), w, b)
             out, _lse, second = ops.qkv_attention_packed(kv, self.n_head, q=q, causal=False, export=kind, export_cols=cols,
                                                          head_sel=self.head_sel, impl=self.impl)
-        return self.out(out), second
+        return (self.out(out) if residual is None else linear_plus_residual(self.out, out, residual)), second
 
     def step(self, x: Tensor, past_k: Optional[Tensor] = None, past_v: Optional[Tensor] = None,
              cross_kv: Optional[Tuple[Tensor, Tensor]] = None):
@@ -237,13 +251,12 @@ class ResidualAttentionBlock(nn.Module):
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
                 kv_cache: Optional[dict] = None):
-        a, second = self.attn(self.attn_ln(x), mask=mask, kv_cache=kv_cache)
-        x = x + a
+        x, second = self.attn(self.attn_ln(x), mask=mask, kv_cache=kv_cache, residual=x)  # x + attn(...)
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)  # post-LN replaces x (:234-236)
         if self.cross_attn is not None:
-            x = x + self.cross_attn(self.cross_attn_ln(x), xa, kv_cache=kv_cache)[0]
-        x = x + self.mlp(self.mlp_ln(x))
+            x = self.cross_attn(self.cross_attn_ln(x), xa, kv_cache=kv_cache, residual=x)[0]
+        x = linear_plus_residual(self.mlp[2], self.mlp[1](self.mlp[0](self.mlp_ln(x))), x)  # x + mlp(...)
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x, second

@@ -147,3 +147,26 @@ def test_conv_stem_gemm_matches_conv1d(A):
             got16 = enc.stem(x)
         assert got16.dtype == torch.bfloat16
         torch.testing.assert_close(got16.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("rows,N,K,with_bias", [(24000, 768, 768, True), (1024, 768, 3072, True), (333, 1280, 1280, False),
+                                                (7, 384, 1536, True)])
+def test_linear_residual_matches_linear_plus_add(A, dtype, tol, rows, N, K, with_bias):
+    """ops.linear_residual == residual + F.linear(x, w, b) (`x = x + self.attn(...)`, whisper/model.py:231-242), forward
+    and the gradients w.r.t. x and the residual."""
+    from aga_b200 import ops
+    g = torch.Generator().manual_seed(rows + N)
+    x = torch.randn(rows, K, generator=g).to(dtype).cuda().requires_grad_()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dtype).cuda()
+    b = torch.randn(N, generator=g).to(dtype).cuda() if with_bias else None
+    r = torch.randn(rows, N, generator=g).to(dtype).cuda().requires_grad_()
+    do = torch.randn(rows, N, generator=g).to(dtype).cuda()
+    out = ops.linear_residual(x, w, b, r)
+    out.backward(do)
+    x64, r64 = x.detach().double(), r.detach().double()
+    ref = r64 + x64 @ w.double().t() + (b.double() if with_bias else 0.0)
+    torch.testing.assert_close(out.double(), ref, rtol=tol, atol=tol * float(ref.abs().max()))
+    dx_ref = do.double() @ w.double()
+    torch.testing.assert_close(x.grad.double(), dx_ref, rtol=tol, atol=tol * float(dx_ref.abs().max()))
+    assert torch.equal(r.grad, do)
