@@ -77,7 +77,7 @@ struct Plan {
 struct Ctx {
   std::mutex mu;
   std::map<int, cublasLtHandle_t> handles;  // per device
-  std::map<std::tuple<int, int, int64_t, int, int, int, size_t>, Plan> plans;
+  std::map<std::tuple<int, int, int64_t, int, int, int, size_t>, Plan> plans;  // (device, dtype | layout, rows, N, K, bias, ws)
 };
 Ctx& ctx() {
   static Ctx c;
@@ -95,12 +95,13 @@ extern "C" int aga_linear_residual_workspace_bytes(size_t* bytes) {
   return AGA_OK;
 }
 
-// out (rows, N) = x (rows, K) @ w (N, K)^T + bias (N) + residual (rows, N); all row-major, contiguous, one dtype.
-extern "C" int aga_linear_residual(const void* x, const void* w, const void* bias, const void* residual, void* out,
-                                   int dtype, int64_t rows, int N, int K, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
+// out (rows, N) = x (rows, K) @ W + bias (N) + residual (rows, N); all row-major, contiguous, one dtype.
+// w_layout 0: w is (N, K) — an nn.Linear weight, W = w^T; 1: w is (K, N), W = w (the dgrad form dY @ weight).
+extern "C" int aga_linear_residual(const void* x, const void* w, int w_layout, const void* bias, const void* residual,
+                                   void* out, int dtype, int64_t rows, int N, int K, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   if (!x || !w || !residual || !out || rows <= 0 || N <= 0 || K <= 0) return AGA_ERR_INVALID_ARGUMENT;
-  if (dtype != AGA_F32 && dtype != AGA_BF16) return AGA_ERR_INVALID_ARGUMENT;
+  if ((dtype != AGA_F32 && dtype != AGA_BF16) || (w_layout != 0 && w_layout != 1)) return AGA_ERR_INVALID_ARGUMENT;
   const LtApi& lt = lt_api();
   if (!lt.ok) return AGA_ERR_UNSUPPORTED;
   const uintptr_t all = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(residual) |
@@ -113,18 +114,19 @@ extern "C" int aga_linear_residual(const void* x, const void* w, const void* bia
   cublasLtHandle_t& handle = c.handles[dev];
   if (!handle && lt.create(&handle) != CUBLAS_STATUS_SUCCESS) return AGA_ERR_CUDA;
   const cudaDataType_t dt = dtype == AGA_BF16 ? CUDA_R_16BF : CUDA_R_32F;
-  const auto key = std::make_tuple(dev, dtype, rows, N, K, bias ? 1 : 0, workspace_bytes);
+  const auto key = std::make_tuple(dev, dtype * 2 + w_layout, rows, N, K, bias ? 1 : 0, workspace_bytes);
   Plan& p = c.plans[key];
   if (!p.valid) {
-    // column-major view: D^T (N x rows) = W (N x K) * x^T (K x rows) + C^T; W row-major (N,K) = col-major (K,N) -> op T
+    // column-major view: D^T (N x rows) = A (N x K) * x^T (K x rows) + C^T.  w row-major (N,K) = col-major (K,N), ld K -> op T;
+    // w row-major (K,N) = col-major (N,K), ld N -> op N
     if (lt.desc_create(&p.op, CUBLAS_COMPUTE_32F, CUDA_R_32F) != CUBLAS_STATUS_SUCCESS) return AGA_ERR_CUDA;
-    const cublasOperation_t ta = CUBLAS_OP_T, tb = CUBLAS_OP_N;
+    const cublasOperation_t ta = w_layout == 0 ? CUBLAS_OP_T : CUBLAS_OP_N, tb = CUBLAS_OP_N;
     lt.desc_set(p.op, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta));
     lt.desc_set(p.op, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb));
     const cublasLtEpilogue_t epi = bias ? CUBLASLT_EPILOGUE_BIAS : CUBLASLT_EPILOGUE_DEFAULT;
     lt.desc_set(p.op, CUBLASLT_MATMUL_DESC_EPILOGUE, &epi, sizeof(epi));
     if (bias) lt.desc_set(p.op, CUBLASLT_MATMUL_DESC_BIAS_DATA_TYPE, &dt, sizeof(dt));
-    bool ok = lt.layout_create(&p.a, dt, K, N, K) == CUBLAS_STATUS_SUCCESS &&
+    bool ok = (w_layout == 0 ? lt.layout_create(&p.a, dt, K, N, K) : lt.layout_create(&p.a, dt, N, K, N)) == CUBLAS_STATUS_SUCCESS &&
               lt.layout_create(&p.b, dt, K, rows, K) == CUBLAS_STATUS_SUCCESS &&
               lt.layout_create(&p.c, dt, N, rows, N) == CUBLAS_STATUS_SUCCESS &&
               lt.layout_create(&p.d, dt, N, rows, N) == CUBLAS_STATUS_SUCCESS;

@@ -504,7 +504,10 @@ class _AdapterLayerNormFn(torch.autograd.Function):
         dw2 = _wgrad(ds.t(), g, dts[2])                # (D, bottleneck)
         dh1, db1 = gelu_bwd_colsum(dg, h1)
         dw1 = _wgrad(dh1.t(), x2, dts[0])              # (bottleneck, D)
-        dx = torch.addmm(ds, dh1, w1c)                 # the residual branch's gradient rides the GEMM's beta = 1
+        if _ADAPTER_BWD_LT:
+            dx = _linear_residual_raw(dh1, w1c, None, ds, w_kn=True)  # ds + dh1 @ W1: the residual branch's gradient rides the GEMM
+        else:
+            dx = torch.addmm(ds, dh1, w1c)
         return (dx.view(ctx.shape), dw1, db1.to(dts[1]), dw2, db2.to(dts[3]), dgamma.to(dts[4]), dbeta.to(dts[5]), None)
 
 
@@ -519,6 +522,8 @@ def adapter_layer_norm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: 
 # 8f #2. Linear with the residual add folded into the GEMM
 # ------------------------------------------------------------------------------------------------
 _LR_WORKSPACE = {}
+import os as _os
+_ADAPTER_BWD_LT = _os.environ.get("AGA_ADAPTER_BWD_LT", "1") != "0"
 
 
 def _lr_workspace(device) -> torch.Tensor:
@@ -531,6 +536,21 @@ def _lr_workspace(device) -> torch.Tensor:
     return ws
 
 
+def _linear_residual_raw(x2: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], r2: torch.Tensor, w_kn: bool = False):
+    """r2 + x2 @ W (+ b) on contiguous 2-D operands; W = w^T for an (N, K) weight, W = w for a (K, N) one (``w_kn``)."""
+    K = x2.shape[1]
+    N = w.shape[1] if w_kn else w.shape[0]
+    out = torch.empty_like(r2)
+    ws = _lr_workspace(x2.device)
+    st = L.lib().aga_linear_residual(_ptr(x2), _ptr(w), 1 if w_kn else 0, _ptr(b), _ptr(r2), _ptr(out), _DTYPES[x2.dtype],
+                                     x2.shape[0], N, K, _ptr(ws), ws.numel(), _stream_ptr(x2.device))
+    if st == -2:  # AGA_ERR_UNSUPPORTED: no cuBLASLt in the process / unaligned operands -> the two-kernel form
+        W = w if w_kn else w.t()
+        return torch.addmm(r2, x2, W) if b is None else torch.addmm(b, x2, W) + r2
+    L.check(st, "aga_linear_residual")
+    return out
+
+
 class _LinearResidualFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, residual):
@@ -540,14 +560,7 @@ class _LinearResidualFn(torch.autograd.Function):
         r2 = residual.reshape(-1, N)
         r2 = r2 if r2.is_contiguous() else r2.contiguous()
         wc = w if w.is_contiguous() else w.contiguous()
-        out = torch.empty_like(r2)
-        ws = _lr_workspace(x.device)
-        st = L.lib().aga_linear_residual(_ptr(x2), _ptr(wc), _ptr(b), _ptr(r2), _ptr(out), _DTYPES[x2.dtype], x2.shape[0], N, K,
-                                         _ptr(ws), ws.numel(), _stream_ptr(x.device))
-        if st == -2:  # AGA_ERR_UNSUPPORTED: no cuBLASLt in the process / unaligned operands -> the two-kernel form
-            out = torch.addmm(r2, x2, wc.t()) if b is None else torch.addmm(b, x2, wc.t()) + r2
-        else:
-            L.check(st, "aga_linear_residual")
+        out = _linear_residual_raw(x2, wc, b, r2)
         ctx.save_for_backward(x2 if ctx.needs_input_grad[1] else torch.empty(0), wc)
         ctx.shapes = (x.shape, residual.shape)
         return out.view(residual.shape)

@@ -201,14 +201,15 @@ AGA_API int aga_ls_ce_bwd(const void* logits, int dtype, int64_t rows, int V, in
                   int64_t padding_idx, float smoothing, const float* row_lse, const float* gscale, float inv_denom,
                   void* dlogits, void* stream);
 
-/* out (rows, N) = x (rows, K) @ w (N, K)^T + bias (N) + residual (rows, N): a Linear with the residual add folded into the
+/* out (rows, N) = x (rows, K) @ W + bias (N) + residual (rows, N), W = w^T for w_layout 0 (w is an (N, K) nn.Linear weight)
+ * or W = w for w_layout 1 (w is (K, N): the dgrad form dY @ weight): a Linear with the residual add folded into the
  * GEMM (cuBLASLt: C = residual, beta = 1, bias epilogue) — `x = x + self.attn(...)`, `x = x + self.mlp(...)` of
  * ResidualAttentionBlock.forward (W/model.py:231-242).  All row-major contiguous, one dtype, 16-byte
  * aligned; bias may be NULL; workspace of aga_linear_residual_workspace_bytes() bytes.  AGA_ERR_UNSUPPORTED when cuBLASLt
  * is not available in the process. */
 AGA_API int aga_linear_residual_workspace_bytes(size_t* bytes);
-AGA_API int aga_linear_residual(const void* x, const void* w, const void* bias, const void* residual, void* out, int dtype,
-                        int64_t rows, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
+AGA_API int aga_linear_residual(const void* x, const void* w, int w_layout, const void* bias, const void* residual, void* out,
+                        int dtype, int64_t rows, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
