@@ -141,8 +141,8 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, in
 template <typename T, int V, int NC, int kParamGrads>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t rows, const float* __restrict__ gamma,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ dres,
+                     T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int D = NC * 32 * V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[NC][V];
@@ -195,6 +195,12 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t 
         o[e] = rs * (gy[c][e] - c1 - xh[c][e] * c2);
         if (kParamGrads == 2) ax[c][e] += o[e];
       }
+      if (dres) {  // the gradient that reached the same tensor through the residual connection: one pass instead of an add kernel
+        float r[V];
+        Vec<T, V>::load(dres + row * D + c * 32 * V + lane * V, r);
+#pragma unroll
+        for (int e = 0; e < V; ++e) o[e] = round_to<T>(o[e]) + r[e];
+      }
       Vec<T, V>::store(dx + row * D + c * 32 * V + lane * V, o);
     }
   }
@@ -233,7 +239,7 @@ int launch_fwd(const void* x, const void* residual, int64_t rows, const float* g
 
 template <typename T, int V, int NC>
 int launch_bwd(const void* dy, const void* x, int64_t rows, const float* gamma, const float* mean, const float* rstd,
-               void* dx, float* dgamma, float* dbeta, float* dxsum, cudaStream_t s) {
+               const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, cudaStream_t s) {
   constexpr int D = NC * 32 * V;
   const int64_t want = (rows + kLnWarps - 1) / kLnWarps;
   const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 4)));
@@ -243,14 +249,14 @@ int launch_bwd(const void* dy, const void* x, int64_t rows, const float* gamma, 
     if (dxsum) {
       AGA_CUDA_TRY(cudaMemsetAsync(dxsum, 0, D * sizeof(float), s));
       layernorm_bwd_kernel<T, V, NC, 2><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
-                                                                        gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta, dxsum);
+                                                                        gamma, mean, rstd, static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, dxsum);
     } else {
       layernorm_bwd_kernel<T, V, NC, 1><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
-                                                                        gamma, mean, rstd, static_cast<T*>(dx), dgamma, dbeta, nullptr);
+                                                                        gamma, mean, rstd, static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, nullptr);
     }
   } else {
     layernorm_bwd_kernel<T, V, NC, 0><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows, gamma,
-                                                                      mean, rstd, static_cast<T*>(dx), nullptr, nullptr, nullptr);
+                                                                      mean, rstd, static_cast<const T*>(dres), static_cast<T*>(dx), nullptr, nullptr, nullptr);
   }
   AGA_AFTER_LAUNCH();
   return AGA_OK;
@@ -293,14 +299,14 @@ extern "C" int aga_layernorm_fwd(const void* x, const void* residual, int dtype,
 }
 
 extern "C" int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
-                                 const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                                 float* dxsum, void* stream) {
+                                 const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma,
+                                 float* dbeta, float* dxsum, void* stream) {
   int st = check(x, dx, dtype, rows, D);
   if (st != AGA_OK) return st;
   if (!dy || !gamma || !mean || !rstd || ((dgamma == nullptr) != (dbeta == nullptr)) || (dxsum && !dgamma))
     return AGA_ERR_INVALID_ARGUMENT;
-  if (reinterpret_cast<uintptr_t>(dy) & 15) return AGA_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dres)) & 15) return AGA_ERR_UNSUPPORTED;
   const bool bf16 = dtype == AGA_BF16;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  AGA_LN_DISPATCH(launch_bwd, dy, x, rows, gamma, mean, rstd, dx, dgamma, dbeta, dxsum, s)
+  AGA_LN_DISPATCH(launch_bwd, dy, x, rows, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, s)
 }

@@ -387,7 +387,7 @@ def _ln_fwd(x2, residual2, w32, b32, eps, want_sum):
     return y, (s if s is not None else x2), mean, rstd
 
 
-def _ln_bwd(dy2, s2, w32, mean, rstd, need_params, need_dxsum=False):
+def _ln_bwd(dy2, s2, w32, mean, rstd, need_params, need_dxsum=False, dres2=None):
     rows, D = s2.shape
     dx = torch.empty_like(s2)
     dgamma = torch.empty(D, dtype=torch.float32, device=s2.device) if need_params else None
@@ -395,7 +395,7 @@ def _ln_bwd(dy2, s2, w32, mean, rstd, need_params, need_dxsum=False):
     dxsum = torch.empty(D, dtype=torch.float32, device=s2.device) if (need_params and need_dxsum) else None
     tm = _Timed("layernorm_bwd", 3.0 * rows * D * s2.element_size(), s2.device)
     L.check(L.lib().aga_layernorm_bwd(_ptr(dy2), _ptr(s2), _DTYPES[s2.dtype], rows, D, _ptr(w32), _ptr(mean), _ptr(rstd),
-                                      _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), _stream_ptr(s2.device)),
+                                      _ptr(dres2), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), _stream_ptr(s2.device)),
             "aga_layernorm_bwd")
     tm.done(s2.device)
     return dx, dgamma, dbeta, dxsum
@@ -427,6 +427,44 @@ class _LayerNormFn(torch.autograd.Function):
         wd, bd = ctx.param_dtypes
         return (dx.view(ctx.shape), dgamma.to(wd) if ctx.needs_input_grad[1] else None,
                 dbeta.to(bd) if ctx.needs_input_grad[2] else None, None)
+
+
+class _LayerNormResidualFn(torch.autograd.Function):
+    """(LN(x), x): the pre-LayerNorm of a residual branch together with the tensor the branch is later added to
+    (`x = x + f(ln(x))`, whisper/model.py:231-242).  Owning both uses of x lets the backward add the gradient arriving
+    through the residual connection inside the LayerNorm-backward kernel instead of a separate full-size add."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        _require_cuda(x, "x")
+        if x.dtype not in _DTYPES:
+            raise L.AgaError(f"layer_norm supports fp32 and bf16 rows, got {x.dtype}")
+        D = x.shape[-1]
+        x2 = _rows(x, D)
+        w32 = weight.detach().float().contiguous()
+        b32 = bias.detach().float().contiguous()
+        y, _, mean, rstd = _ln_fwd(x2, None, w32, b32, eps, False)
+        ctx.save_for_backward(x2, w32, mean, rstd)
+        ctx.shape = x.shape
+        ctx.param_dtypes = (weight.dtype, bias.dtype)
+        return y.view(x.shape), x2.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x2, w32, mean, rstd = ctx.saved_tensors
+        rows, D = x2.shape
+        dy2 = _rows(dy.to(x2.dtype), D)
+        dres2 = None if dres is None else _rows(dres.to(x2.dtype), D)
+        need_params = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx, dgamma, dbeta, _ = _ln_bwd(dy2, x2, w32, mean, rstd, need_params, dres2=dres2)
+        wd, bd = ctx.param_dtypes
+        return (dx.view(ctx.shape), dgamma.to(wd) if ctx.needs_input_grad[1] else None,
+                dbeta.to(bd) if ctx.needs_input_grad[2] else None, None)
+
+
+def layer_norm_residual(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5):
+    """``(layer_norm(x), x)``: use the second value as the residual the branch output is added to."""
+    return _LayerNormResidualFn.apply(x, weight, bias, float(eps))
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:

@@ -62,6 +62,13 @@ class LayerNorm(nn.LayerNorm):
     def forward(self, x: Tensor) -> Tensor:
         return ops.layer_norm(x, self.weight, self.bias, self.eps)
 
+    def with_residual(self, x: Tensor):
+        """(LN(x), x') with x' == x: feed x' to the residual add of the branch (`x = x + f(ln(x))`) and the backward
+        pass adds the residual path's gradient inside the LayerNorm-backward kernel."""
+        if x.is_cuda and torch.is_grad_enabled() and x.requires_grad:
+            return ops.layer_norm_residual(x, self.weight, self.bias, self.eps)
+        return self.forward(x), x
+
 
 def cast_param(owner: nn.Module, slot: str, p: Optional[Tensor], dtype: torch.dtype) -> Optional[Tensor]:
     """``p.to(dtype)`` as the reference writes it (whisper/model.py:35-49), except that the cast of a FROZEN
@@ -251,12 +258,15 @@ class ResidualAttentionBlock(nn.Module):
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
                 kv_cache: Optional[dict] = None):
-        x, second = self.attn(self.attn_ln(x), mask=mask, kv_cache=kv_cache, residual=x)  # x + attn(...)
+        y, x = self.attn_ln.with_residual(x)
+        x, second = self.attn(y, mask=mask, kv_cache=kv_cache, residual=x)  # x + attn(...)
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)  # post-LN replaces x (:234-236)
         if self.cross_attn is not None:
-            x = self.cross_attn(self.cross_attn_ln(x), xa, kv_cache=kv_cache, residual=x)[0]
-        x = linear_plus_residual(self.mlp[2], self.mlp[1](self.mlp[0](self.mlp_ln(x))), x)  # x + mlp(...)
+            y, x = self.cross_attn_ln.with_residual(x)
+            x = self.cross_attn(y, xa, kv_cache=kv_cache, residual=x)[0]
+        y, x = self.mlp_ln.with_residual(x)
+        x = linear_plus_residual(self.mlp[2], self.mlp[1](self.mlp[0](y)), x)  # x + mlp(...)
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x, second

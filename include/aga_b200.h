@@ -169,12 +169,14 @@ AGA_API int aga_head_vote(const float* probs, int L, int B, int H, int T, uint8_
  *   gamma, beta  : (D) fp32;  mean, rstd : (rows) fp32, written by fwd and read by bwd (x of bwd = the normalised tensor)
  *   dgamma, dbeta: (D) fp32, OVERWRITTEN with this call's parameter gradients, or both NULL (frozen LN)
  *   dxsum        : NULL, or (D) fp32 OVERWRITTEN with sum_rows dx — the bias gradient of the Linear that produced `residual`
+ *   dres         : NULL, or (rows, D): the gradient that reached the normalised tensor through the block's residual
+ *                  connection (`x = x + f(ln(x))`, W/model.py:231-242); dx = dtype(dx_ln) + dres in the same pass
  * ------------------------------------------------------------------------------------------ */
 AGA_API int aga_layernorm_fwd(const void* x, const void* residual, int dtype, int64_t rows, int D, const float* gamma,
                       const float* beta, float eps, void* y, void* sum_out, float* mean, float* rstd, void* stream);
 AGA_API int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
-                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
-                      void* stream);
+                      const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                      float* dxsum, void* stream);
 
 /* Backward of the Adapter's GELU fused with the bias gradient of its first Linear (W/model.py:181-194,
  * Adapter.model = Linear -> GELU -> Linear).  dh = dg * gelu'(h) (exact erf form, fp32 math,

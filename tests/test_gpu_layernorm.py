@@ -170,3 +170,30 @@ def test_linear_residual_matches_linear_plus_add(A, dtype, tol, rows, N, K, with
     dx_ref = do.double() @ w.double()
     torch.testing.assert_close(x.grad.double(), dx_ref, rtol=tol, atol=tol * float(dx_ref.abs().max()))
     assert torch.equal(r.grad, do)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_layer_norm_residual_backward_adds_residual_gradient(A, dtype, tol):
+    """ops.layer_norm_residual: (LN(x), x) whose backward adds the residual path's gradient inside the LayerNorm-backward
+    kernel == layer_norm(x) used next to x itself (`x = x + f(ln(x))`, whisper/model.py:231-242)."""
+    from aga_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    D = 768
+    x0 = torch.randn(3, 50, D, generator=g).to(dtype).cuda()
+    w = (1 + 0.1 * torch.randn(D, generator=g)).cuda().requires_grad_()
+    b = (0.1 * torch.randn(D, generator=g)).cuda().requires_grad_()
+    m = torch.randn(D, D, generator=g).to(dtype).cuda() / D ** 0.5
+    do = torch.randn(3, 50, D, generator=g).to(dtype).cuda()
+    res = {}
+    for fused in (True, False):
+        x = x0.clone().requires_grad_()
+        if fused:
+            y, xr = ops.layer_norm_residual(x, w, b)
+        else:
+            y, xr = A.layer_norm(x, w, b, 1e-5), x
+        out = xr + torch.tanh(y @ m)
+        gx, gw, gb = torch.autograd.grad(out, (x, w, b), do)
+        res[fused] = (out.detach(), gx, gw, gb)
+    assert torch.equal(res[True][0], res[False][0])
+    for a, r in zip(res[True][1:], res[False][1:]):
+        torch.testing.assert_close(a.float(), r.float(), rtol=tol, atol=tol * float(r.float().abs().max()))
