@@ -244,10 +244,16 @@ int launch_bwd(const void* dy, const void* x, int64_t rows, const float* gamma, 
   const int64_t want = (rows + kLnWarps - 1) / kLnWarps;
   const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 4)));
   if (dgamma && dbeta) {
-    AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, D * sizeof(float), s));
-    AGA_CUDA_TRY(cudaMemsetAsync(dbeta, 0, D * sizeof(float), s));
+    // one memset node when the caller packed the parameter-gradient rows back to back (ops.py does)
+    const bool packed = dbeta == dgamma + D && (!dxsum || dxsum == dbeta + D);
+    if (packed) {
+      AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, (dxsum ? 3 : 2) * D * sizeof(float), s));
+    } else {
+      AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, D * sizeof(float), s));
+      AGA_CUDA_TRY(cudaMemsetAsync(dbeta, 0, D * sizeof(float), s));
+      if (dxsum) AGA_CUDA_TRY(cudaMemsetAsync(dxsum, 0, D * sizeof(float), s));
+    }
     if (dxsum) {
-      AGA_CUDA_TRY(cudaMemsetAsync(dxsum, 0, D * sizeof(float), s));
       layernorm_bwd_kernel<T, V, NC, 2><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,
                                                                         gamma, mean, rstd, static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, dxsum);
     } else {

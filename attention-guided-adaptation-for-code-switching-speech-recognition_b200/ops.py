@@ -390,9 +390,11 @@ def _ln_fwd(x2, residual2, w32, b32, eps, want_sum):
 def _ln_bwd(dy2, s2, w32, mean, rstd, need_params, need_dxsum=False, dres2=None):
     rows, D = s2.shape
     dx = torch.empty_like(s2)
-    dgamma = torch.empty(D, dtype=torch.float32, device=s2.device) if need_params else None
-    dbeta = torch.empty(D, dtype=torch.float32, device=s2.device) if need_params else None
-    dxsum = torch.empty(D, dtype=torch.float32, device=s2.device) if (need_params and need_dxsum) else None
+    dgamma = dbeta = dxsum = None
+    if need_params:  # rows of one buffer: the library clears them with a single memset
+        pg = torch.empty((3 if need_dxsum else 2, D), dtype=torch.float32, device=s2.device)
+        dgamma, dbeta = pg[0], pg[1]
+        dxsum = pg[2] if need_dxsum else None
     tm = _Timed("layernorm_bwd", 3.0 * rows * D * s2.element_size(), s2.device)
     L.check(L.lib().aga_layernorm_bwd(_ptr(dy2), _ptr(s2), _DTYPES[s2.dtype], rows, D, _ptr(w32), _ptr(mean), _ptr(rstd),
                                       _ptr(dres2), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), _stream_ptr(s2.device)),
