@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--text-len", type=int, default=64, help="decoder input length T (ys_in)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="drive the step from Python instead of replaying CUDA graphs")
+    ap.add_argument("--specaug", action="store_true", help="apply the recipe's SpecAug (graph-safe device variant) in the step")
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances per CPU-baseline step (bounded sample)")
     return ap.parse_args()
 
@@ -62,12 +63,19 @@ def synthetic_batch(batch, text_len, seed):
     return speech, speech_lengths, text, text_lengths
 
 
-def build_model(name, device, export_mode="compact"):
+# specaug_conf of espnet/egs2/seame/asr1/conf/whisper/train_asr_whisper_small_adapter_csloss_2stage_check.yaml:7-24
+RECIPE_SPECAUG = dict(apply_time_warp=True, time_warp_window=5, time_warp_mode="bicubic", apply_freq_mask=True,
+                      freq_mask_width_range=(0, 30), num_freq_mask=2, apply_time_mask=True, time_mask_width_range=(0, 40),
+                      num_time_mask=2)
+
+
+def build_model(name, device, export_mode="compact", specaug=False):
     import aga_b200  # noqa: F401
     from aga_b200 import espnet_model as EM, espnet_whisper as EW, whisper_model as W
 
     d = W.MODEL_DIMS[name]
-    enc = EW.OpenAIWhisperEncoder(whisper_model=name, adapter=True)
+    enc = EW.OpenAIWhisperEncoder(whisper_model=name, adapter=True, use_specaug=specaug,
+                                  specaug_conf=dict(RECIPE_SPECAUG, graph_safe=True) if specaug else None)
     dec = EW.OpenAIWhisperDecoder(d.n_vocab, d.n_text_state, whisper_model=name, adapter=True, whisper_cs=True,
                                   src_layer=1, export_mode=export_mode, fused_loss=str(device) != "cpu")
     toks = [str(i) for i in range(d.n_vocab)]
@@ -171,7 +179,7 @@ def workload_config(args):
     return {"workload": f"Whisper-{args.model} attention-guided adaptation training step (configs[1])",
             "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "audio_seconds": AUDIO_SECONDS,
             "text_len": args.text_len, "adapters": True, "export": "decoder self-attn cols 1:3 (compact)",
-            "optimizer": "AdamW(adapters)", "parallelism": f"dp{args.gpus}", "specaug": False,
+            "optimizer": "AdamW(adapters)", "parallelism": f"dp{args.gpus}", "specaug": bool(args.specaug),
             "l2_policy": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -197,7 +205,7 @@ def main():
     from aga_b200.parallel import FlatGradBucket, all_reduce_stats
 
     torch.manual_seed(2022)
-    model = build_model(args.model, dev)
+    model = build_model(args.model, dev, specaug=args.specaug)
     params = [p for p in model.parameters() if p.requires_grad]
     bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16)
     opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01, fused=True,
