@@ -44,7 +44,8 @@ def parse_args():
     ap.add_argument("--text-len", type=int, default=64, help="decoder input length T (ys_in)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="drive the step from Python instead of replaying CUDA graphs")
-    ap.add_argument("--specaug", action="store_true", help="apply the recipe's SpecAug (graph-safe device variant) in the step")
+    ap.add_argument("--no-specaug", dest="specaug", action="store_false",
+                    help="leave out the recipe's SpecAug (graph-safe device variant; on by default, both arms)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances per CPU-baseline step (bounded sample)")
     return ap.parse_args()
 
@@ -130,14 +131,14 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_rate(model_name, batch, text_len, steps, warmup, threads):
+def cpu_reference_rate(model_name, batch, text_len, steps, warmup, threads, specaug=True):
     """The reference's eager-PyTorch path (oracle/torch_port.py inside the mirror modules) on the host cores, fp32."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch_port
 
     torch.set_num_threads(threads)
     with torch_port.patched_ops():
-        model = build_model(model_name, "cpu", export_mode="full")
+        model = build_model(model_name, "cpu", export_mode="full", specaug=specaug)
         params = [p for p in model.parameters() if p.requires_grad]
         opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01)
         data = synthetic_batch(batch, text_len, seed=2022)
@@ -160,7 +161,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    rate, ms = cpu_reference_rate(args.model, args.cpu_batch, args.text_len, args.steps, args.warmup, cores)
+    rate, ms = cpu_reference_rate(args.model, args.cpu_batch, args.text_len, args.steps, args.warmup, cores, args.specaug)
     line = {
         "impl": "reference", "metric": "train audio-sec/s, Whisper AGA step", "value": rate, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -363,7 +364,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         t0 = time.time()
-        rate, ms = cpu_reference_rate(args.model, args.cpu_batch, args.text_len, steps=2, warmup=1, threads=cores)
+        rate, ms = cpu_reference_rate(args.model, args.cpu_batch, args.text_len, steps=2, warmup=1, threads=cores,
+                                      specaug=args.specaug)
         cpu_baseline = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
                         "sample": f"2 timed steps (+1 warm-up) of {args.cpu_batch} x 30 s utterance(s): eager-PyTorch port "
                                   f"of the reference step (oracle/torch_port.py), fp32, {cores} host threads, "
