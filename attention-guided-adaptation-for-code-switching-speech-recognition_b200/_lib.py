@@ -78,6 +78,8 @@ _SIGNATURES = {
     "aga_linear_residual_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
     "aga_linear_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                       C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "aga_gemm_gelu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                C.c_void_p]),
     "aga_gelu_bwd_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

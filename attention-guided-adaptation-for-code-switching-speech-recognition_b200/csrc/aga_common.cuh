@@ -33,6 +33,17 @@ inline int cuda_fail(cudaError_t e) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cuTensorMapEncodeTiled is a driver-API call: it fails in a thread that has no current context yet (PyTorch's autograd
+// threads have only had cudaSetDevice called, which binds lazily).  One runtime call per thread makes the primary
+// context current before the first tensor map is encoded there.
+inline void ensure_context_in_this_thread() {
+  thread_local bool done = false;
+  if (!done) {
+    cudaFree(nullptr);
+    done = true;
+  }
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

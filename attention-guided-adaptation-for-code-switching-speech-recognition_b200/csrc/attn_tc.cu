@@ -712,6 +712,7 @@ PFN_cuTensorMapEncodeTiled get_encode_fn() {
 // (B, T, H*64) bf16 activations as a rank-4 tensor (c=64, h, t, b); box = 64 x 1 x rows x 1, SWIZZLE_128B.
 // Rows past T are zero-filled by the TMA unit.
 int make_map(CUtensorMap* map, const void* base, int B, int H, int T, int64_t stride_b, int64_t stride_t, int rows) {
+  ensure_context_in_this_thread();
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
   if (!enc) return AGA_ERR_UNSUPPORTED;
   cuuint64_t dims[4] = {cuuint64_t(kHeadDim), cuuint64_t(H), cuuint64_t(T), cuuint64_t(B)};

@@ -1,0 +1,326 @@
+// bf16 GEMM with the exact (erf) GELU fused into its epilogue, on tcgen05 / TMEM / TMA.
+//
+// Reference: ResidualAttentionBlock.mlp = Linear(D, 4D) -> GELU -> Linear(4D, D), whisper/whisper/model.py:213,242.
+// With cuBLAS the GELU is a separate HBM pass each way (forward: read h, write g; backward: read h and dg, write dh —
+// 2.9 ms of a 26 ms step), and cuBLASLt's GELU epilogue is the tanh approximation.  Two modes of one kernel:
+//   mode 0 (forward) : h = bf16(A W^T + bias),  g = bf16(gelu(h))             -> writes h (kept for backward) and g
+//   mode 1 (backward): dh = bf16( bf16(A W^T) * gelu'(h) )                     -> reads h tiles in the epilogue
+// A (M, K) and W (N, K) are row-major bf16 (both K-major operands; the backward passes the cached transpose of the
+// second Linear's frozen weight).  Persistent CTAs, one per SM; CTA tile 128 x 256, K in steps of 64 through a 3-stage
+// TMA ring; tcgen05.mma M128 N256 K16 (128 clk each, 96 B/clk of shared-memory operand traffic); the fp32 accumulator is
+// double-buffered in TMEM (2 x 256 columns) so that the 8 epilogue warps (erf costs ~25 instructions per element)
+// work on tile i while the tensor core runs tile i+1; results leave through swizzled staging rows and TMA tile stores.
+#include "aga_common.cuh"
+#include "tc_ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace aga {
+namespace {
+
+using namespace ptx;
+
+constexpr int kTM = 128, kTN = 256, kTK = 64;
+constexpr int kGStages = 3;
+constexpr int kATile = kTM * kTK * 2;   // 16 KiB
+constexpr int kBTile = kTN * kTK * 2;   // 32 KiB
+constexpr int kEpiWarps = 8;
+constexpr int kGTmaWarp = 0, kGMmaWarp = 1, kGEpiWarp0 = 4;
+constexpr int kGThreads = (kGEpiWarp0 + kEpiWarps) * 32;  // 384
+constexpr int kChunkBytes = 32 * 128;   // one warp's 32 rows x 64 bf16 columns
+
+struct GSmem {
+  uint64_t full[kGStages], empty[kGStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t h_ready[kEpiWarps];
+  uint32_t tmem_base;
+  alignas(16) float bias[kTN];
+};
+// stages | per epilogue warp: two 4 KiB staging chunks (h / g, or h_in / dh)
+constexpr size_t kGSmemBytes = 1024 + size_t(kGStages) * (kATile + kBTile) + size_t(kEpiWarps) * 2 * kChunkBytes + sizeof(GSmem);
+static_assert(kGSmemBytes <= 227 * 1024, "gemm_gelu exceeds the shared-memory limit");
+
+struct GArgs {
+  int M, N, K;
+  int mode;             // 0: forward (bias, h and g out), 1: backward (h in, dh out)
+  const __nv_bfloat16* bias;  // (N) or nullptr
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// erf through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result): two MUFU ops
+// (rcp, ex2) and seven FMA-pipe instructions instead of erff's ~25 — at 35 instructions per element the epilogue of a
+// 128 x 256 tile would need 9000 issue cycles per sub-partition against the 6144 cycles of its MMAs.
+//   cdf(x) = Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  e = exp(-x^2 / 2)
+__device__ __forceinline__ void cdf_exp(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  e = ex2(-z * z * 1.4426950408889634f);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * e;          // 0.5 * erfc(|x| / sqrt 2)
+  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, e;
+  cdf_exp(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float dgelu_erf(float x) {
+  float cdf, e;
+  cdf_exp(x, cdf, e);
+  return fmaf(x, e * 0.39894228040143267794f, cdf);
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void __launch_bounds__(kGThreads, 1)
+gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_o, const GArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kGStages * kATile;
+  uint8_t* sE = sB + kGStages * kBTile;  // epilogue staging: warp w -> [2][32 rows x 128 B]
+  GSmem* sb = reinterpret_cast<GSmem*>(sE + kEpiWarps * 2 * kChunkBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_mt = (a.M + kTM - 1) / kTM, n_nt = (a.N + kTN - 1) / kTN, n_k = (a.K + kTK - 1) / kTK;
+  const int n_tiles = n_mt * n_nt;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGStages; ++s) {
+      mbar_init(&sb->full[s], 1);
+      mbar_init(&sb->empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sb->acc_full[i], 1);
+      mbar_init(&sb->acc_empty[i], kEpiWarps);
+    }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&sb->h_ready[w], 1);
+    fence_barrier_init();
+  }
+  if (warp == kGMmaWarp) {
+    tmem_alloc(&sb->tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == kGTmaWarp && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_w);
+    prefetch_tensormap(&map_h);
+    prefetch_tensormap(&map_o);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sb->tmem_base;
+
+  if (warp == kGTmaWarp) {
+    // ============================== TMA producer ==============================
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int mt = t / n_nt, nt = t % n_nt;  // n fastest: neighbouring CTAs share the A rows in L2
+      for (int k = 0; k < n_k; ++k, ++it) {
+        const int s = it % kGStages;
+        mbar_wait(&sb->empty[s], ((it / kGStages) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sb->full[s], kATile + kBTile);
+          tma_load_2d(sA + s * kATile, &map_a, &sb->full[s], k * kTK, mt * kTM);
+          tma_load_2d(sB + s * kBTile, &map_w, &sb->full[s], k * kTK, nt * kTN);
+        }
+      }
+    }
+  } else if (warp == kGMmaWarp) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc = make_idesc_bf16(kTM, kTN, 0, 0);
+    int it = 0, tile_i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+      const int buf = tile_i & 1;
+      mbar_wait(&sb->acc_empty[buf], ((tile_i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+      tc_fence_after();
+      for (int k = 0; k < n_k; ++k, ++it) {
+        const int s = it % kGStages;
+        mbar_wait(&sb->full[s], (it / kGStages) & 1);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc_sw128(smem_u32(sA + s * kATile));
+        const uint64_t db = make_smem_desc_sw128(smem_u32(sB + s * kBTile));
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kTK / 16; ++kk)
+            mma_ss(tmem + buf * kTN, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          tc_commit(&sb->empty[s]);
+          if (k == n_k - 1) tc_commit(&sb->acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= kGEpiWarp0) {
+    // ============================== epilogue: warp = (row quadrant, column half) ==============================
+    const int ew = warp - kGEpiWarp0;
+    const int quad = warp & 3, half = ew >> 2;  // TMEM lanes [32 quad, +32); columns [128 half, +128)
+    const uint32_t lane_base = uint32_t(quad * 32);
+    uint8_t* st0 = sE + ew * 2 * kChunkBytes;   // h (mode 0) / h_in (mode 1)
+    uint8_t* st1 = st0 + kChunkBytes;           // g (mode 0) / dh  (mode 1)
+    const uint32_t row0_addr = smem_u32(st0 + lane * 128), row1_addr = smem_u32(st1 + lane * 128);
+    int tile_i = 0, hph = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+      const int mt = t / n_nt, nt = t % n_nt;
+      const int buf = tile_i & 1;
+      const int grow = mt * kTM + int(lane_base);  // first global row of this warp
+      if (a.mode == 0) {
+        // this tile's bias slice -> smem (all epilogue warps of the tile; 256 threads, one value each)
+        named_bar_sync(1, kEpiWarps * 32);  // the previous tile's readers are done
+        const int n = nt * kTN + ew * 32 + lane;
+        sb->bias[ew * 32 + lane] = (a.bias && n < a.N) ? __bfloat162float(a.bias[n]) : 0.f;
+        named_bar_sync(1, kEpiWarps * 32);
+      }
+      mbar_wait(&sb->acc_full[buf], (tile_i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {  // two 64-column chunks per warp
+        const int col0 = half * 128 + c * 64;         // column inside the tile
+        const int gcol = nt * kTN + col0;
+        if (lane == 0) bulk_wait_group_read0();       // the previous chunk's stores have read the staging rows
+        __syncwarp();
+        if (a.mode == 1) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&sb->h_ready[ew], kChunkBytes);
+            tma_load_2d(st0, &map_h, &sb->h_ready[ew], gcol, grow);
+          }
+        }
+        uint32_t v[2][32];
+        tmem_ld32(tmem + (lane_base << 16) + buf * kTN + col0, v[0]);
+        tmem_ld32(tmem + (lane_base << 16) + buf * kTN + col0 + 32, v[1]);
+        tmem_wait_ld();
+        if (c == 1) {  // both chunks of this warp are in registers: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sb->acc_empty[buf]);
+        }
+        if (a.mode == 1) {
+          mbar_wait(&sb->h_ready[ew], hph & 1);
+          ++hph;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {  // 16-byte chunk q of the 128-byte row = 8 columns
+          const uint32_t* src = v[q >> 2];
+          const int e0 = (q & 3) * 8;
+          uint32_t w0[4], w1[4];
+          if (a.mode == 0) {
+            const float4 b0 = *reinterpret_cast<const float4*>(&sb->bias[col0 + q * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sb->bias[col0 + q * 8 + 4]);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float h0 = bf16_round(__uint_as_float(src[e0 + 2 * e]) + bb[2 * e]);
+              const float h1 = bf16_round(__uint_as_float(src[e0 + 2 * e + 1]) + bb[2 * e + 1]);
+              __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1), gg = __floats2bfloat162_rn(gelu_erf(h0), gelu_erf(h1));
+              w0[e] = *reinterpret_cast<uint32_t*>(&hh);
+              w1[e] = *reinterpret_cast<uint32_t*>(&gg);
+            }
+            sts128(row0_addr + uint32_t((q ^ (lane & 7)) * 16), w0[0], w0[1], w0[2], w0[3]);
+          } else {
+            uint4 hv;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hv.x), "=r"(hv.y), "=r"(hv.z), "=r"(hv.w)
+                         : "r"(row0_addr + uint32_t((q ^ (lane & 7)) * 16)) : "memory");
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[e]));
+              const float d0 = bf16_round(__uint_as_float(src[e0 + 2 * e])) * dgelu_erf(hf.x);
+              const float d1 = bf16_round(__uint_as_float(src[e0 + 2 * e + 1])) * dgelu_erf(hf.y);
+              __nv_bfloat162 dd = __floats2bfloat162_rn(d0, d1);
+              w1[e] = *reinterpret_cast<uint32_t*>(&dd);
+            }
+          }
+          sts128(row1_addr + uint32_t((q ^ (lane & 7)) * 16), w1[0], w1[1], w1[2], w1[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (a.mode == 0) tma_store_2d(&map_h, st0, gcol, grow);
+          tma_store_2d(&map_o, st1, gcol, grow);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_group_read0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGMmaWarp) tmem_dealloc(tmem, 512);
+}
+
+PFN_cuTensorMapEncodeTiled encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }();
+  return fn;
+}
+
+// row-major (rows, cols) bf16 matrix; box = 64 columns x box_rows rows, SWIZZLE_128B; out-of-range parts zero-filled / clipped
+int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  ensure_context_in_this_thread();
+  PFN_cuTensorMapEncodeTiled enc = encode_fn();
+  if (!enc) return AGA_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
+  cuuint32_t box[2] = {64, cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? AGA_OK : AGA_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace
+}  // namespace aga
+
+using namespace aga;
+
+// mode 0: h (M,N) = bf16(a (M,K) @ w (N,K)^T + bias (N)),  out (M,N) = bf16(gelu(h));  h is an OUTPUT
+// mode 1: out (M,N) = bf16(bf16(a @ w^T) * gelu'(h));                                   h is an INPUT, bias ignored
+extern "C" int aga_gemm_gelu(const void* a, const void* w, const void* bias, void* h, void* out, int mode, int64_t M, int N,
+                             int K, void* stream) {
+  if (!a || !w || !h || !out || M <= 0 || N <= 0 || K <= 0 || (mode != 0 && mode != 1)) return AGA_ERR_INVALID_ARGUMENT;
+  if (K % 8 != 0 || N % 8 != 0) return AGA_ERR_UNSUPPORTED;  // 16-byte global strides for TMA
+  const uintptr_t all = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(h) |
+                        reinterpret_cast<uintptr_t>(out);
+  if (all & 15) return AGA_ERR_UNSUPPORTED;
+  if (M > 2147483647LL) return AGA_ERR_UNSUPPORTED;
+  CUtensorMap ma, mw, mh, mo;
+  int st;
+  if ((st = make_map_2d(&ma, a, M, K, K, kTM)) != AGA_OK) return st;
+  if ((st = make_map_2d(&mw, w, N, K, K, kTN)) != AGA_OK) return st;
+  if ((st = make_map_2d(&mh, h, M, N, N, 32)) != AGA_OK) return st;
+  if ((st = make_map_2d(&mo, out, M, N, N, 32)) != AGA_OK) return st;
+  GArgs ga{int(M), N, K, mode, static_cast<const __nv_bfloat16*>(bias)};
+  static const int n_sm = []() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const int n_tiles = int((M + kTM - 1) / kTM) * ((N + kTN - 1) / kTN);
+  AGA_CUDA_TRY(cudaFuncSetAttribute(gemm_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)));
+  gemm_gelu_kernel<<<std::min(n_tiles, n_sm), kGThreads, kGSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mw, mh, mo, ga);
+  AGA_AFTER_LAUNCH();
+  return AGA_OK;
+}

@@ -628,6 +628,72 @@ def linear_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.
 
 
 # ------------------------------------------------------------------------------------------------
+# 8f #2. the block's MLP: GEMM with the exact GELU in its epilogue (tcgen05), second GEMM with the residual add
+# ------------------------------------------------------------------------------------------------
+def gemm_gelu_fwd(x2: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]):
+    """(h, gelu(h)) with h = x2 @ w^T + b, bf16, in one tcgen05 GEMM (csrc/gemm_gelu.cu, mode 0)."""
+    M, K = x2.shape
+    N = w.shape[0]
+    h = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device)
+    g = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device)
+    L.check(L.lib().aga_gemm_gelu(_ptr(x2), _ptr(w), _ptr(b), _ptr(h), _ptr(g), 0, M, N, K, _stream_ptr(x2.device)),
+            "aga_gemm_gelu")
+    return h, g
+
+
+def gemm_gelu_bwd(dy2: torch.Tensor, w_t: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """dh = (dy2 @ w_t^T) * gelu'(h): the second Linear's dgrad GEMM with the GELU backward in its epilogue (mode 1);
+    ``w_t`` (N, K) is the transpose of that Linear's (K, N) weight."""
+    M, K = dy2.shape
+    N = w_t.shape[0]
+    dh = torch.empty((M, N), dtype=torch.bfloat16, device=dy2.device)
+    L.check(L.lib().aga_gemm_gelu(_ptr(dy2), _ptr(w_t), None, _ptr(h), _ptr(dh), 1, M, N, K, _stream_ptr(dy2.device)),
+            "aga_gemm_gelu")
+    return dh
+
+
+class _MlpResidualFn(torch.autograd.Function):
+    """residual + W2 gelu(W1 x + b1) + b2 for FROZEN bf16 weights: `x = x + self.mlp(self.mlp_ln(x))`
+    (whisper/model.py:213,242) as two GEMMs and nothing else — the GELU lives in the first GEMM's epilogue, the residual
+    add in the second's, the GELU backward in the epilogue of the second Linear's dgrad GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, w2_t, b2, residual):
+        K = w1.shape[1]
+        x2 = x.reshape(-1, K)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        r2 = residual.reshape(-1, w2.shape[0])
+        r2 = r2 if r2.is_contiguous() else r2.contiguous()
+        h, g = gemm_gelu_fwd(x2, w1, b1)
+        out = _linear_residual_raw(g, w2, b2, r2)
+        ctx.save_for_backward(h, w1, w2_t)
+        ctx.shapes = (x.shape, residual.shape)
+        return out.view(residual.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, w1, w2_t = ctx.saved_tensors
+        d2 = dout.reshape(-1, w2_t.shape[1])
+        d2 = d2 if d2.is_contiguous() else d2.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dh = gemm_gelu_bwd(d2, w2_t, h)
+            dx = (dh @ w1).view(ctx.shapes[0])
+        return dx, None, None, None, None, None, (dout if ctx.needs_input_grad[6] else None)
+
+
+def mlp_residual(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, w2_t: torch.Tensor,
+                 b2: Optional[torch.Tensor], residual: torch.Tensor) -> torch.Tensor:
+    """``residual + F.linear(gelu(F.linear(x, w1, b1)), w2, b2)`` for frozen bf16 weights (``w2_t`` = ``w2.t().contiguous()``,
+    prepared once by the caller)."""
+    _require_cuda(x, "x")
+    for t in (x, w1, w2, w2_t, residual):
+        if t.dtype != torch.bfloat16:
+            raise L.AgaError("mlp_residual runs in bf16")
+    return _MlpResidualFn.apply(x, w1, b1, w2, w2_t, b2, residual)
+
+
+# ------------------------------------------------------------------------------------------------
 # 8f #4. vocabulary logits -> label-smoothing KL loss + accuracy, without fp32 logits
 # ------------------------------------------------------------------------------------------------
 class VocabLogits:

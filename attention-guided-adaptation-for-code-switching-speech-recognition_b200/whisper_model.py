@@ -10,6 +10,7 @@ checkpoints are interchangeable.  Everything except ``MultiHeadAttention.qkv_att
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -266,7 +267,7 @@ class ResidualAttentionBlock(nn.Module):
             y, x = self.cross_attn_ln.with_residual(x)
             x = self.cross_attn(y, xa, kv_cache=kv_cache, residual=x)[0]
         y, x = self.mlp_ln.with_residual(x)
-        x = linear_plus_residual(self.mlp[2], self.mlp[1](self.mlp[0](y)), x)  # x + mlp(...)
+        x = self._mlp_residual(y, x)  # x + mlp(...)
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x, second
@@ -288,6 +289,22 @@ class ResidualAttentionBlock(nn.Module):
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x, (k, v, kc, vc)
+
+    def _mlp_residual(self, y: Tensor, x: Tensor) -> Tensor:
+        """``x + self.mlp(y)`` (whisper/model.py:242).  Frozen bf16 MLP on a CUDA device: two GEMMs and nothing else — the
+        exact GELU in the first GEMM's epilogue (tcgen05, csrc/gemm_gelu.cu), the residual add in the second's."""
+        l1, l2 = self.mlp[0], self.mlp[2]
+        frozen = not any(p.requires_grad for p in (l1.weight, l1.bias, l2.weight, l2.bias))
+        dt = torch.get_autocast_dtype("cuda") if (y.is_cuda and torch.is_autocast_enabled("cuda")) else y.dtype
+        if not (y.is_cuda and frozen and dt == torch.bfloat16 and os.environ.get("AGA_MLP_FUSED", "1") != "0"):
+            return linear_plus_residual(l2, self.mlp[1](l1(y)), x)
+        w2 = cast_param(l2, "_w_cast", l2.weight, dt)
+        c = self.__dict__.get("_w2t")
+        if c is None or c[0] is not w2:
+            c = (w2, w2.t().contiguous())
+            self.__dict__["_w2t"] = c
+        return ops.mlp_residual(y.to(dt), cast_param(l1, "_w_cast", l1.weight, dt), cast_param(l1, "_b_cast", l1.bias, dt),
+                                w2, c[1], cast_param(l2, "_b_cast", l2.bias, dt), x.to(dt))
 
     @staticmethod
     def _adapter_ln(adapter: "Adapter", ln: "LayerNorm", x: Tensor) -> Tensor:

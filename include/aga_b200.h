@@ -213,6 +213,13 @@ AGA_API int aga_linear_residual_workspace_bytes(size_t* bytes);
 AGA_API int aga_linear_residual(const void* x, const void* w, int w_layout, const void* bias, const void* residual, void* out,
                         int dtype, int64_t rows, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 
+/* bf16 GEMM with the exact (erf) GELU in its epilogue (tcgen05): the MLP of ResidualAttentionBlock, W/model.py:213,242
+ * (Linear -> GELU -> Linear).  a (M, K), w (N, K) row-major bf16, K and N multiples of 8, 16-byte aligned.
+ *   mode 0: h = bf16(a w^T + bias), out = bf16(gelu(h)) — h (M, N) is written (kept for the backward pass), bias (N) bf16 or NULL
+ *   mode 1: out = bf16(bf16(a w^T) * gelu'(h))          — h (M, N) is read; pass the transposed second-Linear weight as w */
+AGA_API int aga_gemm_gelu(const void* a, const void* w, const void* bias, void* h, void* out, int mode, int64_t M, int N, int K,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
