@@ -52,6 +52,30 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same tile delivered to the same shared-memory offset of every CTA in `mask`; each destination's mbarrier (same
+// offset) receives the bytes
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// mbarrier arrive (same offset) in every CTA of `mask` once this thread's tcgen05 ops have completed
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -59,34 +83,52 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                : "memory");
 }
 
-// erf through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result): two MUFU ops
-// (rcp, ex2) and seven FMA-pipe instructions instead of erff's ~25 — at 35 instructions per element the epilogue of a
-// 128 x 256 tile would need 9000 issue cycles per sub-partition against the 6144 cycles of its MMAs.
-//   cdf(x) = Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  e = exp(-x^2 / 2)
-__device__ __forceinline__ void cdf_exp(float x, float& cdf, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  e = ex2(-z * z * 1.4426950408889634f);
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float half_erfc = 0.5f * p * t * e;          // 0.5 * erfc(|x| / sqrt 2)
-  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+// erf through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result), evaluated on PAIRS
+// with the packed fp32x2 FMA / MUL / ADD of sm_100: two MUFU ops (rcp, ex2) and ~8 issue slots per element instead of
+// erff's ~25.  (At 22 scalar instructions per element the epilogue of a 128 x 256 tile needs 5600 issue cycles per
+// sub-partition against the 6144 cycles of its MMAs — the kernel was epilogue-issue-bound.)
+//   cdf(x) = Phi(x) = 0.5 (1 + erf(x / sqrt 2)) = 0.5 + sign(x) (0.5 - 0.5 erfc(|x| / sqrt 2)),  e = exp(-x^2 / 2)
+__device__ __forceinline__ void cdf_exp2(float2 x, float2& cdf, float2& e) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 z = __fmul2_rn(ax, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+  // exp(-z^2) = 2^(-(z sqrt(log2 e))^2)
+  const float2 w = __fmul2_rn(ax, make_float2(0.84932180028801904272f, 0.84932180028801904272f));
+  const float2 m = __fmul2_rn(w, w);
+  e = make_float2(ex2(-m.x), ex2(-m.y));
+  // 0.5 * (a1 + a2 t + a3 t^2 + a4 t^3 + a5 t^4) (coefficients pre-scaled by 0.5)
+  float2 p = __ffma2_rn(make_float2(0.5307027145f, 0.5307027145f), t, make_float2(-0.7265760135f, -0.7265760135f));
+  p = __ffma2_rn(p, t, make_float2(0.7107068705f, 0.7107068705f));
+  p = __ffma2_rn(p, t, make_float2(-0.142248368f, -0.142248368f));
+  p = __ffma2_rn(p, t, make_float2(0.127414796f, 0.127414796f));
+  const float2 he = __fmul2_rn(__fmul2_rn(p, t), e);                      // 0.5 erfc(|x| / sqrt 2)
+  const float2 u = __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(-he.x, -he.y));  // >= 0
+  cdf = __fadd2_rn(make_float2(copysignf(u.x, x.x), copysignf(u.y, x.y)), make_float2(0.5f, 0.5f));
 }
-__device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, e;
-  cdf_exp(x, cdf, e);
-  return x * cdf;
+#ifdef AGA_GEMM_NOMATH  // experiment builds: the epilogue's transcendental work removed
+__device__ __forceinline__ float2 gelu_erf2(float2 x) { return x; }
+__device__ __forceinline__ float2 dgelu_erf2(float2 x) { return x; }
+#else
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  float2 cdf, e;
+  cdf_exp2(x, cdf, e);
+  return __fmul2_rn(x, cdf);
 }
-__device__ __forceinline__ float dgelu_erf(float x) {
-  float cdf, e;
-  cdf_exp(x, cdf, e);
-  return fmaf(x, e * 0.39894228040143267794f, cdf);
+__device__ __forceinline__ float2 dgelu_erf2(float2 x) {
+  float2 cdf, e;
+  cdf_exp2(x, cdf, e);
+  return __ffma2_rn(x, __fmul2_rn(e, make_float2(0.39894228040143267794f, 0.39894228040143267794f)), cdf);
 }
+#endif
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+// kPair: clusters of two CTAs work on two vertically adjacent 128-row tiles of the same 256-column panel; each CTA
+// fetches HALF of the W tile and multicasts it into both CTAs' shared memory, so the L2 -> SM operand traffic per FLOP is
+// that of a 256 x 256 tile (the kernel is L2-bandwidth-bound with 128 x 256 tiles: 1.33 GB per Whisper-small MLP GEMM).
+template <bool kPair>
 __global__ void __launch_bounds__(kGThreads, 1)
 gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_o, const GArgs a) {
@@ -99,12 +141,20 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_mt = (a.M + kTM - 1) / kTM, n_nt = (a.N + kTN - 1) / kTN, n_k = (a.K + kTK - 1) / kTK;
-  const int n_tiles = n_mt * n_nt;
+  // work units: tiles, or (pair of m-tiles, n-tile) per cluster; `rank` selects this CTA's m-tile of the pair
+  const int rank = kPair ? int(cluster_ctarank()) : 0;
+  const int n_units = kPair ? ((n_mt + 1) / 2) * n_nt : n_mt * n_nt;
+  const int unit0 = kPair ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int unit_step = kPair ? int(gridDim.x >> 1) : int(gridDim.x);
+  auto tile_of = [&](int u, int& mt, int& nt) {
+    nt = u % n_nt;  // n fastest: neighbouring CTAs share the A rows in L2
+    mt = kPair ? 2 * (u / n_nt) + rank : u / n_nt;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGStages; ++s) {
       mbar_init(&sb->full[s], 1);
-      mbar_init(&sb->empty[s], 1);
+      mbar_init(&sb->empty[s], kPair ? 2 : 1);  // pair: both CTAs' MMA warps release a stage (its W half lives in both)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->acc_full[i], 1);
@@ -125,21 +175,29 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
 
   if (warp == kGTmaWarp) {
     // ============================== TMA producer ==============================
     int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int mt = t / n_nt, nt = t % n_nt;  // n fastest: neighbouring CTAs share the A rows in L2
+    for (int u = unit0; u < n_units; u += unit_step) {
+      int mt, nt;
+      tile_of(u, mt, nt);
       for (int k = 0; k < n_k; ++k, ++it) {
         const int s = it % kGStages;
         mbar_wait(&sb->empty[s], ((it / kGStages) & 1) ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&sb->full[s], kATile + kBTile);
           tma_load_2d(sA + s * kATile, &map_a, &sb->full[s], k * kTK, mt * kTM);
-          tma_load_2d(sB + s * kBTile, &map_w, &sb->full[s], k * kTK, nt * kTN);
+          if (kPair) {  // this CTA's half of the W tile (128 of its 256 rows), delivered to both CTAs
+            tma_load_2d_multicast(sB + s * kBTile + rank * (kBTile / 2), &map_w, &sb->full[s], k * kTK,
+                                  nt * kTN + rank * (kTN / 2), uint16_t(3));
+          } else {
+            tma_load_2d(sB + s * kBTile, &map_w, &sb->full[s], k * kTK, nt * kTN);
+            tma_load_2d(sB + s * kBTile + kBTile / 2, &map_w, &sb->full[s], k * kTK, nt * kTN + kTN / 2);
+          }
         }
       }
     }
@@ -147,7 +205,7 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ============================== MMA issuer ==============================
     constexpr uint32_t idesc = make_idesc_bf16(kTM, kTN, 0, 0);
     int it = 0, tile_i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+    for (int u = unit0; u < n_units; u += unit_step, ++tile_i) {
       const int buf = tile_i & 1;
       mbar_wait(&sb->acc_empty[buf], ((tile_i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
       tc_fence_after();
@@ -161,7 +219,7 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < kTK / 16; ++kk)
             mma_ss(tmem + buf * kTN, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
-          tc_commit(&sb->empty[s]);
+          if (kPair) tc_commit_multicast(&sb->empty[s], uint16_t(3)); else tc_commit(&sb->empty[s]);
           if (k == n_k - 1) tc_commit(&sb->acc_full[buf]);
         }
         __syncwarp();
@@ -176,8 +234,9 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint8_t* st1 = st0 + kChunkBytes;           // g (mode 0) / dh  (mode 1)
     const uint32_t row0_addr = smem_u32(st0 + lane * 128), row1_addr = smem_u32(st1 + lane * 128);
     int tile_i = 0, hph = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
-      const int mt = t / n_nt, nt = t % n_nt;
+    for (int u = unit0; u < n_units; u += unit_step, ++tile_i) {
+      int mt, nt;
+      tile_of(u, mt, nt);
       const int buf = tile_i & 1;
       const int grow = mt * kTM + int(lane_base);  // first global row of this warp
       if (a.mode == 0) {
@@ -222,13 +281,14 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (a.mode == 0) {
             const float4 b0 = *reinterpret_cast<const float4*>(&sb->bias[col0 + q * 8]);
             const float4 b1 = *reinterpret_cast<const float4*>(&sb->bias[col0 + q * 8 + 4]);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float h0 = bf16_round(__uint_as_float(src[e0 + 2 * e]) + bb[2 * e]);
-              const float h1 = bf16_round(__uint_as_float(src[e0 + 2 * e + 1]) + bb[2 * e + 1]);
-              __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1), gg = __floats2bfloat162_rn(gelu_erf(h0), gelu_erf(h1));
+              const float2 acc = __fadd2_rn(make_float2(__uint_as_float(src[e0 + 2 * e]), __uint_as_float(src[e0 + 2 * e + 1])), bb[e]);
+              __nv_bfloat162 hh = __floats2bfloat162_rn(acc.x, acc.y);  // h as the reference's separate GELU kernel sees it
               w0[e] = *reinterpret_cast<uint32_t*>(&hh);
+              const float2 g2 = gelu_erf2(make_float2(__uint_as_float(w0[e] << 16), __uint_as_float(w0[e] & 0xffff0000u)));
+              __nv_bfloat162 gg = __floats2bfloat162_rn(g2.x, g2.y);
               w1[e] = *reinterpret_cast<uint32_t*>(&gg);
             }
             sts128(row0_addr + uint32_t((q ^ (lane & 7)) * 16), w0[0], w0[1], w0[2], w0[3]);
@@ -239,10 +299,11 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[e]));
-              const float d0 = bf16_round(__uint_as_float(src[e0 + 2 * e])) * dgelu_erf(hf.x);
-              const float d1 = bf16_round(__uint_as_float(src[e0 + 2 * e + 1])) * dgelu_erf(hf.y);
-              __nv_bfloat162 dd = __floats2bfloat162_rn(d0, d1);
+              const float2 dgp = dgelu_erf2(make_float2(__uint_as_float(hw[e] << 16), __uint_as_float(hw[e] & 0xffff0000u)));
+              __nv_bfloat162 db = __floats2bfloat162_rn(__uint_as_float(src[e0 + 2 * e]), __uint_as_float(src[e0 + 2 * e + 1]));
+              const uint32_t dw = *reinterpret_cast<uint32_t*>(&db);  // the dgrad GEMM's result as bf16, like cuBLAS writes it
+              const float2 d2 = __fmul2_rn(make_float2(__uint_as_float(dw << 16), __uint_as_float(dw & 0xffff0000u)), dgp);
+              __nv_bfloat162 dd = __floats2bfloat162_rn(d2.x, d2.y);
               w1[e] = *reinterpret_cast<uint32_t*>(&dd);
             }
           }
@@ -261,6 +322,7 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == kGMmaWarp) tmem_dealloc(tmem, 512);
 }
 
@@ -309,7 +371,7 @@ extern "C" int aga_gemm_gelu(const void* a, const void* w, const void* bias, voi
   CUtensorMap ma, mw, mh, mo;
   int st;
   if ((st = make_map_2d(&ma, a, M, K, K, kTM)) != AGA_OK) return st;
-  if ((st = make_map_2d(&mw, w, N, K, K, kTN)) != AGA_OK) return st;
+  if ((st = make_map_2d(&mw, w, N, K, K, kTN / 2)) != AGA_OK) return st;  // W tiles arrive as two 128-row halves
   if ((st = make_map_2d(&mh, h, M, N, N, 32)) != AGA_OK) return st;
   if ((st = make_map_2d(&mo, out, M, N, N, 32)) != AGA_OK) return st;
   GArgs ga{int(M), N, K, mode, static_cast<const __nv_bfloat16*>(bias)};
@@ -318,9 +380,31 @@ extern "C" int aga_gemm_gelu(const void* a, const void* w, const void* bias, voi
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n > 0 ? n : 148;
   }();
-  const int n_tiles = int((M + kTM - 1) / kTM) * ((N + kTN - 1) / kTN);
-  AGA_CUDA_TRY(cudaFuncSetAttribute(gemm_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)));
-  gemm_gelu_kernel<<<std::min(n_tiles, n_sm), kGThreads, kGSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mw, mh, mo, ga);
+  const int n_mt = int((M + kTM - 1) / kTM), n_nt = (N + kTN - 1) / kTN;
+#ifndef AGA_GEMM_NO_PAIR
+  if (n_mt >= 2) {
+    const int n_units = ((n_mt + 1) / 2) * n_nt;
+    const int n_clusters = std::max(1, std::min(n_units, n_sm / 2));
+    AGA_CUDA_TRY(cudaFuncSetAttribute(gemm_gelu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(2 * n_clusters));
+    cfg.blockDim = dim3(kGThreads);
+    cfg.dynamicSmemBytes = kGSmemBytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AGA_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_gelu_kernel<true>, ma, mw, mh, mo, ga));
+    AGA_AFTER_LAUNCH();
+    return AGA_OK;
+  }
+#endif
+  AGA_CUDA_TRY(cudaFuncSetAttribute(gemm_gelu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)));
+  gemm_gelu_kernel<false><<<std::min(n_mt * n_nt, n_sm), kGThreads, kGSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mw, mh, mo, ga);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }

@@ -5,6 +5,9 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tools")]
 import torch
 import torch.nn.functional as F
 import aga_b200  # noqa: F401
+if len(sys.argv) > 1:
+    from aga_b200 import _lib
+    _lib.LIB_PATH = os.path.abspath(sys.argv[1])
 from aga_b200 import ops
 from bench_cross import graph_time
 
