@@ -13,7 +13,7 @@ timeout 700 ncu --metrics gpu__time_duration.sum --clock-control none --launch-s
 echo "launch list rc=$? lines=$(wc -l < $OUT/${TAG}_launches.csv)"
 python tools/profile_target.py > $OUT/${TAG}_plain_target.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k 'regex:logmel_frames|logmel_normalise|attn_fwd_tc_split_kernel|attn_bwd_tc_kernel|attn_bwd_tc_qres_kernel' -s 10 -c 6 -f -o $OUT/${TAG}_hot \
+    -k 'regex:logmel_frames|logmel_normalise|attn_fwd_tc_split_kernel|attn_bwd_tc_kernel|attn_bwd_tc_qres_kernel|gemm_gelu_kernel' -s 12 -c 8 -f -o $OUT/${TAG}_hot \
     python tools/profile_target.py > $OUT/${TAG}_ncu_hot.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT | tail -8

@@ -14,7 +14,14 @@ def main():
     # decoder cross attention (Tq = 64: the one-query-tile backward kernel)
     qc = torch.randn(B, 64, H * 64, generator=g).bfloat16().cuda().requires_grad_()
     doc = torch.randn(B, 64, H * 64, generator=g).bfloat16().cuda()
+    from aga_b200 import ops
+    xm = torch.randn(B * T, H * 64, generator=g).bfloat16().cuda()
+    w1 = (torch.randn(4 * H * 64, H * 64, generator=g) / 28).bfloat16().cuda()
+    b1 = torch.randn(4 * H * 64, generator=g).bfloat16().cuda()
+    w2t = (torch.randn(4 * H * 64, H * 64, generator=g) / 55).bfloat16().cuda()
     for _ in range(3):
+        hm, _ = ops.gemm_gelu_fwd(xm, w1, b1)          # the MLP GEMM with the GELU epilogue, forward ...
+        ops.gemm_gelu_bwd(xm, w2t, hm)                 # ... and backward
         A.log_mel_spectrogram(audio)
         out, _, _ = A.qkv_attention(q, k, v, H)
         out.backward(do)
