@@ -173,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -185,8 +185,22 @@ def workload_config(args):
 
 
 # ---------------------------------------------------------------------------------------------- main arm
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract goes to the process's original stdout."""
+    print(json.dumps(line), file=_REAL_STDOUT or sys.stdout, flush=True)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # stdout carries exactly one JSON line: whatever else writes to fd 1 (NCCL's version banner, library chatter) is
+    # sent to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -382,7 +396,7 @@ def main():
         "cpu_baseline": cpu_baseline, "allreduce_bytes_per_step": bucket.nbytes if world > 1 else 0,
         "step_driver": "python-eager" if args.no_graph else "cuda-graph replay", "eager_ms_per_step": eager_ms / args.steps,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
