@@ -22,6 +22,9 @@ constexpr int kLnWarps = 8;
 // V consecutive elements of a row <-> fp32 registers; 16-byte accesses wherever the row length allows (bf16: V = 8)
 template <typename T, int V> struct Vec;
 template <> struct Vec<float, 4> {
+  using Raw = float4;
+  static __device__ __forceinline__ Raw load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -31,6 +34,13 @@ template <> struct Vec<float, 4> {
   }
 };
 template <> struct Vec<__nv_bfloat16, 4> {
+  using Raw = uint2;
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&v)[4]) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
     const uint2 t = *reinterpret_cast<const uint2*>(p);
     const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
@@ -46,6 +56,17 @@ template <> struct Vec<__nv_bfloat16, 4> {
   }
 };
 template <> struct Vec<__nv_bfloat16, 8> {
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+      v[2 * e] = f.x;
+      v[2 * e + 1] = f.y;
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     const uint4 t = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
@@ -171,6 +192,13 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t 
       Vec<T, V>::load(x + row * D + c * 32 * V + lane * V, xh[c]);
       Vec<T, V>::load(dy + row * D + c * 32 * V + lane * V, gy[c]);
     }
+    // the residual-path gradient is fetched together with x and dy (kept packed): behind the two warp reductions its
+    // latency would be exposed a second time per row
+    typename Vec<T, V>::Raw rr[NC];
+    if (dres) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) rr[c] = Vec<T, V>::load_raw(dres + row * D + c * 32 * V + lane * V);
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
 #pragma unroll
@@ -197,7 +225,7 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t 
       }
       if (dres) {  // the gradient that reached the same tensor through the residual connection: one pass instead of an add kernel
         float r[V];
-        Vec<T, V>::load(dres + row * D + c * 32 * V + lane * V, r);
+        Vec<T, V>::unpack(rr[c], r);
 #pragma unroll
         for (int e = 0; e < V; ++e) o[e] = round_to<T>(o[e]) + r[e];
       }
