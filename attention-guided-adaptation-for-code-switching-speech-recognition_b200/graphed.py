@@ -17,6 +17,7 @@ class GraphedTrainStep:
         self.model, self.opt, self.bucket = model, optimizer, bucket
         self.max_grad_norm, self.amp_dtype = max_grad_norm, amp_dtype
         self.static_in = tuple(t.clone() for t in example_batch)
+        self._stage = self._copy_stream = self._staged = self._consumed = None
         self.multi = bucket.world_size() > 1
         model.static_shapes = True
         # warm up on a side stream (allocator pools, cuBLAS handles, packed-filter cache, lazy CUDA modules)
@@ -57,12 +58,38 @@ class GraphedTrainStep:
         self.bucket.clip_grad_norm_(self.max_grad_norm)
         self.opt.step()
 
-    def __call__(self, batch: Sequence[torch.Tensor]) -> torch.Tensor:
-        for dst, src in zip(self.static_in, batch):
-            if dst.data_ptr() != src.data_ptr():
+    # ---- pipelined input path: the NEXT batch crosses PCIe on a copy stream while the current step runs; at the start of
+    #      its own step it is moved into the graph's static input buffers with a device-to-device copy (microseconds)
+    def prefetch(self, host_batch: Sequence[torch.Tensor]) -> None:
+        """Start the host->device copy of the batch the next ``run_prefetched()`` will train on (pinned host memory)."""
+        if self._stage is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = tuple(torch.empty_like(t) for t in self.static_in)
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
+        self._copy_stream.wait_event(self._consumed)  # the previous staged batch has been moved into the static buffers
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._stage, host_batch):
                 dst.copy_(src, non_blocking=True)
+            self._staged.record(self._copy_stream)
+
+    def run_prefetched(self) -> torch.Tensor:
+        main = torch.cuda.current_stream()
+        main.wait_event(self._staged)
+        for dst, src in zip(self.static_in, self._stage):
+            dst.copy_(src, non_blocking=True)
+        self._consumed.record(main)
+        return self._replay()
+
+    def _replay(self) -> torch.Tensor:
         self.g_fb.replay()
         if self.multi:
             self._reduce()
             self.g_up.replay()
         return self.loss
+
+    def __call__(self, batch: Sequence[torch.Tensor]) -> torch.Tensor:
+        for dst, src in zip(self.static_in, batch):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        return self._replay()
