@@ -806,7 +806,7 @@ namespace {
 constexpr int kBwdPolyQuads = AGA_BWD_POLY;  // of every 4 element quads of phase 1, this many use ex2_poly2
 constexpr int kBwdThreads = 768;
 constexpr int kBwdSoftmaxWarps = 16;
-constexpr int kBwdDrainWarp0 = 16;
+[[maybe_unused]] constexpr int kBwdDrainWarp0 = 16;  // (timeline build)
 constexpr int kBwdTmaWarp = 20;
 constexpr int kBwdMmaWarp = 21;
 constexpr uint32_t kColBS = 0, kColBdP = 128, kColBdV = 256, kColBdK = 320, kColBdQ = 384;
@@ -854,20 +854,6 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssr
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// 8 column-chunks of 8 bf16 from 32 fp32 TMEM values, scaled, to one 64-byte row segment
-__device__ __forceinline__ void store_row_chunk(__nv_bfloat16* dst, const uint32_t (&v)[32], float scale) {
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    uint32_t w[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[8 * q4 + 2 * e]) * scale, __uint_as_float(v[8 * q4 + 2 * e + 1]) * scale);
-      w[e] = *reinterpret_cast<uint32_t*>(&hb);
-    }
-    *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
