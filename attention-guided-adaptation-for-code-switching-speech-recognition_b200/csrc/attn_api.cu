@@ -74,7 +74,9 @@ extern "C" int aga_attn_fwd(const aga_attn_params* p, void* workspace, size_t wo
   if (st != AGA_OK) return st;
   if (need > 0 && (!workspace || workspace_bytes < need)) return AGA_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->causal && p->export_kind != AGA_EXPORT_NONE) {
+  // (the tcgen05 kernel never skips key tile 0, so columns below 128 are always written by the kernel itself)
+  const bool kernel_writes_all = use_tc(*p) && p->export_hi <= 128;
+  if (p->causal && p->export_kind != AGA_EXPORT_NONE && !kernel_writes_all) {
     const int64_t per_head = int64_t(p->Tq) * (p->export_hi - p->export_lo);
     const int64_t total = per_head * p->H * p->B;
     const unsigned gx = unsigned(std::min<int64_t>((total + 255) / 256, 148 * 8));
