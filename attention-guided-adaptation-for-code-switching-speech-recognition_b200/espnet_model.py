@@ -188,6 +188,21 @@ class ESPnetASRModel(torch.nn.Module):
             self.attention_count[l + 1][h + 1] += int(counts[l, h])
 
     # ------------------------------------------------------------------ a12
+    def check_attention_language(self, attention_maps: torch.Tensor, k: int = 2) -> None:
+        """The older head vote (:312-363, "old formulation"): per (utterance, layer, head) the two key indices that
+        appear most often among the rows' top-2 entries must be {1, 2}.  Runs where the maps live (no per-head Python
+        loop, no host copies of the maps); ties are resolved towards the smaller index (stable sorts), which is also
+        what the reference's ``torch.unique`` + stable ``sorted`` do for equal counts."""
+        L, B, H, T, _ = attention_maps.shape
+        top = torch.argsort(attention_maps, dim=-1, descending=True, stable=True)[..., :k]        # (L,B,H,T,k)
+        votes = torch.zeros((L, B, H, T), dtype=torch.int64, device=attention_maps.device)
+        votes.scatter_add_(-1, top.reshape(L, B, H, T * k), torch.ones((L, B, H, T * k), dtype=torch.int64, device=votes.device))
+        best = torch.argsort(votes, dim=-1, descending=True, stable=True)[..., :k]               # most frequent indices
+        picked = ((best == 1).any(-1) & (best == 2).any(-1)).sum(dim=1).cpu()                    # (L,H) utterance counts
+        for layer in range(L):
+            for head in range(H):
+                self.attention_count[layer + 1][head + 1] += int(picked[layer, head])
+
     def calculate_cs_loss(self, attention_maps: torch.Tensor, ground_truth_token: torch.Tensor,
                           attention_default: float = 0.6) -> torch.Tensor:
         """attention_maps: (L,B,H,T,T) full maps (reference layout) or the compact (L,B,H,T,2) export of key

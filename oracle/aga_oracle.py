@@ -245,6 +245,31 @@ def literal_head_mask() -> np.ndarray:
 # ----------------------------------------------------------------------------
 # a10. head selection — E2/asr/espnet_model.py:285-310
 # ----------------------------------------------------------------------------
+def check_attention_language(maps: np.ndarray, k: int = 2) -> np.ndarray:
+    """The OLDER head vote, E2/asr/espnet_model.py:312-363: maps (L,B,H,T,T) -> int64 (L,H) count increments.
+
+    Per utterance and (layer, head): every row is arg-sorted in descending order and its first ``k`` = 2 key indices
+    are kept (:325-337); the indices are counted over all rows (:340-343); the ``k`` most frequent indices — equal counts
+    resolved towards the SMALLER index, because ``torch.unique`` lists them ascending and Python's ``sorted`` is stable
+    (:340-349) — must contain both 1 and 2 (<|zh|>, <|en|>) for the head to be selected (:352-357).
+    Ties INSIDE a row (e.g. the zeros above the diagonal of a causal probability map, which decide the second index
+    of row 0) are resolved towards the smaller index here (a stable sort); ``torch.argsort`` leaves them unspecified.
+    """
+    maps = np.asarray(maps)
+    L, B, H, T, _ = maps.shape
+    counts = np.zeros((L, H), dtype=np.int64)
+    for b in range(B):
+        for l in range(L):
+            for h in range(H):
+                order = np.argsort(-maps[l, b, h], axis=-1, kind="stable")[:, :k]
+                idx, cnt = np.unique(order.reshape(-1), return_counts=True)
+                top = [int(i) for i, _ in sorted(zip(idx, cnt), key=lambda x: x[1], reverse=True)[:k]]
+                if 1 in top and 2 in top:
+                    counts[l, h] += 1
+    return counts
+
+
+
 def new_check_attention_language(maps: np.ndarray) -> np.ndarray:
     """maps (L,B,H,T,T) *probabilities* -> int64 (L,H) count increments.
 

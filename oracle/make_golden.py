@@ -247,6 +247,26 @@ def _logmel64(x):
     return (ls + 4.0) / 4.0, None
 
 
+def old_vote_golden():
+    """ESPnetASRModel.check_attention_language (espnet_model.py:312-363, the older per-row top-2 vote) run on the
+    probabilities of cs_loss.npz plus a tie-free random case -> tests/golden/head_vote_old.npz."""
+    m = bare_asr_model()
+    out = {}
+    for name, probs in (("cs", torch.from_numpy(np.load(os.path.join(OUT, "cs_loss.npz"))["probs"])),
+                        ("dense", torch.softmax(3.0 * torch.randn(12, 2, 12, 9, 9, generator=torch.Generator().manual_seed(3)), -1))):
+        m.attention_count = {l: {h: 0 for h in range(1, 13)} for l in range(1, 13)}
+        m.check_attention_language(probs)
+        out[name + "_counts"] = np.array([[m.attention_count[l + 1][h + 1] for h in range(12)] for l in range(12)], dtype=np.int64)
+        if name == "dense":
+            out["dense_probs"] = probs.numpy()
+    np.savez_compressed(os.path.join(OUT, "head_vote_old.npz"), **out)
+    print("wrote head_vote_old.npz", {k: (v.shape, int(v.sum())) for k, v in out.items() if k.endswith("counts")})
+
+
+if __name__ == "__main__" and "--oldvote" in sys.argv:
+    old_vote_golden()
+    sys.exit(0)
+
 if __name__ == "__main__" and "--e2e" not in sys.argv and "--decode" not in sys.argv:
     main()
 
