@@ -8,6 +8,7 @@ Same constructor keywords, same forward signatures and return conventions, same 
 """
 from __future__ import annotations
 
+import contextlib
 import copy
 from typing import Any, List, Optional, Tuple, Union
 
@@ -95,6 +96,58 @@ class OpenAIWhisperEncoder(torch.nn.Module):
             feats, feats_lens = self.specaug(feats, feats_lens)
         xs_pad, olens = self.whisper_encode(feats, feats_lens)
         return xs_pad, olens, None
+
+
+class WhisperFrontend(torch.nn.Module):
+    """Mirror of espnet2/asr/frontend/whisper.py:11-135 (``frontend: whisper`` in the task registry, tasks/asr.py:95): the
+    Whisper log-mel + audio encoder used as a feature extractor.  Same constructor keywords, ``output_size()``,
+    ``log_mel_spectrogram`` (the twin of the encoder's, :54-83 — the same fused CUDA pass here), ``whisper_encode`` and
+    ``forward(input, input_lengths) -> (feats (B, T', D), feats_lens)``; the whole Whisper model hangs under ``.whisper``
+    as in the reference, so ``state_dict`` keys are ``whisper.encoder.*`` / ``whisper.decoder.*``.  (The reference's
+    ``x = block(x)`` at :104 no longer works with the fork's tuple-returning blocks; the tuple is unpacked here.)"""
+
+    def __init__(self, whisper_model: str = "small", freeze_weights: bool = True, download_dir: Optional[str] = None,
+                 seed: int = 0):
+        super().__init__()
+        self.n_fft, self.win_length, self.hop_length = ops.N_FFT, ops.N_FFT, ops.HOP_LENGTH
+        assert whisper_model in W.available_models(), f"unknown whisper model {whisper_model}"
+        self.whisper = W.load_model(whisper_model, download_root=download_dir, seed=seed)
+        self.whisper.eval()
+        self.n_mels = self.whisper.dims.n_mels
+        self.mel_filters = ops.mel_filters
+        self.freeze_weights = freeze_weights
+
+    def output_size(self) -> int:
+        return self.whisper.encoder.ln_post.normalized_shape[-1]
+
+    def pad_or_trim(self, array: torch.Tensor, length: int = N_SAMPLES, axis: int = -1) -> torch.Tensor:
+        return OpenAIWhisperEncoder.pad_or_trim(self, array, length, axis)
+
+    def log_mel_spectrogram(self, audio: torch.Tensor, ilens: torch.Tensor = None):
+        return ops.log_mel_spectrogram(audio, ilens, n_mels=self.n_mels)
+
+    def whisper_encode(self, input: torch.Tensor, ilens: torch.Tensor = None):
+        enc = self.whisper.encoder
+        x = enc.stem(input)
+        n_frames, max_pos = x.size(1), enc.positional_embedding.size(0)
+        if n_frames <= max_pos:
+            x = (x + enc.positional_embedding[:n_frames, :]).to(x.dtype)
+        else:
+            x = x[:, :max_pos, :] + enc.positional_embedding
+        for block in enc.blocks:
+            x, _ = block(x)
+        x = enc.ln_post(x)
+        olens = None
+        if ilens is not None:
+            olens = 1 + (ilens - enc.conv2.kernel_size[0] + 2 * enc.conv2.padding[0]) // enc.conv2.stride[0]
+            olens = torch.clamp(olens, max=max_pos)
+        return x, olens
+
+    def forward(self, input: torch.Tensor, input_lengths: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        feats, feats_lens = self.log_mel_spectrogram(input, input_lengths)
+        with torch.no_grad() if self.freeze_weights else contextlib.nullcontext():
+            feats, feats_lens = self.whisper_encode(feats, feats_lens)
+        return feats, feats_lens
 
 
 class OpenAIWhisperDecoder(torch.nn.Module):
