@@ -71,3 +71,31 @@ def test_label_smoothing_and_sos_eos_vs_oracle(pkg):
     crit0 = EM.LabelSmoothingLoss(V, -1, 0.0, True)
     np.testing.assert_allclose(crit0(torch.from_numpy(logits), yout).item(),
                                O.label_smoothing_loss(logits, yout_r, 0.0, -1, True), rtol=1e-5)
+
+
+def test_whisper_frontend_constructor_and_keys(pkg):
+    """WhisperFrontend (espnet2/asr/frontend/whisper.py:17-52): keywords, output_size, the `whisper.*` state_dict layout
+    of a stock (adapter-free) Whisper, frozen-weights flag; unknown model names are rejected like the reference does."""
+    W, EW, _ = pkg
+    fe = EW.WhisperFrontend(whisper_model="tiny", freeze_weights=True, download_dir=None)
+    assert fe.output_size() == 384 and fe.n_mels == 80 and (fe.n_fft, fe.hop_length, fe.win_length) == (400, 160, 400)
+    keys = list(fe.state_dict().keys())
+    assert keys[0] == "whisper.encoder.positional_embedding" and "whisper.decoder.token_embedding.weight" in keys
+    assert not any("adapter" in k for k in keys)
+    assert "whisper.encoder.blocks.3.mlp.2.bias" in keys and "whisper.decoder.blocks.3.cross_attn.key.weight" in keys
+    assert not fe.whisper.training
+    with pytest.raises(AssertionError):
+        EW.WhisperFrontend("no-such-model")
+
+
+def test_specaug_and_kv_cache_flags_do_not_change_state_dict(pkg):
+    W, EW, _ = pkg
+    a = EW.OpenAIWhisperDecoder(51865, 384, whisper_model="tiny", adapter=True, whisper_cs=True, src_layer=1)
+    b = EW.OpenAIWhisperDecoder(51865, 384, whisper_model="tiny", adapter=True, whisper_cs=True, src_layer=1, kv_cache=True,
+                                fused_loss=True)
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    e = EW.OpenAIWhisperEncoder(whisper_model="tiny", adapter=True, use_specaug=True,
+                                specaug_conf=dict(apply_time_warp=True, time_warp_window=5, time_warp_mode="bicubic",
+                                                  apply_freq_mask=True, freq_mask_width_range=[0, 30], num_freq_mask=2,
+                                                  apply_time_mask=True, time_mask_width_range=[0, 40], num_time_mask=2))
+    assert not any("specaug" in k for k in e.state_dict().keys())
