@@ -167,6 +167,9 @@ class OpenAIWhisperDecoder(torch.nn.Module):
                  export_mode: str = "full", export_kind: str = "logits", seed: int = 0, kv_cache: bool = False,
                  fused_loss: bool = False):
         super().__init__()
+        if whisper_model not in W.available_models():  # whisper_decoder.py:55 asserts the same
+            import os
+            assert os.path.isfile(whisper_model), f"unknown whisper model {whisper_model}"
         _model = W.load_model(whisper_model, adapter, pe_whisper, side_network, side_network_conf,
                               download_root=download_dir, seed=seed)
         self.sidenetwork = side_network
