@@ -123,7 +123,12 @@ ls_ce_fwd_kernel(const T* __restrict__ logits, int V, int64_t ld, const int64_t*
     const bool ignore = tg == padding_idx;
     float kl = 0.f;
     int32_t correct = 0;
-    if (!ignore) {
+    if (!ignore && (tg < 0 || tg >= V)) {
+      // a target outside [0, V) that is not the padding index (token list / vocabulary mismatch): the reference's
+      // scatter_ raises there (label_smoothing_loss.py:56).  No out-of-bounds read here: the row's loss is NaN, which
+      // the caller sees in the loss and the training step's non-finite check turns into a skipped update.
+      kl = __int_as_float(0x7fc00000);
+    } else if (!ignore) {
       const float conf = 1.0f - smoothing, eps = smoothing / float(V - 1);
       float c = conf > 0.f ? conf * logf(conf) : 0.f;
       if (eps > 0.f) c += float(V - 1) * eps * logf(eps);
@@ -149,7 +154,8 @@ ls_ce_bwd_kernel(const T* __restrict__ logits, int V, int64_t ld, int width, con
   T* dx = dlogits + row * ld;
   const int64_t tg = target[row];
   const bool ignore = tg == padding_idx;
-  const float g = (gscale ? *gscale : 1.0f) * inv_denom;
+  const bool bad = !ignore && (tg < 0 || tg >= V);  // out-of-range target: NaN gradient row (see the forward kernel)
+  const float g = bad ? __int_as_float(0x7fc00000) : (gscale ? *gscale : 1.0f) * inv_denom;
   const float lse = row_lse[row];
   const float conf = 1.0f - smoothing, eps = smoothing / float(V - 1);
   const int n_vec = width / VEC;

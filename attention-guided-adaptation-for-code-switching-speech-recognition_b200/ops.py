@@ -544,10 +544,7 @@ class _AdapterLayerNormFn(torch.autograd.Function):
         dw2 = _wgrad(ds.t(), g, dts[2])                # (D, bottleneck)
         dh1, db1 = gelu_bwd_colsum(dg, h1)
         dw1 = _wgrad(dh1.t(), x2, dts[0])              # (bottleneck, D)
-        if _ADAPTER_BWD_LT:
-            dx = _linear_residual_raw(dh1, w1c, None, ds, w_kn=True)  # ds + dh1 @ W1: the residual branch's gradient rides the GEMM
-        else:
-            dx = torch.addmm(ds, dh1, w1c)
+        dx = _linear_residual_raw(dh1, w1c, None, ds, w_kn=True)  # ds + dh1 @ W1: the residual branch's gradient rides the GEMM
         return (dx.view(ctx.shape), dw1, db1.to(dts[1]), dw2, db2.to(dts[3]), dgamma.to(dts[4]), dbeta.to(dts[5]), None)
 
 
@@ -562,8 +559,6 @@ def adapter_layer_norm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: 
 # 8f #2. Linear with the residual add folded into the GEMM
 # ------------------------------------------------------------------------------------------------
 _LR_WORKSPACE = {}
-import os as _os
-_ADAPTER_BWD_LT = _os.environ.get("AGA_ADAPTER_BWD_LT", "1") != "0"
 
 
 def _lr_workspace(device) -> torch.Tensor:
@@ -584,9 +579,7 @@ def _linear_residual_raw(x2: torch.Tensor, w: torch.Tensor, b: Optional[torch.Te
     ws = _lr_workspace(x2.device)
     st = L.lib().aga_linear_residual(_ptr(x2), _ptr(w), 1 if w_kn else 0, _ptr(b), _ptr(r2), _ptr(out), _DTYPES[x2.dtype],
                                      x2.shape[0], N, K, _ptr(ws), ws.numel(), _stream_ptr(x2.device))
-    if st == -2:  # AGA_ERR_UNSUPPORTED: no cuBLASLt in the process / unaligned operands -> the two-kernel form
-        W = w if w_kn else w.t()
-        return torch.addmm(r2, x2, W) if b is None else torch.addmm(b, x2, W) + r2
+    # no fallback: AGA_ERR_UNSUPPORTED (cuBLASLt not loadable in the process, operands not 16-byte aligned) raises
     L.check(st, "aga_linear_residual")
     return out
 

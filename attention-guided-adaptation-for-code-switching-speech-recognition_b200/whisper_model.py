@@ -57,6 +57,14 @@ def available_models():
     return list(MODEL_DIMS)
 
 
+def _native(x: Tensor) -> bool:
+    """True when ``x`` takes the library's fused CUDA paths.  oracle/torch_port.patched_ops() (the eager-PyTorch restatement
+    of the reference, timed as the CPU baseline and as the eager-GPU comparator) replaces this with ``False`` so that the
+    mirror modules run the reference's own op sequence (separate q/k/v Linears, nn.Conv1d stem, unfused residual adds, fp32
+    logits) on either device; the product never does."""
+    return x.is_cuda
+
+
 class LayerNorm(nn.LayerNorm):
     """fp32 statistics whatever the activation dtype (whisper/model.py:30-32), one CUDA kernel each way."""
 
@@ -66,7 +74,7 @@ class LayerNorm(nn.LayerNorm):
     def with_residual(self, x: Tensor):
         """(LN(x), x') with x' == x: feed x' to the residual add of the branch (`x = x + f(ln(x))`) and the backward
         pass adds the residual path's gradient inside the LayerNorm-backward kernel."""
-        if x.is_cuda and torch.is_grad_enabled() and x.requires_grad:
+        if _native(x) and torch.is_grad_enabled() and x.requires_grad:
             return ops.layer_norm_residual(x, self.weight, self.bias, self.eps)
         return self.forward(x), x
 
@@ -96,7 +104,7 @@ class Linear(nn.Linear):
 def linear_plus_residual(lin: "Linear", x: Tensor, residual: Tensor) -> Tensor:
     """``residual + lin(x)``; for a frozen Linear on a CUDA device the add rides the GEMM (ops.linear_residual)."""
     frozen = not (lin.weight.requires_grad or (lin.bias is not None and lin.bias.requires_grad))
-    if not (x.is_cuda and frozen):
+    if not (_native(x) and frozen):
         return residual + lin(x)
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
     if dt not in (torch.float32, torch.bfloat16):
@@ -146,7 +154,7 @@ class MultiHeadAttention(nn.Module):
                 kv_cache: Optional[dict] = None, residual: Optional[Tensor] = None):
         """``residual``: when given, the first return value is ``residual + out`` (the block's `x = x + attn(...)`, with
         the add folded into the output projection's GEMM)."""
-        if kv_cache is None and x.is_cuda and self._frozen():
+        if kv_cache is None and _native(x) and self._frozen():
             return self._forward_packed(x, xa, mask, residual)
         q = self.query(x)
         if kv_cache is None or xa is None or self.key not in kv_cache:
@@ -296,7 +304,7 @@ class ResidualAttentionBlock(nn.Module):
         l1, l2 = self.mlp[0], self.mlp[2]
         frozen = not any(p.requires_grad for p in (l1.weight, l1.bias, l2.weight, l2.bias))
         dt = torch.get_autocast_dtype("cuda") if (y.is_cuda and torch.is_autocast_enabled("cuda")) else y.dtype
-        if not (y.is_cuda and frozen and dt == torch.bfloat16 and os.environ.get("AGA_MLP_FUSED", "1") != "0"):
+        if not (_native(y) and frozen and dt == torch.bfloat16):
             return linear_plus_residual(l2, self.mlp[1](l1(y)), x)
         w2 = cast_param(l2, "_w_cast", l2.weight, dt)
         c = self.__dict__.get("_w2t")
@@ -348,7 +356,7 @@ class AudioEncoder(nn.Module):
         On a CUDA device both convolutions run as ONE cuBLAS GEMM each on token-major activations (k=3 windows are
         gathered once; conv2's stride-2 windows are three row-strided slices): cuDNN serves these shapes with a
         legacy sm_75 implicit-GEMM kernel that is 8x slower, and the token-major result needs no permute."""
-        if not x.is_cuda:
+        if not _native(x):
             x = F.gelu(self.conv1(x))
             return F.gelu(self.conv2(x)).permute(0, 2, 1)
         dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
@@ -411,9 +419,9 @@ class TextDecoder(nn.Module):
         w = self.token_embedding.weight
         n_vocab = w.shape[0]
         pad = (-n_vocab) % 64
-        if not x.is_cuda or pad == 0 or (w.requires_grad and torch.is_grad_enabled()):
+        if not _native(x) or pad == 0 or (w.requires_grad and torch.is_grad_enabled()):
             full = x @ cast_param(self, "_emb_cast", w, x.dtype).t()
-            return ops.VocabLogits(full, n_vocab) if (lazy and x.is_cuda) else full.float()
+            return ops.VocabLogits(full, n_vocab) if (lazy and _native(x)) else full.float()
         c = self.__dict__.get("_emb_pad")
         if c is None or c[0] != (w._version, w.data_ptr(), x.dtype):
             wp = torch.zeros(n_vocab + pad, w.shape[1], dtype=x.dtype, device=w.device)
@@ -469,22 +477,40 @@ def hash_name(name: str) -> int:
     return h
 
 
+_ALLOW_RANDOM_INIT = False
+
+
+def allow_random_init(flag: bool = True) -> None:
+    """Explicit opt-in to name-seeded random weights when no checkpoint exists (tests, bench.py, oracle/make_golden.py)."""
+    global _ALLOW_RANDOM_INIT
+    _ALLOW_RANDOM_INIT = bool(flag)
+
+
+def random_init_allowed() -> bool:
+    import os
+    return _ALLOW_RANDOM_INIT or os.environ.get("AGA_ALLOW_RANDOM_INIT", "0") == "1"
+
+
 def load_model(name: str, adapter: bool = False, pe_whisper: bool = False, side_network: bool = False,
                side_network_conf: Optional[dict] = None, device=None, download_root: Optional[str] = None,
                in_memory: bool = False, seed: int = 0) -> Whisper:
     """Signature of the fork's whisper.load_model (whisper/__init__.py:182-268).
 
     ``name`` is a model size or a path to an OpenAI-format checkpoint ({"dims", "model_state_dict"}); a size name
-    is looked up as ``<download_root>/<name>.pt``.  There is no network here: when no checkpoint file exists the
-    model is initialised deterministically from ``seed`` (adapter runs load with strict=False as the reference does).
+    is looked up as ``<download_root>/<name>.pt`` (default root ``~/.cache/whisper``, as upstream).  There is no
+    network here, so nothing is downloaded: when no checkpoint file exists this RAISES, like the reference does when
+    its download fails — a drop-in that silently trained a random Whisper would be worse than an error.  Tests, the
+    benchmark and the golden generator opt in to the deterministic name-seeded initialisation explicitly
+    (``allow_random_init()`` / ``AGA_ALLOW_RANDOM_INIT=1``), and it is logged whenever it is taken.
     """
     import os
 
     path = None
+    root = download_root if download_root is not None else os.path.join(os.path.expanduser("~"), ".cache", "whisper")
     if os.path.isfile(name):
         path = name
-    elif download_root is not None and os.path.isfile(os.path.join(download_root, f"{name}.pt")):
-        path = os.path.join(download_root, f"{name}.pt")
+    elif os.path.isfile(os.path.join(root, f"{name}.pt")):
+        path = os.path.join(root, f"{name}.pt")
     if path is not None:
         ckpt = torch.load(path, map_location="cpu")
         dims = ModelDimensions(**ckpt["dims"])
@@ -494,6 +520,14 @@ def load_model(name: str, adapter: bool = False, pe_whisper: bool = False, side_
     else:
         if name not in MODEL_DIMS:
             raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
+        if not random_init_allowed():
+            raise RuntimeError(
+                f"no Whisper checkpoint for '{name}' (looked for {os.path.join(root, name + '.pt')}); this build cannot "
+                "download one.  Put the OpenAI checkpoint there / pass download_dir, or opt in to seeded random weights "
+                "with aga_b200.whisper_model.allow_random_init() or AGA_ALLOW_RANDOM_INIT=1 (tests and benchmarks only)")
+        import logging
+        logging.getLogger("aga_b200").warning(
+            "whisper '%s': no checkpoint found, using SEEDED RANDOM weights (seed %d) — explicit opt-in", name, seed)
         model = Whisper(MODEL_DIMS[name], pe_whisper, adapter, side_network, side_network_conf)
         seeded_init_(model, seed)
     return model.to(device) if device is not None else model

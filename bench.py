@@ -31,6 +31,12 @@ import torch.distributed as dist  # noqa: E402
 
 AUDIO_SECONDS = 30
 N_SAMPLES = 480000
+# BASELINE.json configs[1..3]
+CONFIGS = {
+    "small16": {"model": "small", "batch": 16, "baseline_config": "configs[1]"},
+    "medium32": {"model": "medium", "batch": 32, "baseline_config": "configs[2]"},
+    "large8": {"model": "large-v2-mel128", "batch": 8, "baseline_config": "configs[3]"},
+}
 
 
 def parse_args():
@@ -39,15 +45,25 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="aga_b200", choices=["aga_b200", "reference"])
-    ap.add_argument("--model", default="small")
-    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU per step (weak scaling)")
+    ap.add_argument("--config", default=os.environ.get("AGA_BENCH_CONFIG", "small16"), choices=sorted(CONFIGS),
+                    help="BASELINE.json workload: small16 = configs[1] (default), medium32 = configs[2], large8 = configs[3] "
+                         "(large-v2 body, 128-bin mel stem)")
+    ap.add_argument("--model", default=None, help="override the config's model")
+    ap.add_argument("--batch", type=int, default=None, help="override utterances per GPU per step (weak scaling)")
     ap.add_argument("--text-len", type=int, default=64, help="decoder input length T (ys_in)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="drive the step from Python instead of replaying CUDA graphs")
     ap.add_argument("--no-specaug", dest="specaug", action="store_false",
                     help="leave out the recipe's SpecAug (graph-safe device variant; on by default, both arms)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances per CPU-baseline step (bounded sample)")
-    return ap.parse_args()
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch (reference op sequence) leg on the GPU")
+    ap.add_argument("--accum-grad", type=int, default=1, help="micro-batches per optimizer step (recipe: 4); a 'step' stays one micro-batch")
+    ap.add_argument("--comm-chunks", type=int, default=6, help="gradient all-reduce chunks launched from inside the backward pass")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.model = args.model or cfg["model"]
+    args.batch = args.batch or cfg["batch"]
+    return args
 
 
 # ---------------------------------------------------------------------------------------------- data / model
@@ -74,6 +90,7 @@ def build_model(name, device, export_mode="compact", specaug=False):
     import aga_b200  # noqa: F401
     from aga_b200 import espnet_model as EM, espnet_whisper as EW, whisper_model as W
 
+    W.allow_random_init()  # synthetic benchmark: random-init weights of the named architecture (no checkpoints offline)
     d = W.MODEL_DIMS[name]
     enc = EW.OpenAIWhisperEncoder(whisper_model=name, adapter=True, use_specaug=specaug,
                                   specaug_conf=dict(RECIPE_SPECAUG, graph_safe=True) if specaug else None)
@@ -156,6 +173,40 @@ def cpu_reference_rate(model_name, batch, text_len, steps, warmup, threads, spec
     return batch * AUDIO_SECONDS * len(times) / total, 1e3 * total / len(times)
 
 
+def gpu_eager_rate(args, dev, batch, steps=3, warmup=2):
+    """G-eager: the reference's eager-PyTorch op sequence on the SAME B200 under bf16 autocast, as
+    espnet2/train/trainer.py:41-50,567-576 would run it — materialised (B,H,T,T) scores, fp32 softmax, separate q/k/v
+    Linears, nn.Conv1d stem, torch.stft frontend, full (L,B,H,T,T) map export, unfused loss, stock AdamW.  The real
+    "before" number on this box; oracle/torch_port.py supplies the op sequence (a port: /root/reference is not on the box)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port
+
+    with torch_port.patched_ops():
+        model = build_model(args.model, dev, export_mode="full", specaug=args.specaug)
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01)
+        data = tuple(t.to(dev) for t in synthetic_batch(batch, args.text_len, seed=2022))
+        torch.cuda.reset_peak_memory_stats(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss, stats, _ = model(*data)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del model, opt, params, data, loss, stats
+    torch.cuda.empty_cache()
+    return batch * AUDIO_SECONDS / (ms / 1e3), ms, peak_gb
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,7 +217,13 @@ def run_reference(args):
         "impl": "reference", "metric": "train audio-sec/s, Whisper AGA step", "value": rate, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        # what THIS arm timed: a bounded sample (cpu_batch utterances, full maps exported as the reference does), one CPU
+        # process whatever --gpus says — not the GPU arm's batch
+        "config": workload_config(args, batch=args.cpu_batch, world=1, export="decoder self-attn full (L,B,H,T,T) maps "
+                                  "(the reference's export)", note=f"bounded sample of the GPU arm's workload "
+                                  f"(batch_per_gpu {args.batch}); CPU port of the reference (oracle/torch_port.py inside the "
+                                  "repo's mirror modules), 1 process"),
+        "same_config_as_gpu_arm": False,
         "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
                          "sample": f"{args.cpu_batch} x 30 s utterance(s) per step, eager-PyTorch port of the reference "
                                    f"step (oracle/torch_port.py) on {cores} host threads, fp32"},
@@ -176,12 +233,19 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args):
-    return {"workload": f"Whisper-{args.model} attention-guided adaptation training step (configs[1])",
-            "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "audio_seconds": AUDIO_SECONDS,
-            "text_len": args.text_len, "adapters": True, "export": "decoder self-attn cols 1:3 (compact)",
-            "optimizer": "AdamW(adapters)", "parallelism": f"dp{args.gpus}", "specaug": bool(args.specaug),
-            "l2_policy": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush"}
+def workload_config(args, batch=None, world=None, export="decoder self-attn cols 1:3 (compact)", note=None):
+    batch = args.batch if batch is None else batch
+    world = args.gpus if world is None else world
+    cfg = {"workload": f"Whisper-{args.model} attention-guided adaptation training step "
+                       f"({CONFIGS[args.config]['baseline_config']})",
+           "batch_per_gpu": batch, "global_batch": batch * world, "audio_seconds": AUDIO_SECONDS,
+           "text_len": args.text_len, "adapters": True, "export": export,
+           "optimizer": "AdamW(adapters)", "parallelism": f"dp{world}", "specaug": bool(args.specaug),
+           "accum_grad": args.accum_grad,
+           "l2_policy": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush"}
+    if note:
+        cfg["note"] = note
+    return cfg
 
 
 # ---------------------------------------------------------------------------------------------- main arm
@@ -222,7 +286,7 @@ def main():
     torch.manual_seed(2022)
     model = build_model(args.model, dev, specaug=args.specaug)
     params = [p for p in model.parameters() if p.requires_grad]
-    bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16)
+    bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16, n_chunks=args.comm_chunks)
     opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01, fused=True,
                             capturable=not args.no_graph)
 
@@ -233,23 +297,12 @@ def main():
 
     model.static_shapes = True  # synthetic batches are already cut to the longest target: no host syncs in the step
 
-    def eager_step(batch):
-        bucket.begin_step()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss, stats, weight = model(*batch)
-        loss.backward()
-        bucket.gather_()
-        bucket.all_reduce_mean_async()
-        bucket.wait()
-        bucket.clip_grad_norm_(1.0)
-        opt.step()
-        return loss
-
+    from aga_b200.graphed import EagerTrainStep, GraphedTrainStep
+    eager_step = EagerTrainStep(model, opt, bucket, max_grad_norm=1.0, accum_grad=args.accum_grad)
     if args.no_graph:
         step = eager_step
     else:
-        from aga_b200.graphed import GraphedTrainStep
-        step = GraphedTrainStep(model, opt, bucket, resident, max_grad_norm=1.0, warmup=3)
+        step = GraphedTrainStep(model, opt, bucket, resident, max_grad_norm=1.0, warmup=3, accum_grad=args.accum_grad)
 
     def barrier():
         if world > 1:
@@ -385,6 +438,20 @@ def main():
                          "bound": "fp32 issue (400-point DFT on CUDA cores), not HBM: see DESIGN.md",
                          "timed_in": "10 calls captured in one CUDA graph"}
 
+    gpu_eager = None
+    if world == 1 and not args.no_gpu_eager:
+        # free the product model's activations/graph pools first? they stay: 180 GB holds both at these sizes
+        eb = args.batch if args.model in ("tiny", "base", "small") else min(args.batch, 4)
+        try:
+            rate, ms, peak_gb = gpu_eager_rate(args, dev, eb)
+            gpu_eager = {"value": rate, "unit": "audio-s/s", "ms_per_step": ms, "batch": eb, "dtype": "bf16 autocast",
+                         "kind": "port", "peak_mem_gib": peak_gb,
+                         "what": "the reference's eager-PyTorch op sequence (oracle/torch_port.py in the mirror modules) on this "
+                                 "B200: materialised scores, full-map export, unfused loss, stock AdamW; 3 timed steps after 2"}
+        except torch.cuda.OutOfMemoryError as e:  # reported, not hidden
+            gpu_eager = {"unavailable": f"out of memory at batch {eb}: {str(e)[:120]}"}
+            torch.cuda.empty_cache()
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -404,7 +471,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": summary,
-        "cpu_baseline": cpu_baseline, "allreduce_bytes_per_step": bucket.nbytes if world > 1 else 0,
+        "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager,
+        "comm": {"chunks": bucket.n_chunks, "chunks_all_reduced_inside_backward": bucket.chunks_reduced_in_backward > 0,
+                 "one_graph": not args.no_graph},
+        "skipped_steps": float(step.skipped_steps), "allreduce_bytes_per_step": bucket.nbytes if world > 1 else 0,
         "step_driver": "python-eager" if args.no_graph else "cuda-graph replay", "eager_ms_per_step": eager_ms / args.steps,
     }
     emit(line)

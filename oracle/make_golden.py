@@ -267,15 +267,20 @@ if __name__ == "__main__" and "--oldvote" in sys.argv:
     old_vote_golden()
     sys.exit(0)
 
-if __name__ == "__main__" and "--e2e" not in sys.argv and "--decode" not in sys.argv:
+if __name__ == "__main__" and not ({"--e2e", "--e2e12", "--decode"} & set(sys.argv)):
     main()
 
 
 # ----------------------------------------------------------------------------- end-to-end module golden
-def e2e_golden():
+def e2e_golden(n_audio_layer=2, N=32000, tag="e2e_small", with_bf16=False):
     """Reference OpenAIWhisperEncoder + OpenAIWhisperDecoder + ESPnetASRModel.forward (fp32, CPU) on a 12x12-head
     decoder (the guided loss hard-codes 12 layers x 12 heads) with weights from the name-seeded initialiser that the
-    product mirror shares (aga_b200.whisper_model.seeded_init_).  Stores inputs, losses and gradient summaries."""
+    product mirror shares (aga_b200.whisper_model.seeded_init_).  Stores inputs, losses and gradient summaries.
+
+    ``--e2e12`` (n_audio_layer=12, 1 s of audio, tag e2e_full12) is the full Whisper-small depth: every one of the 12
+    encoder attention layers of BASELINE configs[1] is in the parity check; it also stores a strided sample of EVERY
+    adapter gradient and the reference's own bf16-autocast run (trainer.py:569 semantics on the CPU) so that the bf16 gate
+    can be stated relative to the reference's own bf16-vs-fp32 deviation."""
     sys.path.insert(0, os.path.join(HERE, ".."))
     import aga_b200  # noqa: F401  (product package: only its deterministic initialiser is used here)
     from aga_b200.whisper_model import seeded_init_
@@ -283,7 +288,7 @@ def e2e_golden():
     from espnet2.asr.decoder.whisper_decoder import OpenAIWhisperDecoder
     from espnet.nets.pytorch_backend.transformer.label_smoothing_loss import LabelSmoothingLoss
 
-    dims = ModelDimensions(n_mels=80, n_audio_ctx=1500, n_audio_state=768, n_audio_head=12, n_audio_layer=2,
+    dims = ModelDimensions(n_mels=80, n_audio_ctx=1500, n_audio_state=768, n_audio_head=12, n_audio_layer=n_audio_layer,
                            n_vocab=51865, n_text_ctx=448, n_text_state=768, n_text_head=12, n_text_layer=12)
 
     def fake_load_model(name, adapter=False, pe_whisper=False, side_network=False, side_network_conf=None, **kw):
@@ -313,7 +318,7 @@ def e2e_golden():
         p.requires_grad_("adapter" in n)
 
     g = torch.Generator().manual_seed(2022)
-    B, N = 2, 32000
+    B = 2
     speech = (0.1 * torch.randn(B, N, generator=g)).clamp(-1, 1)
     speech_lengths = torch.tensor([N, N - 4000])
     speech[1, N - 4000:] = 0.0
@@ -347,14 +352,41 @@ def e2e_golden():
     out["grad_pick"] = dict(m.named_parameters())[pick].grad.numpy()
     pick2 = "encoder.encoders.blocks.0.adapter_mlp.model.0.bias"
     out["grad_pick2"] = dict(m.named_parameters())[pick2].grad.numpy()
-    np.savez_compressed(os.path.join(OUT, "e2e_small.npz"), **out)
-    with open(os.path.join(OUT, "e2e_small_meta.json"), "w") as f:
+    if with_bf16:
+        # a strided sample (<= 512 elements) of EVERY adapter gradient, and the reference's own bf16-autocast step
+        params = dict(m.named_parameters())
+        samples = []
+        for n in gnames:
+            flat = params[n].grad.reshape(-1)
+            idx = torch.linspace(0, flat.numel() - 1, min(512, flat.numel())).long()
+            samples.append(flat[idx].numpy())
+        out["grad_samples"] = np.concatenate(samples)
+        out["grad_sample_sizes"] = np.array([len(x) for x in samples])
+        out["grad_absmax"] = np.array([float(params[n].grad.abs().max()) for n in gnames])
+        for p in m.parameters():
+            p.grad = None
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            loss16, stats16, _ = m(speech, speech_lengths, text.clone(), text_lengths)
+        loss16.backward()
+        out["bf16_loss_att"] = np.float64(stats16["loss_att"].item())
+        out["bf16_loss_cs"] = np.float64(stats16["loss_cs"].item())
+        out["bf16_grad_norms"] = np.array([float(params[n].grad.double().norm()) for n in gnames])
+        s16 = []
+        for n in gnames:
+            flat = params[n].grad.reshape(-1).float()
+            idx = torch.linspace(0, flat.numel() - 1, min(512, flat.numel())).long()
+            s16.append(flat[idx].numpy())
+        out["bf16_grad_samples"] = np.concatenate(s16)
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    with open(os.path.join(OUT, f"{tag}_meta.json"), "w") as f:
         json.dump({"state_dict": keys, "grad_names": gnames, "grad_pick": pick, "grad_pick2": pick2}, f, indent=0)
     print("e2e golden: loss", loss.item(), {k: (float(v) if v is not None else None) for k, v in stats.items()})
 
 
 if __name__ == "__main__" and "--e2e" in sys.argv:
     e2e_golden()
+if __name__ == "__main__" and "--e2e12" in sys.argv:
+    e2e_golden(n_audio_layer=12, N=16000, tag="e2e_full12", with_bf16=True)
 
 
 # ----------------------------------------------------------------------------- config 1: bundled utterance

@@ -113,7 +113,9 @@ def adapter_layer_norm(x, w1, b1, w2, b2, gamma, beta, eps=1e-5):
 def patched_ops():
     """Route the mirror modules' hot-path calls to the eager port (CPU baseline / eager-GPU comparator only)."""
     import aga_b200
-    from aga_b200 import ops
+    from aga_b200 import ops, whisper_model
+    saved_native = whisper_model._native
+    whisper_model._native = lambda x: False  # the reference's own op sequence on either device
     saved = {n: getattr(ops, n) for n in ("log_mel_spectrogram", "qkv_attention", "qkv_attention_packed", "attention_pattern", "guided_loss",
                                           "head_vote", "layer_norm", "adapter_layer_norm")}
     try:
@@ -127,5 +129,6 @@ def patched_ops():
         ops.adapter_layer_norm = adapter_layer_norm
         yield
     finally:
+        whisper_model._native = saved_native
         for n, f in saved.items():
             setattr(ops, n, f)

@@ -104,12 +104,12 @@ def test_attention_bf16_inputs_simt(A):
     out, _, _ = A.qkv_attention(q, k, v, H, impl="simt")
     r = lambda t: t.detach().float().cpu().numpy()
     o_ref, _, _ = O.qkv_attention(r(q), r(k), r(v), H, False)
-    np.testing.assert_allclose(r(out), o_ref, rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(r(out), o_ref, rtol=2e-2, atol=2e-2 * float(np.abs(o_ref).max()))
     dout = rng.standard_normal((B, Tq, H * 64)).astype(np.float32)
     (out.float() * _t(dout)).sum().backward()
     dq, dk, dv = O.qkv_attention_bwd(r(q), r(k), r(v), H, False, dout)
     for got, ref in ((q.grad, dq), (k.grad, dk), (v.grad, dv)):
-        np.testing.assert_allclose(r(got), ref, rtol=2e-2, atol=2e-2)
+        np.testing.assert_allclose(r(got), ref, rtol=2e-2, atol=2e-2 * float(np.abs(ref).max()))
 
 
 def test_attention_strided_qkv_views(A):

@@ -22,14 +22,23 @@ def _mk(B, Tq, Tk, H, amp, seed):
     return q, k, v
 
 
+def _assert_close_scaled(got, ref, name, tol=2e-2):
+    """North-star bf16 gate: 2e-2 RELATIVE TO THE TENSOR'S OWN SCALE.  With 1500 N(0,1) keys the attention output is an
+    average of ~1500 values (|out| ~ 0.03): an absolute 2e-2 would accept a 60 % error there."""
+    scale = max(float(np.abs(ref).max()), 1e-6)
+    np.testing.assert_allclose(got.float().cpu().numpy(), ref, rtol=tol, atol=tol * scale, err_msg=name)
+
+
 @pytest.mark.parametrize("B,H,Tq,Tk,amp", [
     (1, 1, 128, 128, 1.0), (1, 1, 1, 1, 1.0), (1, 2, 257, 129, 1.0), (2, 3, 300, 200, 1.0), (1, 2, 64, 1500, 1.0),
-    (1, 12, 1500, 1500, 1.0), (1, 2, 512, 640, 4.0), (2, 2, 131, 131, 2.0), (1, 1, 448, 1500, 1.0)])
+    (1, 12, 1500, 1500, 1.0), (1, 2, 512, 640, 4.0), (2, 2, 131, 131, 2.0), (1, 1, 448, 1500, 1.0),
+    # the BASELINE cross-attention shape, and low-entropy (peaked) softmaxes whose outputs are O(1)
+    (16, 12, 64, 1500, 1.0), (1, 2, 1500, 1500, 3.0), (2, 2, 64, 1500, 3.0)])
 def test_tc_forward_vs_oracle(A, B, H, Tq, Tk, amp):
     q, k, v = _mk(B, Tq, Tk, H, amp, seed=Tq + Tk)
     out, lse, _ = A.qkv_attention(q.cuda(), k.cuda(), v.cuda(), H, impl="tcgen05")
     ref, qk, _ = O.qkv_attention(q.float().numpy(), k.float().numpy(), v.float().numpy(), H)
-    np.testing.assert_allclose(out.float().cpu().numpy(), ref, rtol=2e-2, atol=2e-2)
+    _assert_close_scaled(out, ref, "out")
     mx = qk.max(-1)
     lse_ref = mx + np.log(np.exp(qk - mx[..., None]).sum(-1))
     np.testing.assert_allclose(lse.cpu().numpy(), lse_ref, rtol=1e-3, atol=1e-3)
@@ -42,7 +51,7 @@ def test_tc_matches_simt_and_auto_dispatch(A):
     o_tc, l_tc, _ = A.qkv_attention(q.cuda(), k.cuda(), v.cuda(), 4, impl="tcgen05")
     o_si, l_si, _ = A.qkv_attention(q.cuda(), k.cuda(), v.cuda(), 4, impl="simt")
     assert torch.equal(o_auto, o_tc) and torch.equal(l_auto, l_tc)
-    np.testing.assert_allclose(o_tc.float().cpu().numpy(), o_si.float().cpu().numpy(), rtol=2e-2, atol=1e-2)
+    _assert_close_scaled(o_tc, o_si.float().cpu().numpy(), "tc vs simt")
     np.testing.assert_allclose(l_tc.cpu().numpy(), l_si.cpu().numpy(), rtol=1e-4, atol=1e-4)
 
 
@@ -66,7 +75,7 @@ def test_tc_full_size_properties(A):
     assert torch.equal(o2, out[3:5]) and torch.equal(l2, lse[3:5])
     ref, _, _ = O.qkv_attention(q[7:8, :, :128].float().cpu().numpy(), k[7:8, :, :128].float().cpu().numpy(),
                                 v[7:8, :, :128].float().cpu().numpy(), 2)
-    np.testing.assert_allclose(out[7:8, :, :128].float().cpu().numpy(), ref, rtol=2e-2, atol=2e-2)
+    _assert_close_scaled(out[7:8, :, :128], ref, "out[7]")
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,amp", [
@@ -118,7 +127,7 @@ def test_tc_causal_export_forward_vs_oracle(A, B, H, T, cols, sel):
     out, lse, slab = A.qkv_attention(q.cuda(), k.cuda(), v.cuda(), H, causal=True, export="logits", export_cols=cols,
                                      head_sel=head_sel, impl="tcgen05")
     ref, qk, _ = O.qkv_attention(q.float().numpy(), k.float().numpy(), v.float().numpy(), H, causal=True)
-    np.testing.assert_allclose(out.float().cpu().numpy(), ref, rtol=2e-2, atol=2e-2)
+    _assert_close_scaled(out, ref, "out")
     want = qk[..., cols[0]:cols[1]]
     got = slab.cpu().numpy()
     for h in range(H):

@@ -40,6 +40,26 @@ def test_adapter_param_counts(pkg):
     assert (D * D + 6.5 * D) * 2 * L == 14275584
 
 
+def test_load_model_needs_checkpoint_or_opt_in(pkg, monkeypatch, tmp_path):
+    """a registry swap with `whisper_model: small` must not silently train a random Whisper.  Without a
+    checkpoint file load_model raises (as the reference does when its download fails); seeded weights need an opt-in."""
+    W, EW, _ = pkg
+    monkeypatch.setenv("AGA_ALLOW_RANDOM_INIT", "0")
+    W.allow_random_init(False)
+    with pytest.raises(RuntimeError, match="no Whisper checkpoint"):
+        W.load_model("tiny", download_root=str(tmp_path))
+    with pytest.raises(RuntimeError, match="no Whisper checkpoint"):
+        EW.OpenAIWhisperEncoder(whisper_model="tiny", download_dir=str(tmp_path))
+    # a checkpoint in OpenAI format under download_root is found and loaded (adapter run: strict=False)
+    W.allow_random_init(True)
+    ref = W.load_model("tiny", download_root=str(tmp_path), seed=3)
+    W.allow_random_init(False)
+    torch.save({"dims": ref.dims.__dict__, "model_state_dict": ref.state_dict()}, tmp_path / "tiny.pt")
+    got = W.load_model("tiny", adapter=True, download_root=str(tmp_path))
+    assert torch.equal(got.encoder.conv1.weight, ref.encoder.conv1.weight)
+    assert torch.equal(got.decoder.token_embedding.weight, ref.decoder.token_embedding.weight)
+
+
 def test_select_heads_and_literal_mask(pkg, golden_dir):
     _, _, EM = pkg
     meta = json.load(open(os.path.join(golden_dir, "meta.json")))

@@ -25,34 +25,69 @@ def _worker(rank, world, port, q):
         torch.manual_seed(0)  # same weights on every rank
         model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
         model[0].weight.requires_grad_(False)  # frozen params are not part of the bucket
-        bucket = FlatGradBucket(model.parameters())
-        assert bucket.numel == 16 + 16 * 4 + 4
+        bucket = FlatGradBucket(model.parameters(), n_chunks=2)
+        assert bucket.numel == 16 + 16 * 4 + 4 and bucket.n_chunks == 2
+        # the buffer is laid out in backward-completion order: the LAST module's parameters first
+        assert model[2].bias.grad.data_ptr() == bucket.flat[:4].data_ptr()
+        assert model[0].bias.grad.data_ptr() == bucket.flat[-16:].data_ptr()
         data = torch.arange(6 * 8, dtype=torch.float32).reshape(6, 8) / 10
         sl = shard_batch(6, rank, world)
         x = data[sl]
         assert x.shape[0] == 3
         loss = model(x).pow(2).mean()
-        loss.backward()
+        loss.backward()  # hooks not armed: autograd accumulates into the zeroed views
         local = bucket.flat.clone()
         bucket.all_reduce_mean_async()
         bucket.wait()
         gathered = [torch.zeros_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
-        assert torch.allclose(bucket.flat, sum(gathered) / world, atol=1e-7)
-        # grads are views into the flat buffer
-        assert model[2].bias.grad.data_ptr() == bucket.flat[-4:].data_ptr()
+        mean_grad = sum(gathered) / world
+        assert torch.allclose(bucket.flat, mean_grad, atol=1e-7)
         norm = bucket.clip_grad_norm_(1e-3)
         assert torch.linalg.vector_norm(bucket.flat) <= 1e-3 + 1e-6 and norm > 0
-        # assign-then-gather step protocol: same flat contents as accumulating into zeroed views
-        bucket.zero_()
-        model(x).pow(2).mean().backward()
-        ref = bucket.flat.clone()
+        # step protocol: every chunk is gathered AND all-reduced from inside backward (post-accumulate-grad hooks)
         bucket.begin_step()
         assert all(p.grad is None for p in bucket.params)
+        n0 = bucket.chunks_reduced_in_backward
         model(x).pow(2).mean().backward()
-        assert model[2].bias.grad.data_ptr() != bucket.flat[-4:].data_ptr()
-        bucket.gather_()
-        assert torch.equal(bucket.flat, ref) and model[2].bias.grad.data_ptr() == bucket.flat[-4:].data_ptr()
+        assert bucket.chunks_reduced_in_backward - n0 == bucket.n_chunks
+        assert model[2].bias.grad.data_ptr() == bucket.flat[:4].data_ptr()
+        bucket.finish_backward()
+        assert torch.allclose(bucket.flat, mean_grad, atol=1e-7)
+        # accum_grad = 2: the first micro-step stays local (no collective), the second adds and reduces the sum
+        x2 = x * 0.5 + 0.1
+        bucket.begin_step(accumulate=False, sync=False)
+        n0 = bucket.chunks_reduced_in_backward
+        model(x).pow(2).mean().backward()
+        bucket.finish_backward()
+        assert bucket.chunks_reduced_in_backward == n0 and torch.allclose(bucket.flat, local, atol=1e-7)
+        bucket.begin_step(accumulate=True, sync=True)
+        model(x2).pow(2).mean().backward()
+        bucket.finish_backward()
+        bucket.zero_()
+        model(x2).pow(2).mean().backward()
+        local2 = bucket.flat.clone()
+        g2 = [torch.zeros_like(local2) for _ in range(world)]
+        dist.all_gather(g2, local2)
+        # (the buffer was zeroed for the check above; redo the accumulation to compare)
+        bucket.begin_step(accumulate=False, sync=False)
+        model(x).pow(2).mean().backward()
+        bucket.finish_backward()
+        bucket.begin_step(accumulate=True, sync=True)
+        model(x2).pow(2).mean().backward()
+        bucket.finish_backward()
+        assert torch.allclose(bucket.flat, mean_grad + sum(g2) / world, atol=1e-6)
+        # trainer.py:677 — a non-finite gradient norm skips the update (and is counted)
+        from aga_b200.graphed import EagerTrainStep, GuardedUpdate
+        opt = torch.optim.SGD(bucket.params, lr=0.1)
+        upd = GuardedUpdate(opt, bucket, 1.0)
+        before = [p.detach().clone() for p in bucket.params]
+        bucket.flat[3] = float("nan")
+        upd()
+        assert all(torch.equal(a, p.detach()) for a, p in zip(before, bucket.params)) and float(upd.skipped_steps) == 1.0
+        bucket.flat.copy_(mean_grad)
+        upd()
+        assert not torch.equal(before[0], bucket.params[0].detach()) and float(upd.skipped_steps) == 1.0
         stats = all_reduce_stats({"loss": loss.detach(), "acc": torch.tensor(float(rank)), "cer": None},
                                  torch.tensor(float(x.shape[0])))
         assert stats["cer"] is None and abs(float(stats["acc"]) - 0.5) < 1e-6

@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT]
 import torch
 import aga_b200  # noqa: F401
+os.environ.setdefault("AGA_ALLOW_RANDOM_INIT", "1")
 from aga_b200 import espnet_whisper as EW
 
 def run(dec, enc_out, steps, cached):

@@ -19,7 +19,7 @@ def main():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss, stats, w = model(*data)
         loss.backward()
-        bucket.gather_()
+        bucket.finish_backward()
     for _ in range(3): step()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:

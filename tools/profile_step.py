@@ -19,7 +19,7 @@ def main():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss, stats, w = model(*data, static_text=True)
         loss.backward()
-        bucket.gather_()
+        bucket.finish_backward()
         bucket.clip_grad_norm_(1.0)
         opt.step()
     for _ in range(3): step()
