@@ -32,7 +32,7 @@ class AttnParams(C.Structure):
         ("v_stride_b", C.c_int64), ("v_stride_t", C.c_int64),
         ("o_stride_b", C.c_int64), ("o_stride_t", C.c_int64),
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
-        ("lse", C.c_void_p), ("head_sel", C.c_void_p), ("export_buf", C.c_void_p),
+        ("lse", C.c_void_p), ("head_sel", C.c_void_p), ("export_buf", C.c_void_p), ("kv_len", C.c_void_p),
     ]
 
 
@@ -56,6 +56,12 @@ _SIGNATURES = {
     "aga_logmel_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_size_t)]),
     "aga_logmel_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "aga_logmel_filters_banded": (C.c_int, [C.c_void_p, C.c_int]),
+    "aga_logmel_tc_packed_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    "aga_logmel_tc_build_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "aga_logmel_tc_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "aga_logmel_tc_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "aga_attn_fwd_workspace_bytes": (C.c_int, [C.POINTER(AttnParams), C.POINTER(C.c_size_t)]),
     "aga_attn_fwd": (C.c_int, [C.POINTER(AttnParams), C.c_void_p, C.c_size_t, C.c_void_p]),
     "aga_attn_bwd_workspace_bytes": (C.c_int, [C.POINTER(AttnBwdParams), C.POINTER(C.c_size_t)]),
@@ -105,6 +111,25 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+TORCH_EXT_PATH = os.path.join(_PKG_DIR, "aga_torch.so")
+_torch_ops = None
+
+
+def torch_ops():
+    """``torch.ops.aga``: the TORCH_LIBRARY operators of csrc/torch_ext/aga_torch.cpp (a thin C++ layer over the C ABI
+    above: tensors in, raw pointers + the current CUDA stream down, status codes -> exceptions).  Every per-step call of
+    ``ops`` goes through it; this ctypes binding keeps the host-pointer setup calls and the symbol tests."""
+    global _torch_ops
+    if _torch_ops is None:
+        import torch
+        if not os.path.exists(TORCH_EXT_PATH):
+            raise AgaError(f"{TORCH_EXT_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib()  # libaga_b200.so first (the extension links against it)
+        torch.ops.load_library(TORCH_EXT_PATH)
+        _torch_ops = torch.ops.aga
+    return _torch_ops
 
 
 def check(status: int, what: str) -> None:

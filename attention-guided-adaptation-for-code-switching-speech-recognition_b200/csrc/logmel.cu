@@ -283,10 +283,23 @@ logmel_frames_kernel(const float* __restrict__ audio, int64_t N, int64_t ld, int
   }
 }
 
+// max(x, m_b - 8), (x + 4) / 4 in place.  ``Fv`` < F (a batch zero-padded past its true common length, see
+// aga_logmel_tc_fwd's n_valid): frames >= Fv were never computed and are written as exact zeros — what the conv stem's
+// own zero padding would have supplied to the reference, which never sees those frames.
 __global__ void __launch_bounds__(256)
-logmel_normalise_kernel(float* __restrict__ out, const uint32_t* __restrict__ maxkey, int64_t per_utt, int vec) {
+logmel_normalise_kernel(float* __restrict__ out, const uint32_t* __restrict__ maxkey, int64_t per_utt, int vec, int F,
+                        const int32_t* __restrict__ n_valid, int raw_power) {
   const int b = blockIdx.y;
-  const float floor_v = key_to_float(maxkey[b]) - 8.0f;
+  // raw_power (logmel_tc.cu): `out` and the maximum hold the mel POWER; log10(clamp 1e-10) happens here (monotone, so
+  // the maximum of the logs is the log of the maximum)
+  const float kLog10Of2 = 0.30102999566398120f;
+  const float mx = key_to_float(maxkey[b]);
+  const float floor_v = (raw_power ? __log2f(fmaxf(mx, 1e-10f)) * kLog10Of2 : mx) - 8.0f;
+  auto fin = [&](float x) {
+    if (raw_power) x = __log2f(fmaxf(x, 1e-10f)) * kLog10Of2;
+    return (fmaxf(x, floor_v) + 4.0f) * 0.25f;
+  };
+  const int Fv = n_valid ? min(F, *n_valid / kHop) : F;
   float* o = out + int64_t(b) * per_utt;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -295,14 +308,15 @@ logmel_normalise_kernel(float* __restrict__ out, const uint32_t* __restrict__ ma
     const int64_t n4 = per_utt / 4;
     for (; i < n4; i += stride) {
       float4 v = o4[i];
-      v.x = (fmaxf(v.x, floor_v) + 4.0f) * 0.25f;
-      v.y = (fmaxf(v.y, floor_v) + 4.0f) * 0.25f;
-      v.z = (fmaxf(v.z, floor_v) + 4.0f) * 0.25f;
-      v.w = (fmaxf(v.w, floor_v) + 4.0f) * 0.25f;
+      const int f = int((4 * i) % F);  // F % 4 == 0 on this path: the four elements share a row
+      v.x = f + 0 < Fv ? fin(v.x) : 0.0f;
+      v.y = f + 1 < Fv ? fin(v.y) : 0.0f;
+      v.z = f + 2 < Fv ? fin(v.z) : 0.0f;
+      v.w = f + 3 < Fv ? fin(v.w) : 0.0f;
       o4[i] = v;
     }
   } else {
-    for (; i < per_utt; i += stride) o[i] = (fmaxf(o[i], floor_v) + 4.0f) * 0.25f;
+    for (; i < per_utt; i += stride) o[i] = int(i % F) < Fv ? fin(o[i]) : 0.0f;
   }
 }
 
@@ -347,6 +361,18 @@ __global__ void logmel_pack_filters_kernel(const float* __restrict__ fb, int n_m
 }
 
 }  // namespace
+
+// shared with logmel_tc.cu
+int logmel_launch_normalise(float* out, const uint32_t* maxkey, int64_t B, int64_t per_utt, int64_t F, const int32_t* n_valid,
+                            int raw_power, cudaStream_t s) {
+  const int vec = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int64_t work = vec ? per_utt / 4 : per_utt;
+  unsigned gx = unsigned(std::min<int64_t>((work + 255) / 256, 1024));
+  if (gx == 0) gx = 1;
+  logmel_normalise_kernel<<<dim3(gx, unsigned(B)), 256, 0, s>>>(out, maxkey, per_utt, vec, int(F), n_valid, raw_power);
+  AGA_AFTER_LAUNCH();
+  return AGA_OK;
+}
 }  // namespace aga
 
 using namespace aga;
@@ -402,12 +428,5 @@ extern "C" int aga_logmel_fwd(const float* audio, int64_t B, int64_t N, int64_t 
       audio, N, ld, int(F), int(n_fblocks), int(n_blocks), static_cast<const unsigned char*>(packed_filters), n_mels, out,
       maxkey);
   AGA_AFTER_LAUNCH();
-  const int64_t per_utt = int64_t(n_mels) * F;
-  const int vec = (per_utt % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  const int64_t work = vec ? per_utt / 4 : per_utt;
-  unsigned gx = unsigned(std::min<int64_t>((work + 255) / 256, 1024));
-  if (gx == 0) gx = 1;
-  logmel_normalise_kernel<<<dim3(gx, unsigned(B)), 256, 0, s>>>(out, maxkey, per_utt, vec);
-  AGA_AFTER_LAUNCH();
-  return AGA_OK;
+  return logmel_launch_normalise(out, maxkey, B, int64_t(n_mels) * F, F, nullptr, /*raw_power=*/0, s);
 }

@@ -100,22 +100,48 @@ def mel_filters(device, n_mels: int = 80) -> torch.Tensor:
     return _FILTER_CACHE[key]
 
 
-def _packed_filters(filters: torch.Tensor) -> torch.Tensor:
+def _packed_filters(filters: torch.Tensor):
+    """(algo, packed device buffer) for a filterbank tensor, cached.  algo "tc": banded filterbank (the stock Slaney
+    triangles), packed for the tensor-core frontend (csrc/logmel_tc.cu); "simt": any other matrix, packed for the general
+    CUDA-core kernel (csrc/logmel.cu).  The choice depends on the filterbank's structure only, never on the device or the
+    environment."""
     key = (filters.data_ptr(), filters._version, tuple(filters.shape), str(filters.device))
     hit = _PACKED_CACHE.get(key)
     if hit is not None:
         return hit
     lib = L.lib()
     n_mels = filters.shape[0]
+    host = np.ascontiguousarray(filters.detach().cpu().numpy(), dtype=np.float32)  # once per filterbank
+    hptr = C.c_void_p(host.ctypes.data)
+    nbytes = C.c_size_t()
+    if lib.aga_logmel_filters_banded(hptr, n_mels) == 1:
+        L.check(lib.aga_logmel_tc_packed_bytes(n_mels, C.byref(nbytes)), "aga_logmel_tc_packed_bytes")
+        packed = torch.empty(nbytes.value, dtype=torch.uint8, device=filters.device)
+        L.check(lib.aga_logmel_tc_pack(hptr, n_mels, _ptr(packed), nbytes.value, _stream_ptr(filters.device)),
+                "aga_logmel_tc_pack")
+        entry = ("tc", packed)
+    else:
+        L.check(lib.aga_logmel_packed_filter_bytes(n_mels, C.byref(nbytes)), "aga_logmel_packed_filter_bytes")
+        packed = torch.empty(nbytes.value, dtype=torch.uint8, device=filters.device)
+        L.check(lib.aga_logmel_pack_filters(_ptr(filters), n_mels, _ptr(packed), nbytes.value,
+                                            _stream_ptr(filters.device)), "aga_logmel_pack_filters")
+        entry = ("simt", packed)
+    if len(_PACKED_CACHE) > 16:
+        _PACKED_CACHE.clear()
+    _PACKED_CACHE[key] = entry
+    packed._aga_keepalive = filters
+    return entry
+
+
+def _packed_filters_simt(filters: torch.Tensor) -> torch.Tensor:
+    """The general kernel's packing of any filterbank (tests compare the two frontends on the stock banks)."""
+    lib = L.lib()
+    n_mels = filters.shape[0]
     nbytes = C.c_size_t()
     L.check(lib.aga_logmel_packed_filter_bytes(n_mels, C.byref(nbytes)), "aga_logmel_packed_filter_bytes")
     packed = torch.empty(nbytes.value, dtype=torch.uint8, device=filters.device)
-    L.check(lib.aga_logmel_pack_filters(_ptr(filters), n_mels, _ptr(packed), nbytes.value,
-                                        _stream_ptr(filters.device)), "aga_logmel_pack_filters")
-    if len(_PACKED_CACHE) > 16:
-        _PACKED_CACHE.clear()
-    _PACKED_CACHE[key] = packed
-    packed._aga_keepalive = filters
+    L.check(lib.aga_logmel_pack_filters(_ptr(filters), n_mels, _ptr(packed), nbytes.value, _stream_ptr(filters.device)),
+            "aga_logmel_pack_filters")
     return packed
 
 
@@ -123,10 +149,14 @@ def _packed_filters(filters: torch.Tensor) -> torch.Tensor:
 # a1. log-mel
 # ------------------------------------------------------------------------------------------------
 def log_mel_spectrogram(audio: torch.Tensor, ilens: Optional[torch.Tensor] = None, n_mels: int = 80,
-                        filters: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+                        filters: Optional[torch.Tensor] = None, valid_samples: Optional[torch.Tensor] = None,
+                        algo: Optional[str] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """(B, N) fp32 -> ((B, n_mels, N//160) fp32, ilens // 160).
 
     Same contract as OpenAIWhisperEncoder.log_mel_spectrogram (espnet2/asr/encoder/whisper_encoder.py:105-135).
+    ``valid_samples`` (device int32 scalar): the batch's true common length when ``audio`` has been zero-padded to a
+    static bucket length (graphed.BucketedTrainStep) — frames past it come back as zeros.  ``algo`` ("tc" / "simt")
+    forces a kernel for tests; by default banded filterbanks run on the tensor cores.
     """
     _require_cuda(audio, "audio")
     if audio.dim() != 2:
@@ -146,15 +176,18 @@ def log_mel_spectrogram(audio: torch.Tensor, ilens: Optional[torch.Tensor] = Non
     if filters.shape != (n_mels, N_FREQ):
         raise L.AgaError(f"filters must be ({n_mels}, {N_FREQ})")
     lib = L.lib()
-    packed = _packed_filters(filters)
+    kind, packed = _packed_filters(filters)
+    if algo == "simt" and kind == "tc":
+        kind, packed = "simt", _packed_filters_simt(filters)
+    elif algo == "tc" and kind != "tc":
+        raise L.AgaError("the tensor-core frontend needs a banded filterbank")
+    if valid_samples is not None and kind != "tc":
+        raise L.AgaError("valid_samples is served by the tensor-core frontend (banded filterbanks) only")
     F = N // HOP_LENGTH
-    out = torch.empty((B, n_mels, F), dtype=torch.float32, device=audio.device)
-    nbytes = C.c_size_t()
-    L.check(lib.aga_logmel_workspace_bytes(B, N, n_mels, C.byref(nbytes)), "aga_logmel_workspace_bytes")
-    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=audio.device)
+    if valid_samples is not None:
+        valid_samples = valid_samples.to(device=audio.device, dtype=torch.int32).reshape(())
     tm = _Timed("logmel", float(B) * (N * 4 + n_mels * F * 4), audio.device)
-    L.check(lib.aga_logmel_fwd(_ptr(audio), B, N, audio.stride(0), _ptr(packed), n_mels, _ptr(out), _ptr(ws),
-                               nbytes.value, _stream_ptr(audio.device)), "aga_logmel_fwd")
+    out = L.torch_ops().logmel(audio, packed, n_mels, valid_samples, kind == "tc")
     tm.done(audio.device)
     olens = None if ilens is None else ilens // HOP_LENGTH
     return out, olens
@@ -187,78 +220,36 @@ def _prep(t: torch.Tensor) -> torch.Tensor:
     return t if ok else t.contiguous()
 
 
-def _fill_params(p: L.AttnParams, q, k, v, out, lse, n_head, causal, kind, cols, head_sel, export_buf, impl):
-    B, Tq, D = q.shape
-    p.dtype = _DTYPES[q.dtype]
-    p.impl = impl
-    p.B, p.H, p.Tq, p.Tk = B, n_head, Tq, k.shape[1]
-    p.causal = 1 if causal else 0
-    p.export_kind = kind
-    p.export_lo, p.export_hi = (cols if kind != L.EXPORT_NONE else (0, 0))
-    p.q_stride_b, p.q_stride_t = q.stride(0), q.stride(1)
-    p.k_stride_b, p.k_stride_t = k.stride(0), k.stride(1)
-    p.v_stride_b, p.v_stride_t = v.stride(0), v.stride(1)
-    p.o_stride_b, p.o_stride_t = out.stride(0), out.stride(1)
-    p.q, p.k, p.v, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
-    p.lse = lse.data_ptr()
-    p.head_sel = 0 if head_sel is None else head_sel.data_ptr()
-    p.export_buf = 0 if export_buf is None else export_buf.data_ptr()
-
-
-def _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl):
+def _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl, kv_len=None):
     """One aga_attn_fwd call on (possibly strided) q (B,Tq,D), k, v (B,Tk,D) -> (out, lse, export_buf or None)."""
     B, Tq, D = q.shape
     if D != n_head * 64:
         raise L.AgaError("head dim must be 64 (every Whisper size)")
-    lib = L.lib()
-    out = torch.empty((B, Tq, D), dtype=q.dtype, device=q.device)
-    lse = torch.empty((B, n_head, Tq), dtype=torch.float32, device=q.device)
-    export_buf = None
-    if kind != L.EXPORT_NONE:
-        lo, hi = cols
-        # rows of unselected heads are never written by the kernel: define them as zero
-        alloc = torch.zeros if head_sel is not None else torch.empty
-        export_buf = alloc((B, n_head, Tq, hi - lo), dtype=torch.float32, device=q.device)
-    p = L.AttnParams()
-    _fill_params(p, q, k, v, out, lse, n_head, causal, kind, cols, head_sel, export_buf, impl)
-    nbytes = C.c_size_t()
-    L.check(lib.aga_attn_fwd_workspace_bytes(C.byref(p), C.byref(nbytes)), "aga_attn_fwd_workspace_bytes")
-    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
+    lo, hi = cols if kind != L.EXPORT_NONE else (0, 0)
     flops = 4.0 * B * n_head * Tq * k.shape[1] * 64 * (0.5 if causal else 1.0)
     tm = _Timed(f"attn_fwd_{_impl_name(q, causal, kind, impl, cols=cols)}_{Tq}x{k.shape[1]}", flops, q.device)
-    L.check(lib.aga_attn_fwd(C.byref(p), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_fwd")
+    out, lse, export_buf = L.torch_ops().attn_fwd(q, k, v, n_head, causal, kind, lo, hi, head_sel, impl, kv_len)
     tm.done(q.device)
-    return out, lse, export_buf
+    return out, lse, (export_buf if kind != L.EXPORT_NONE else None)
 
 
-def _attn_backward(q, k, v, out, lse, head_sel, probs, cfg, dout, dexport, dq, dk, dv):
+def _attn_backward(q, k, v, out, lse, head_sel, probs, cfg, dout, dexport, dq, dk, dv, kv_len=None):
     """One aga_attn_bwd call; dq / dk / dv are caller-allocated and share the strides of q / k / v."""
     n_head, causal, kind, cols, impl, has_sel = cfg
-    lib = L.lib()
     if dout is None:
         dout = torch.zeros_like(out)
     dout = dout.to(out.dtype)
     if dout.stride() != out.stride():
         dout = dout.contiguous()
-    bp = L.AttnBwdParams()
-    export_buf = probs if probs.numel() else None
     if dexport is not None:
         dexport = dexport.float().contiguous()
-    _fill_params(bp.fwd, q, k, v, out, lse, n_head, causal, kind if dexport is not None else L.EXPORT_NONE, cols,
-                 head_sel if has_sel else None, export_buf, impl)
-    if dexport is not None and kind == L.EXPORT_LOGITS:
-        bp.fwd.export_buf = dexport.data_ptr()  # logits export: only the gradient is needed (non-null marker)
-    bp.dout = dout.data_ptr()
-    bp.d_export = 0 if dexport is None else dexport.data_ptr()
-    bp.dq, bp.dk, bp.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     assert dq.stride() == q.stride() and dk.stride() == k.stride() and dv.stride() == v.stride()
-    nbytes = C.c_size_t()
-    L.check(lib.aga_attn_bwd_workspace_bytes(C.byref(bp), C.byref(nbytes)), "aga_attn_bwd_workspace_bytes")
-    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=q.device)
     flops = 10.0 * q.shape[0] * n_head * q.shape[1] * k.shape[1] * 64 * (0.5 if causal else 1.0)
     tm = _Timed(f"attn_bwd_{_impl_name(q, causal, kind if dexport is not None else L.EXPORT_NONE, impl, bwd=True, cols=cols)}"
                 f"_{q.shape[1]}x{k.shape[1]}", flops, q.device)
-    L.check(lib.aga_attn_bwd(C.byref(bp), _ptr(ws), nbytes.value, _stream_ptr(q.device)), "aga_attn_bwd")
+    lo, hi = cols if kind != L.EXPORT_NONE else (0, 0)
+    L.torch_ops().attn_bwd(q, k, v, out, lse, dout, dexport, probs if probs.numel() else None, dq, dk, dv, n_head, causal, kind,
+                           lo, hi, head_sel if has_sel else None, impl, kv_len)
     tm.done(q.device)
 
 
@@ -271,7 +262,7 @@ def _save(ctx, tensors, out, lse, head_sel, export_buf, n_head, causal, kind, co
 
 class _AttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, n_head, causal, kind, cols, head_sel, impl):
+    def forward(ctx, q, k, v, n_head, causal, kind, cols, head_sel, impl, kv_len=None):
         for name, t in (("q", q), ("k", k), ("v", v)):
             _require_cuda(t, name)
         if q.dtype not in _DTYPES:
@@ -279,17 +270,20 @@ class _AttnFn(torch.autograd.Function):
         k = k.to(q.dtype)
         v = v.to(q.dtype)
         q, k, v = _prep(q), _prep(k), _prep(v)
-        out, lse, export_buf = _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl)
+        out, lse, export_buf = _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl, kv_len)
         _save(ctx, (q, k, v), out, lse, head_sel, export_buf, n_head, causal, kind, cols, impl)
+        ctx.kv_len = kv_len
         return out, lse, export_buf
 
     @staticmethod
     def backward(ctx, dout, _dlse, dexport):
         q, k, v, out, lse, head_sel, probs = ctx.saved_tensors
         # gradients share the strides of q / k / v (strided inputs were made dense by _prep or are dense slices' parents)
-        dq, dk, dv = (torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device) for t in (q, k, v))
-        _attn_backward(q, k, v, out, lse, head_sel, probs, ctx.cfg, dout, dexport, dq, dk, dv)
-        return dq, dk, dv, None, None, None, None, None, None
+        # (with kv_len the kernel never visits key tiles past the true length: those dk / dv rows are zero)
+        alloc = torch.empty_strided if ctx.kv_len is None else (lambda sh, st, dtype, device: torch.zeros(sh, dtype=dtype, device=device))
+        dq, dk, dv = (alloc(t.shape, t.stride(), dtype=t.dtype, device=t.device) for t in (q, k, v))
+        _attn_backward(q, k, v, out, lse, head_sel, probs, ctx.cfg, dout, dexport, dq, dk, dv, ctx.kv_len)
+        return dq, dk, dv, None, None, None, None, None, None, None
 
 
 class _AttnPackedFn(torch.autograd.Function):
@@ -299,7 +293,7 @@ class _AttnPackedFn(torch.autograd.Function):
     one packed gradient, so the projection's backward is a single GEMM with no gradient-accumulation adds."""
 
     @staticmethod
-    def forward(ctx, q, x, n_head, causal, kind, cols, head_sel, impl):
+    def forward(ctx, q, x, n_head, causal, kind, cols, head_sel, impl, kv_len=None):
         _require_cuda(x, "packed projection")
         if x.dtype not in _DTYPES:
             raise L.AgaError(f"attention supports fp32 and bf16, got {x.dtype}")
@@ -310,16 +304,17 @@ class _AttnPackedFn(torch.autograd.Function):
             qv, kv, vv = x[..., :D], x[..., D:2 * D], x[..., 2 * D:]
         else:
             qv, kv, vv = _prep(q.to(x.dtype)), x[..., :D], x[..., D:]
-        out, lse, export_buf = _attn_forward(qv, kv, vv, n_head, causal, kind, cols, head_sel, impl)
+        out, lse, export_buf = _attn_forward(qv, kv, vv, n_head, causal, kind, cols, head_sel, impl, kv_len)
         _save(ctx, (qv if q is not None else torch.empty(0), x), out, lse, head_sel, export_buf, n_head, causal, kind, cols, impl)
         ctx.packed_q = q is None
+        ctx.kv_len = kv_len
         return out, lse, export_buf
 
     @staticmethod
     def backward(ctx, dout, _dlse, dexport):
         qs, x, out, lse, head_sel, probs = ctx.saved_tensors
         D = ctx.cfg[0] * 64
-        dx = torch.empty_like(x)
+        dx = torch.empty_like(x) if ctx.kv_len is None else torch.zeros_like(x)  # rows past kv_len are never visited
         if ctx.packed_q:
             q, k, v = x[..., :D], x[..., D:2 * D], x[..., 2 * D:]
             dq, dk, dv = dx[..., :D], dx[..., D:2 * D], dx[..., 2 * D:]
@@ -327,32 +322,36 @@ class _AttnPackedFn(torch.autograd.Function):
             q, k, v = qs, x[..., :D], x[..., D:]
             dq = torch.empty_strided(q.shape, q.stride(), dtype=q.dtype, device=q.device)
             dk, dv = dx[..., :D], dx[..., D:]
-        _attn_backward(q, k, v, out, lse, head_sel, probs, ctx.cfg, dout, dexport, dq, dk, dv)
-        return (None if ctx.packed_q else dq), dx, None, None, None, None, None, None
+        _attn_backward(q, k, v, out, lse, head_sel, probs, ctx.cfg, dout, dexport, dq, dk, dv, ctx.kv_len)
+        return (None if ctx.packed_q else dq), dx, None, None, None, None, None, None, None
 
 
 def qkv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int, causal: bool = False,
                   export: Optional[str] = None, export_cols: Optional[Tuple[int, int]] = None,
-                  head_sel: Optional[torch.Tensor] = None, impl: str = "auto"):
+                  head_sel: Optional[torch.Tensor] = None, impl: str = "auto", kv_len: Optional[torch.Tensor] = None):
     """Fused MultiHeadAttention.qkv_attention (whisper/model.py:93-109).
 
     q (B,Tq,D), k,v (B,Tk,D), D = n_head*64.  Returns (out (B,Tq,D), lse (B,H,Tq), exported) where
     ``exported`` is None or the fp32 (B,H,Tq,hi-lo) side buffer holding key columns [lo,hi) of the
     scaled, masked logits (``export="logits"``, what the reference returns at HEAD) or of the softmax
     (``export="probs"``).  Differentiable in q, k, v through ``out`` and through ``exported``.
+    ``kv_len`` (device int32 scalar, non-causal bf16 only): keys at or past it do not exist — a batch zero-padded to a
+    static key length for CUDA-graph replay attends exactly like the unpadded one.
     """
+    if kv_len is not None:
+        kv_len = kv_len.to(device=q.device, dtype=torch.int32).reshape(())
     kind = _KINDS[export]
     if kind != L.EXPORT_NONE and export_cols is None:
         export_cols = (0, k.shape[1])
     if head_sel is not None:
         head_sel = head_sel.to(device=q.device, dtype=torch.uint8).contiguous()
     empty_cols = export_cols if export_cols is not None else (0, 0)
-    return _AttnFn.apply(q, k, v, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl])
+    return _AttnFn.apply(q, k, v, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl], kv_len)
 
 
 def qkv_attention_packed(x: torch.Tensor, n_head: int, q: Optional[torch.Tensor] = None, causal: bool = False,
                          export: Optional[str] = None, export_cols: Optional[Tuple[int, int]] = None,
-                         head_sel: Optional[torch.Tensor] = None, impl: str = "auto"):
+                         head_sel: Optional[torch.Tensor] = None, impl: str = "auto", kv_len: Optional[torch.Tensor] = None):
     """``qkv_attention`` on a packed projection: x = [q | k | v] (B,T,3D), or x = [k | v] (B,Tk,2D) with ``q`` given.
     Same results as :func:`qkv_attention` on the three column slices; one packed gradient comes back."""
     kind = _KINDS[export]
@@ -362,7 +361,9 @@ def qkv_attention_packed(x: torch.Tensor, n_head: int, q: Optional[torch.Tensor]
     if head_sel is not None:
         head_sel = head_sel.to(device=x.device, dtype=torch.uint8).contiguous()
     empty_cols = export_cols if export_cols is not None else (0, 0)
-    return _AttnPackedFn.apply(q, x, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl])
+    if kv_len is not None:
+        kv_len = kv_len.to(device=x.device, dtype=torch.int32).reshape(())
+    return _AttnPackedFn.apply(q, x, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl], kv_len)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -376,30 +377,22 @@ def _rows(t: torch.Tensor, D: int) -> torch.Tensor:
 def _ln_fwd(x2, residual2, w32, b32, eps, want_sum):
     """x2 (rows, D) [+ residual2] -> (y, s, mean, rstd); s = x2 + residual2 in x2.dtype (or x2 itself)."""
     rows, D = x2.shape
-    y = torch.empty_like(x2)
-    s = torch.empty_like(x2) if (residual2 is not None and want_sum) else None
-    mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
-    rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
-    tm = _Timed("layernorm_fwd", (2.0 + (residual2 is not None) + (s is not None)) * rows * D * x2.element_size(), x2.device)
-    L.check(L.lib().aga_layernorm_fwd(_ptr(x2), _ptr(residual2), _DTYPES[x2.dtype], rows, D, _ptr(w32), _ptr(b32), float(eps),
-                                      _ptr(y), _ptr(s), _ptr(mean), _ptr(rstd), _stream_ptr(x2.device)), "aga_layernorm_fwd")
+    has_sum = residual2 is not None and want_sum
+    tm = _Timed("layernorm_fwd", (2.0 + (residual2 is not None) + has_sum) * rows * D * x2.element_size(), x2.device)
+    y, s, mean, rstd = L.torch_ops().layernorm_fwd(x2, residual2, w32, b32, float(eps), bool(want_sum))
     tm.done(x2.device)
-    return y, (s if s is not None else x2), mean, rstd
+    return y, s, mean, rstd
 
 
 def _ln_bwd(dy2, s2, w32, mean, rstd, need_params, need_dxsum=False, dres2=None):
     rows, D = s2.shape
-    dx = torch.empty_like(s2)
+    tm = _Timed("layernorm_bwd", 3.0 * rows * D * s2.element_size(), s2.device)
+    dx, pg = L.torch_ops().layernorm_bwd(dy2, s2, w32, mean, rstd, bool(need_params), bool(need_dxsum), dres2)
+    tm.done(s2.device)
     dgamma = dbeta = dxsum = None
     if need_params:  # rows of one buffer: the library clears them with a single memset
-        pg = torch.empty((3 if need_dxsum else 2, D), dtype=torch.float32, device=s2.device)
         dgamma, dbeta = pg[0], pg[1]
         dxsum = pg[2] if need_dxsum else None
-    tm = _Timed("layernorm_bwd", 3.0 * rows * D * s2.element_size(), s2.device)
-    L.check(L.lib().aga_layernorm_bwd(_ptr(dy2), _ptr(s2), _DTYPES[s2.dtype], rows, D, _ptr(w32), _ptr(mean), _ptr(rstd),
-                                      _ptr(dres2), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), _stream_ptr(s2.device)),
-            "aga_layernorm_bwd")
-    tm.done(s2.device)
     return dx, dgamma, dbeta, dxsum
 
 
@@ -497,13 +490,8 @@ def _wgrad(a_t: torch.Tensor, b: torch.Tensor, dtype: torch.dtype) -> torch.Tens
 def gelu_bwd_colsum(dg: torch.Tensor, h: torch.Tensor):
     """(dg * gelu'(h), column sums of that product) in one pass — at::gelu_backward + sum(0) of the Adapter backward."""
     _require_cuda(dg, "dg")
-    rows, cols = h.shape
     dg = dg if dg.is_contiguous() else dg.contiguous()
-    dh = torch.empty_like(h)
-    colsum = torch.empty(cols, dtype=torch.float32, device=h.device)
-    L.check(L.lib().aga_gelu_bwd_colsum(_ptr(dg), _ptr(h), _DTYPES[h.dtype], rows, cols, _ptr(dh), _ptr(colsum),
-                                        _stream_ptr(h.device)), "aga_gelu_bwd_colsum")
-    return dh, colsum
+    return L.torch_ops().gelu_bwd_colsum(dg, h)
 
 
 class _AdapterLayerNormFn(torch.autograd.Function):
@@ -573,15 +561,8 @@ def _lr_workspace(device) -> torch.Tensor:
 
 def _linear_residual_raw(x2: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], r2: torch.Tensor, w_kn: bool = False):
     """r2 + x2 @ W (+ b) on contiguous 2-D operands; W = w^T for an (N, K) weight, W = w for a (K, N) one (``w_kn``)."""
-    K = x2.shape[1]
-    N = w.shape[1] if w_kn else w.shape[0]
-    out = torch.empty_like(r2)
-    ws = _lr_workspace(x2.device)
-    st = L.lib().aga_linear_residual(_ptr(x2), _ptr(w), 1 if w_kn else 0, _ptr(b), _ptr(r2), _ptr(out), _DTYPES[x2.dtype],
-                                     x2.shape[0], N, K, _ptr(ws), ws.numel(), _stream_ptr(x2.device))
     # no fallback: AGA_ERR_UNSUPPORTED (cuBLASLt not loadable in the process, operands not 16-byte aligned) raises
-    L.check(st, "aga_linear_residual")
-    return out
+    return L.torch_ops().linear_residual(x2, w, bool(w_kn), b, r2, _lr_workspace(x2.device))
 
 
 class _LinearResidualFn(torch.autograd.Function):
@@ -625,24 +606,13 @@ def linear_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.
 # ------------------------------------------------------------------------------------------------
 def gemm_gelu_fwd(x2: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]):
     """(h, gelu(h)) with h = x2 @ w^T + b, bf16, in one tcgen05 GEMM (csrc/gemm_gelu.cu, mode 0)."""
-    M, K = x2.shape
-    N = w.shape[0]
-    h = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device)
-    g = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device)
-    L.check(L.lib().aga_gemm_gelu(_ptr(x2), _ptr(w), _ptr(b), _ptr(h), _ptr(g), 0, M, N, K, _stream_ptr(x2.device)),
-            "aga_gemm_gelu")
-    return h, g
+    return L.torch_ops().gemm_gelu_fwd(x2, w, b)
 
 
 def gemm_gelu_bwd(dy2: torch.Tensor, w_t: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
     """dh = (dy2 @ w_t^T) * gelu'(h): the second Linear's dgrad GEMM with the GELU backward in its epilogue (mode 1);
     ``w_t`` (N, K) is the transpose of that Linear's (K, N) weight."""
-    M, K = dy2.shape
-    N = w_t.shape[0]
-    dh = torch.empty((M, N), dtype=torch.bfloat16, device=dy2.device)
-    L.check(L.lib().aga_gemm_gelu(_ptr(dy2), _ptr(w_t), None, _ptr(h), _ptr(dh), 1, M, N, K, _stream_ptr(dy2.device)),
-            "aga_gemm_gelu")
-    return dh
+    return L.torch_ops().gemm_gelu_bwd(dy2, w_t, h)
 
 
 class _MlpResidualFn(torch.autograd.Function):
@@ -709,13 +679,7 @@ class _LsCeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits2, target, n_vocab, padding_idx, smoothing, denom):
         _require_cuda(logits2, "logits")
-        rows, ld = logits2.shape
-        row_loss = torch.empty(rows, dtype=torch.float32, device=logits2.device)
-        row_lse = torch.empty(rows, dtype=torch.float32, device=logits2.device)
-        row_correct = torch.empty(rows, dtype=torch.int32, device=logits2.device)
-        L.check(L.lib().aga_ls_ce_fwd(_ptr(logits2), _DTYPES[logits2.dtype], rows, n_vocab, ld, _ptr(target), padding_idx,
-                                      float(smoothing), _ptr(row_loss), _ptr(row_lse), _ptr(row_correct),
-                                      _stream_ptr(logits2.device)), "aga_ls_ce_fwd")
+        row_loss, row_lse, row_correct = L.torch_ops().ls_ce_fwd(logits2, target, n_vocab, padding_idx, float(smoothing))
         ctx.save_for_backward(logits2, target, row_lse, denom)
         ctx.cfg = (n_vocab, padding_idx, float(smoothing))
         ctx.mark_non_differentiable(row_correct)
@@ -725,12 +689,8 @@ class _LsCeFn(torch.autograd.Function):
     def backward(ctx, g, _):
         logits2, target, row_lse, denom = ctx.saved_tensors
         n_vocab, padding_idx, smoothing = ctx.cfg
-        rows, ld = logits2.shape
         gscale = (g.float() / denom).reshape(1).contiguous()  # upstream gradient / denominator, as a device scalar
-        dlogits = torch.empty_like(logits2)
-        L.check(L.lib().aga_ls_ce_bwd(_ptr(logits2), _DTYPES[logits2.dtype], rows, n_vocab, ld, _ptr(target), padding_idx,
-                                      smoothing, _ptr(row_lse), _ptr(gscale), 1.0, _ptr(dlogits),
-                                      _stream_ptr(logits2.device)), "aga_ls_ce_bwd")
+        dlogits = L.torch_ops().ls_ce_bwd(logits2, target, n_vocab, padding_idx, smoothing, row_lse, gscale)
         return dlogits, None, None, None, None, None
 
 
@@ -772,10 +732,7 @@ def attention_pattern(tokens: torch.Tensor, lid_table: torch.Tensor, c: float = 
     tokens = tokens.to(torch.int64).contiguous()
     B, T = tokens.shape
     lid_table = lid_table.to(device=tokens.device, dtype=torch.uint8).contiguous()
-    out = torch.empty((B, T, 2), dtype=torch.float32, device=tokens.device)
-    L.check(L.lib().aga_attention_pattern(_ptr(tokens), _ptr(lid_table), lid_table.numel(), B, T, float(c), _ptr(out),
-                                          _stream_ptr(tokens.device)), "aga_attention_pattern")
-    return out
+    return L.torch_ops().attention_pattern(tokens, lid_table, float(c))
 
 
 class _GuidedLossFn(torch.autograd.Function):
@@ -789,20 +746,12 @@ class _GuidedLossFn(torch.autograd.Function):
         head_mask = head_mask.to(device=slab.device, dtype=torch.float32).contiguous()
         if pattern.shape != (B, T, 2) or head_mask.shape != (Lyr, H):
             raise L.AgaError("pattern must be (B,T,2) and head_mask (L,H)")
-        lib = L.lib()
-        loss = torch.empty((), dtype=torch.float32, device=slab.device)
         need_grad = ctx.needs_input_grad[0]
         # a strided view (columns 1:3 of full maps) is gathered once: the slab is only L*B*H*T*2 floats,
         # and autograd scatters the dense gradient back through the view
         src = slab.contiguous()
-        d_slab = torch.empty_like(src) if need_grad else None
-        nbytes = C.c_size_t()
-        L.check(lib.aga_guided_loss_workspace_bytes(Lyr, B, H, C.byref(nbytes)), "aga_guided_loss_workspace_bytes")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=slab.device)
-        L.check(lib.aga_guided_loss_fwd_bwd(_ptr(src), src.stride(0), src.stride(1), src.stride(2), src.stride(3),
-                                            _ptr(pattern), _ptr(head_mask), Lyr, B, H, T, int(n_early), _ptr(loss),
-                                            _ptr(d_slab), _ptr(ws), nbytes.value, _stream_ptr(slab.device)),
-                "aga_guided_loss_fwd_bwd")
+        loss, d_slab = L.torch_ops().guided_loss(src, pattern, head_mask, int(n_early), bool(need_grad))
+        d_slab = d_slab if need_grad else None
         ctx.d_slab = d_slab
         return loss
 
@@ -823,9 +772,7 @@ def head_vote(probs: torch.Tensor, counts: Optional[torch.Tensor] = None):
     probs = probs.float().contiguous()
     Lyr, B, H, T, T2 = probs.shape
     assert T == T2
-    dec = torch.empty((Lyr, B, H), dtype=torch.uint8, device=probs.device)
     if counts is None:
         counts = torch.zeros((Lyr, H), dtype=torch.int32, device=probs.device)
-    L.check(L.lib().aga_head_vote(_ptr(probs), Lyr, B, H, T, _ptr(dec), _ptr(counts), _stream_ptr(probs.device)),
-            "aga_head_vote")
+    dec = L.torch_ops().head_vote(probs, counts)
     return dec, counts

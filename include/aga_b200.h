@@ -87,6 +87,23 @@ AGA_API int aga_logmel_workspace_bytes(int64_t B, int64_t N, int n_mels, size_t*
 AGA_API int aga_logmel_fwd(const float* audio, int64_t B, int64_t N, int64_t ld, const void* packed_filters, int n_mels,
                    float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core frontend (csrc/logmel_tc.cu): the same function for BANDED filterbanks — every bin feeds at most two
+ * adjacent filters and the filter index does not decrease with the bin (the Slaney triangles of W/audio.py:92-107 and
+ * their 128-bin sibling).  The 400-point DFT runs as split-precision fp16 GEMMs on tcgen05 (fp32-FFT accuracy).
+ *   aga_logmel_filters_banded: 1 when the HOST filterbank (n_mels x 201, row-major) has that structure.
+ *   aga_logmel_tc_pack: builds mel bands + DFT tables on the host and enqueues their upload into `packed`
+ *     (aga_logmel_tc_packed_bytes bytes of device memory, 16-byte aligned); AGA_ERR_UNSUPPORTED if not banded.
+ *   aga_logmel_tc_fwd: as aga_logmel_fwd.  `n_valid` (device int32 scalar, may be NULL): the batch's true common length
+ *     when `audio` is zero-padded to N for a static launch shape — reflect padding happens at *n_valid, frames past
+ *     *n_valid / 160 are written as zeros (what the reference's conv stem would pad with) and do not enter the maximum. */
+AGA_API int aga_logmel_filters_banded(const float* melfb_host, int n_mels);
+AGA_API int aga_logmel_tc_packed_bytes(int n_mels, size_t* bytes);
+/* the packed image in HOST memory (what aga_logmel_tc_pack uploads): header | float4 bin[201] = {w(L), w(L+1), L, 0} | DFT tables */
+AGA_API int aga_logmel_tc_build_host(const float* melfb_host, int n_mels, void* packed_host, size_t packed_bytes);
+AGA_API int aga_logmel_tc_pack(const float* melfb_host, int n_mels, void* packed, size_t packed_bytes, void* stream);
+AGA_API int aga_logmel_tc_fwd(const float* audio, int64_t B, int64_t N, int64_t ld, const void* packed_tc, int n_mels,
+                      float* out, const int32_t* n_valid, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Multi-head attention core, head dim 64 (every Whisper size).
  * Replaces MultiHeadAttention.qkv_attention (W/model.py:93-109) and what autograd replays for it.
@@ -112,6 +129,9 @@ typedef struct aga_attn_params {
   float* lse;               /* (B, H, Tq) fp32 natural-log row log-sum-exp of S (needed by backward) */
   const uint8_t* head_sel;  /* (H) 0/1: heads whose columns are exported; NULL = all heads */
   float* export_buf;        /* (B, H, Tq, hi-lo) fp32; rows of unselected heads are left untouched */
+  const int32_t* kv_len;    /* NULL, or a DEVICE scalar: only keys [0, min(*kv_len, Tk)) exist (non-causal attention on a batch
+                             * zero-padded to a static Tk for CUDA-graph replay; the reference never computes the padded keys).
+                             * Backward: dk / dv rows at or past *kv_len are written as zeros.  tcgen05 path only. */
 } aga_attn_params;
 
 AGA_API int aga_attn_fwd_workspace_bytes(const aga_attn_params* p, size_t* bytes);
