@@ -128,8 +128,31 @@ def torch_ops():
             raise AgaError(f"{TORCH_EXT_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
         lib()  # libaga_b200.so first (the extension links against it)
         torch.ops.load_library(TORCH_EXT_PATH)
-        _torch_ops = torch.ops.aga
+        _torch_ops = _Ops(torch.ops.aga)
     return _torch_ops
+
+
+class _Ops:
+    """``torch.ops.aga`` with the extension's TORCH_CHECK failures (status codes of the C ABI, wrong devices / dtypes)
+    re-raised as :class:`AgaError`, the package's one error type."""
+
+    def __init__(self, ns):
+        self._ns = ns
+
+    def __getattr__(self, name):
+        fn = getattr(self._ns, name)
+
+        def call(*args):
+            try:
+                return fn(*args)
+            except AgaError:
+                raise
+            except (RuntimeError, NotImplementedError) as e:
+                raise AgaError(str(e).split("\n")[0]) from None
+
+        call.__name__ = name
+        self.__dict__[name] = call
+        return call
 
 
 def check(status: int, what: str) -> None:

@@ -116,7 +116,13 @@ struct FwdArgs {
   int export_lo, export_hi;    // exported key columns [lo, hi) of the scaled, masked logits (decoder self attention)
   float* export_buf;           // (B, H, Tq, hi - lo) fp32 or nullptr
   const uint8_t* head_sel;     // (H) or nullptr: heads whose columns are exported
+  const int32_t* kv_len;       // nullptr, or device scalar: only keys [0, min(*kv_len, Tk)) exist (zero-padded static shapes)
 };
+
+// effective key count of a launch whose key length is padded to a static Tk (aga_attn_params::kv_len)
+__device__ __forceinline__ int effective_tk(const int32_t* kv_len, int Tk) {
+  return kv_len ? max(1, min(__ldg(kv_len), Tk)) : Tk;
+}
 
 // 32 fp32 TMEM columns (scaled) -> the bf16 half `half` (64 bytes) of a 128-byte row of a SWIZZLE_128B staging tile
 __device__ __forceinline__ void stage_half_row_bf16(uint32_t row_addr, int row, int half, const uint32_t (&v)[32], float scale) {
@@ -154,7 +160,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row0 = qt * NT * kBlockM;
-  const int n_kt_all = (a.Tk + kBlockN - 1) / kBlockN;
+  const int Tk = effective_tk(a.kv_len, a.Tk);
+  const int n_kt_all = (Tk + kBlockN - 1) / kBlockN;
   const int n_kt = a.causal ? min(n_kt_all, (row0 + NT * kBlockM - 1) / kBlockN + 1) : n_kt_all;
   const bool active_b = NT == 2 && row0 + kBlockM < a.Tq;  // tile B exists and holds at least one valid row
 
@@ -305,7 +312,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&sb->s_free[t]);
         TL(22);
-        int valid = a.Tk - j * kBlockN;  // keys of this tile this row may see (>= 128 except on the last / diagonal tile)
+        int valid = Tk - j * kBlockN;  // keys of this tile this row may see (>= 128 except on the last / diagonal tile)
         if (a.causal) valid = min(valid, row - j * kBlockN + 1);
         if (valid < kBlockN) {
 #pragma unroll
@@ -461,7 +468,8 @@ attn_fwd_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row0 = qt * kBlockM;
-  const int n_kt_all = (a.Tk + kBlockN - 1) / kBlockN;
+  const int Tk = effective_tk(a.kv_len, a.Tk);
+  const int n_kt_all = (Tk + kBlockN - 1) / kBlockN;
   const int n_kt = a.causal ? min(n_kt_all, (row0 + kBlockM - 1) / kBlockN + 1) : n_kt_all;
 
   if (threadIdx.x == 0) {
@@ -590,7 +598,7 @@ attn_fwd_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb->s_free);
       const int kbase = j * kBlockN + ch * 64;
-      int valid = a.Tk - kbase;  // keys of this 64-column slice the row may see
+      int valid = Tk - kbase;  // keys of this 64-column slice the row may see
       if (a.causal) valid = min(valid, row - kbase + 1);
       if (valid < 64) {
 #pragma unroll
@@ -752,7 +760,7 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
   const bool exporting = p.export_kind == AGA_EXPORT_LOGITS && p.export_buf != nullptr;
   FwdArgs a{p.B, p.H, p.Tq, p.Tk, p.o_stride_b, p.o_stride_t, static_cast<__nv_bfloat16*>(p.out), p.lse, p.causal,
             exporting ? p.export_lo : 0, exporting ? p.export_hi : 0, exporting ? p.export_buf : nullptr,
-            exporting ? p.head_sel : nullptr};
+            exporting ? p.head_sel : nullptr, p.kv_len};
 #ifdef AGA_FWD_TWO_TILES  // one CTA per SM, two query tiles sharing each K/V tile
   constexpr int NT = 2;
 #else                     // two independent single-tile CTAs per SM (measured faster: see DESIGN.md)
@@ -834,6 +842,7 @@ struct BwdArgs {
   float* dq_accum;  // (B, H, ceil(Tq/128), 2, 128, 32) fp32, zero-initialised, 16-byte chunks XOR-swizzled with (row & 7)
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
+  const int32_t* kv_len;  // nullptr, or device scalar: keys at or past it do not exist (their P is forced to 0; key tiles past it are skipped)
 };
 
 // MN-major operand spanning two 64-element panels along M (dS^T rows as the A of dQ): LBO = panel stride
@@ -875,10 +884,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   CTA_LOG(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (a.Tq + kBlockM - 1) / kBlockM;
-  const int n_kt = (a.Tk + kBlockN - 1) / kBlockN;
+  const int Tk = effective_tk(a.kv_len, a.Tk);
+  const int n_kt = (Tk + kBlockN - 1) / kBlockN;
   // work items of this CTA: w = blockIdx.x + it * gridDim.x;  item w = ((b * H + h) * n_kt + kt)
+  // (with kv_len the item list is re-enumerated over the key tiles that exist: a.n_items is the static upper bound)
+  const int n_items = a.kv_len ? a.B * a.H * n_kt : a.n_items;
   const int first_item = blockIdx.x, item_step = gridDim.x;
-  const int my_items = first_item < a.n_items ? (a.n_items - first_item + item_step - 1) / item_step : 0;
+  const int my_items = first_item < n_items ? (n_items - first_item + item_step - 1) / item_step : 0;
   const int total_tiles = my_items * n_qt;  // tiles this CTA processes (the global tile counter c runs over them)
 
   if (threadIdx.x == 0) {
@@ -1106,6 +1118,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     TL_DECL(((warp & 7) == 0 && lane == 0) ? 1 + g : -1);
     int c = 0;
     for (int it = 0; it < my_items; ++it) {
+      // keys past the effective length (kv_len inside a static Tk) keep P^T = 0: this lane's key is masked for the item
+      uint32_t keep = 0xffffffffu;
+      if (a.kv_len) {
+        int kt_i, h_i, b_i;
+        decode(it, kt_i, h_i, b_i);
+        keep = (kt_i * kBlockN + r < Tk) ? 0xffffffffu : 0u;
+      }
       for (int i = 0; i < n_qt; ++i, ++c) {
         const uint32_t par = c & 1;
         TL(20);
@@ -1154,6 +1173,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #ifndef AGA_BWD_NO_TOKEN
           if (!(g == 1 && c == total_tiles - 1)) pk[15] ^= __float_as_uint(named_bar_arrive_dep(5 - g, 512, chk)) ^ __float_as_uint(chk);
 #endif
+        }
+        if (a.kv_len) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[e] &= keep;
         }
         tmem_st16(t_s, pk);  // 32 queries as bf16 pairs over the first 16 of this slice's S^T columns
         tmem_wait_st();
@@ -1412,6 +1435,7 @@ struct QrArgs {
   const uint8_t* head_sel;    // (H) or nullptr
   const float* stats;  // (B, H, 1, 2, 128): lse * log2(e) | delta, zero past Tq
   float* dq_accum;     // (B, H, 1, 2, 128, 32) fp32, zero-initialised, chunk-swizzled like the persistent kernel's
+  const int32_t* kv_len;  // as BwdArgs::kv_len
 };
 
 __global__ void __launch_bounds__(kQrThreads, 1)
@@ -1432,9 +1456,11 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int n_kt = (a.Tk + kBlockN - 1) / kBlockN;
+  const int Tk = effective_tk(a.kv_len, a.Tk);
+  const int n_kt = (Tk + kBlockN - 1) / kBlockN;
   const int kt0 = blockIdx.x * a.tiles_per_cta;
-  const int n_my = min(a.tiles_per_cta, n_kt - kt0);  // >= 1 by construction of the grid
+  const int n_my = min(a.tiles_per_cta, n_kt - kt0);  // >= 1 by construction of the grid, unless kv_len cut the key range
+  if (n_my <= 0) return;  // (whole CTA, before any barrier / TMEM allocation: its key tiles do not exist)
 
   if (threadIdx.x == 0) {
     mbar_init(&sb->qdo_full, 1);
@@ -1631,8 +1657,10 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sb->s_free);
-        if (a.causal) {  // key > query: -inf -> P = 0
-          const int vis = row - ((kt0 + jj) * kBlockN + cs * 32) + 1;  // keys of this 32-column slice the row may see
+        if (a.causal || a.kv_len) {  // key > query (causal) or key >= kv_len: -inf -> P = 0
+          const int kbase = (kt0 + jj) * kBlockN + cs * 32;
+          int vis = a.causal ? row - kbase + 1 : 32;  // keys of this 32-column slice the row may see
+          if (a.kv_len) vis = min(vis, Tk - kbase);
           if (vis < 32) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -1806,7 +1834,7 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
     const int n_chunks = (n_kt + per - 1) / per;
     const bool dexp = p.export_kind == AGA_EXPORT_LOGITS && bp.d_export != nullptr;
     QrArgs qa{p.B, p.H, p.Tq, p.Tk, per, p.causal, dexp ? p.export_lo : 0, dexp ? p.export_hi : 0,
-              dexp ? bp.d_export : nullptr, dexp ? p.head_sel : nullptr, stats, dq_acc};
+              dexp ? bp.d_export : nullptr, dexp ? p.head_sel : nullptr, stats, dq_acc, p.kv_len};
     CUtensorMap mdk, mdv;  // 32-row boxes: one store per drain warp
     if ((st = make_map(&mdk, bp.dk, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, 32)) != AGA_OK) return st;
     if ((st = make_map(&mdv, bp.dv, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, 32)) != AGA_OK) return st;
@@ -1818,7 +1846,7 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
   {
   const int n_items = p.B * p.H * n_kt;
   BwdArgs a{p.B, p.H, p.Tq, p.Tk, n_items, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, stats, dq_acc,
-            static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv)};
+            static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv), p.kv_len};
   AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBwdSmemBytes)));
   const unsigned grid = unsigned(std::min(n_items, n_sm));  // persistent: one CTA per SM walks the items
   CUtensorMap mdk, mdv;

@@ -89,9 +89,14 @@ constexpr int kAccStride = kN;                  // TMEM columns between the four
 constexpr int kColAhi = 4 * kN;                 // [448, 512): HI halves of the A operands, 2 ring slots x 4 sequences x 8 columns
 constexpr int kTmemCols = 512;
 
+// Warp roles.  The SM sub-partition schedulers prefer the HIGHEST warp id among the ready warps: the epilogue (which holds
+// the accumulators and therefore the tensor core) gets the top ids, the producers the middle, the two single-thread
+// issuers the bottom; every long wait backs off with nanosleep instead of polling.  (With the epilogue on warps 0-7 and
+// polling waits above it, it ran at one instruction per ~10 cycles.)  Warps 2, 3 only keep the role blocks aligned to
+// the TMEM lane quarters (warp % 4) that tcgen05.ld / .st impose.
 constexpr int kEpiWarps = 8, kPrepWarps = 8;
-constexpr int kWarpPrep0 = kEpiWarps, kWarpMma = kEpiWarps + kPrepWarps, kWarpLoad = kWarpMma + 1;
-constexpr int kThreads = (kWarpLoad + 1) * 32;  // 576
+constexpr int kWarpMma = 0, kWarpLoad = 1, kWarpPrep0 = 4, kWarpEpi0 = kWarpPrep0 + kPrepWarps;
+constexpr int kThreads = (kWarpEpi0 + kEpiWarps) * 32;  // 640
 constexpr int kPrepThreads = kPrepWarps * 32;
 constexpr int kStageVecs = (kChunk / 4 + kPrepThreads - 1) / kPrepThreads;  // float4 per producer thread per tile (21)
 constexpr int kMaxMels = 256;
@@ -149,6 +154,10 @@ __device__ __forceinline__ float load_reflect(const float* __restrict__ row, int
   if (g < 0) g = -g;                    // reflect, no edge repeat: x_pad[199 - i] = x[i + 1]
   if (g >= N) g = 2 * (N - 1) - g;
   return (g >= 0 && g < N) ? __ldg(row + g) : 0.0f;
+}
+
+__device__ __forceinline__ void st_global_pred(float* ptr, float v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(ptr), "f"(v), "r"(int(pred)) : "memory");
 }
 
 // v -> (hi, lo) fp16 pairs of two values, packed
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
 
   const int n_my_tiles = (p.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
 
-  if (warp >= kWarpPrep0 && warp < kWarpMma) {
+  if (warp >= kWarpPrep0 && warp < kWarpEpi0) {
     // =========================================================== producers: staging + A operands
     const int ptid = tid - kWarpPrep0 * 32;
     const int quarter = warp & 3, khalf = (warp - kWarpPrep0) >> 2;  // this warp builds K columns [8 khalf, 8 khalf + 8) of a step
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
       for (int j = 0; j < kKSteps; ++j) {
         const int it = ti * kKSteps + j, slot_i = it & 1, use = it >> 1;
         LTL(110);
-        if (use > 0) mbar_wait(&bar_empty[slot_i], (use - 1) & 1);
+        if (use > 0) mbar_wait_sleep(&bar_empty[slot_i], (use - 1) & 1, 40);
         tc_fence_after();
         LTL(111);
         // K columns kk = 8 khalf + c (c = 0..7) need n = 32 j + t, t = 16 khalf + t', t' = 1..16, and x_{400-n}:
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
       for (int it = 0; it < total; ++it) {
         const int s = it & 1, use = it >> 1, j = it % kKSteps;
         LTL(400);
-        if (use > 0) mbar_wait(&bar_empty[s], (use - 1) & 1);
+        if (use > 0) mbar_wait_sleep(&bar_empty[s], (use - 1) & 1, 100);
         LTL(401);
         mbar_arrive_expect_tx(&bar_full[s], kStageT);
         bulk_load(smem + Smem::kStage + size_t(s) * kStageBytes + kStageA, g_tables + size_t(j) * kStageT, kStageT, &bar_full[s]);
@@ -377,14 +386,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
     for (int ti = 0; ti < n_my_tiles; ++ti) {
       LTL(200);
       if (ti > 0) {
-        mbar_wait(bar_acc_empty, (ti - 1) & 1);
+        mbar_wait_sleep(bar_acc_empty, (ti - 1) & 1, 100);
         tc_fence_after();
       }
       LTL(201);
       for (int j = 0; j < kKSteps; ++j) {
         const int it = ti * kKSteps + j, s = it & 1, use = it >> 1;
         LTL(210);
-        mbar_wait(&bar_full[s], use & 1);
+        mbar_wait_sleep(&bar_full[s], use & 1, 20);
         LTL(211);
         tc_fence_after();
         if (elect_one()) {
@@ -407,14 +416,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
         LTL(212);
       }
     }
-  } else {
+  } else if (warp >= kWarpEpi0) {
     // =========================================================== epilogue: power spectrum -> banded mel -> log10
     // Two streams per TMEM lane quarter (see TcHeader): warp q walks bins 0..100 upwards, warp 4 + q bins 200..101
     // downwards, with the SAME code (sign of the Co / So terms, tables and output direction are data): a rolled loop over
     // 7 blocks of 16 accumulator columns whose body is unrolled over the 16 register-resident columns.  The hand-over of
     // the running sums is a warp-uniform branch on two 16-bit masks per block.  (Fully unrolled over the filterbank the
     // epilogue was 50-200 KB of straight-line code and instruction-fetch bound — the MMAs wait for the accumulators.)
-    const int quarter = warp & 3, role = warp >> 2;
+    const int quarter = warp & 3, role = (warp - kWarpEpi0) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t tq = tmem + (uint32_t(quarter * 32) << 16);
     const int n_mels = p.n_mels;
@@ -431,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
       const int b = t / p.tiles_per_utt, f = (t - b * p.tiles_per_utt) * kTileFrames + r;
       const bool live = f < Fv;
       float* obase = p.out + int64_t(b) * n_mels * F + f;
-      mbar_wait(bar_acc_full, ti & 1);
+      mbar_wait_sleep(bar_acc_full, ti & 1, 200);
       LTL(301);
       tc_fence_after();
       const float inv_s2 = s_scale[ti & 1].y;
@@ -441,11 +450,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
         const float v = acc * inv_s2;
         if (live && m >= 0 && m < n_mels) {
           obase[int64_t(m) * F] = v;
-          vmax = fmaxf(vmax, v);
+          vmax = fmaxf(vmax, v == v ? v : INFINITY);
         }
       };
       float accA = 0.f, accB = 0.f;  // running sums of the older / newer filter
       int m_id = first_id;           // the older filter
+      const int64_t step_f = int64_t(step) * F;
+      float* optr = obase + int64_t(m_id) * F;  // where the older filter's value of this frame goes (dereferenced only when valid)
 #pragma unroll 1
       for (int blk = 0; blk < 7; ++blk) {
         float pw[16];
@@ -454,8 +465,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
           tmem_ld16(tq + 0 * kAccStride + blk * 16, ce);
           tmem_ld16(tq + 1 * kAccStride + blk * 16, co);
           tmem_ld16(tq + 2 * kAccStride + blk * 16, se);
+          LTL(310 + blk);
           tmem_ld16(tq + 3 * kAccStride + blk * 16, so);
           tmem_wait_ld();
+          LTL(320 + blk);
           if (blk == 6) {  // last TMEM read of the tile: the accumulators are free for the next tile's MMAs
             tc_fence_before();
             __syncwarp();
@@ -470,26 +483,41 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Params p) 
             pw[i] = fmaf(re, re, im * im);
           }
         }
+        LTL(330 + blk);
         const uint32_t m1 = mk[2 * blk], m2 = mk[2 * blk + 1];
         float2 wv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) wv[i] = wt[blk * 16 + i];
-        // phase 2: the running sums, handed over where the masks say so (warp-uniform branches)
+        // phase 2: the running sums.  The hand-over (where the block's masks say so) is PREDICATED, not branched: a
+        // completed filter leaves through a predicated store and the sums rotate through selects.  (With a branch per
+        // bin the warp spent its time on instruction-fetch bubbles behind the reconvergence points: 15 k cycles per tile.)
+        auto hand_over = [&](bool rot) {
+          const bool pe = rot && live && unsigned(m_id) < unsigned(n_mels);
+          const float v = accA * inv_s2;
+          st_global_pred(optr, v, pe);
+          // (a NaN power — non-finite samples — must not vanish in fmaxf: it raises the utterance maximum to +inf, which
+          //  makes the whole utterance non-finite downstream, as the reference's NaN-propagating max does)
+          vmax = fmaxf(vmax, pe ? (v == v ? v : INFINITY) : 0.f);
+          accA = rot ? accB : accA;
+          accB = rot ? 0.f : accB;
+          m_id += rot ? step : 0;
+          optr += rot ? step_f : 0;
+        };
+        if (m2 == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if ((m1 >> i) & 1) {
-            emit(m_id, accA);
-            accA = accB;
-            accB = 0.f;
-            m_id += step;
-            if ((m2 >> i) & 1) {
-              emit(m_id, accA);
-              accA = accB;  // = 0
-              m_id += step;
-            }
+          for (int i = 0; i < 16; ++i) {
+            hand_over((m1 >> i) & 1);
+            accA = fmaf(wv[i].x, pw[i], accA);
+            accB = fmaf(wv[i].y, pw[i], accB);
           }
-          accA = fmaf(wv[i].x, pw[i], accA);
-          accB = fmaf(wv[i].y, pw[i], accB);
+        } else {  // a bin that completes two filters at once (once per stock filterbank)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            hand_over((m1 >> i) & 1);
+            hand_over((m2 >> i) & 1);
+            accA = fmaf(wv[i].x, pw[i], accA);
+            accB = fmaf(wv[i].y, pw[i], accB);
+          }
         }
       }
       // the streams meet between bins 100 and 101.  ascending: accA <-> filter L100, accB <-> L100 + 1;

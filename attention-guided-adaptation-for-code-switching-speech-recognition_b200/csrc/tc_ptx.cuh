@@ -54,6 +54,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same with a back-off between polls: a warp that is expected to wait for hundreds of cycles must not keep polling —
+// the scheduler issues from the highest warp id first, and a spinning high-id warp starves the working low-id ones.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
 // named barriers (ids 1..15; id 0 is __syncthreads): `count` threads in total take part (syncing + arriving)
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }

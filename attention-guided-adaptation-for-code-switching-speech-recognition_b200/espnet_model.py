@@ -213,13 +213,16 @@ class ESPnetASRModel(torch.nn.Module):
         return ops.guided_loss(slab, pattern, self.cs_head_mask, self.n_early_layers)
 
     # ------------------------------------------------------------------ plumbing
-    def encode(self, speech: torch.Tensor, speech_lengths: torch.Tensor):
+    def encode(self, speech: torch.Tensor, speech_lengths: torch.Tensor, valid_samples: Optional[torch.Tensor] = None):
         """:723-788 for frontend=None / Whisper: the encoder consumes raw audio."""
-        encoder_out, encoder_out_lens, _ = self.encoder(speech, speech_lengths)
+        if valid_samples is None:
+            encoder_out, encoder_out_lens, _ = self.encoder(speech, speech_lengths)
+        else:
+            encoder_out, encoder_out_lens, _ = self.encoder(speech, speech_lengths, valid_samples=valid_samples)
         assert encoder_out.size(0) == speech.size(0)
         return encoder_out, encoder_out_lens
 
-    def _calc_att_loss(self, encoder_out, encoder_out_lens, ys_pad, ys_pad_lens):
+    def _calc_att_loss(self, encoder_out, encoder_out_lens, ys_pad, ys_pad_lens, memory_len=None):
         """:900-961."""
         if self.lang_token_id is not None:
             ys_pad = torch.cat([self.lang_token_id.repeat(ys_pad.size(0), 1).to(ys_pad.device), ys_pad], dim=1)
@@ -229,7 +232,10 @@ class ESPnetASRModel(torch.nn.Module):
         else:
             ys_in_pad, ys_out_pad = add_sos_eos(ys_pad, self.sos, self.eos, self.ignore_id)
         ys_in_lens = ys_pad_lens + 1
-        decoder_out, att_map = self.decoder(encoder_out, encoder_out_lens, ys_in_pad, ys_in_lens)
+        if memory_len is None:
+            decoder_out, att_map = self.decoder(encoder_out, encoder_out_lens, ys_in_pad, ys_in_lens)
+        else:
+            decoder_out, att_map = self.decoder(encoder_out, encoder_out_lens, ys_in_pad, ys_in_lens, memory_len=memory_len)
         fused = isinstance(decoder_out, ops.VocabLogits)
         if fused:  # decoder(fused_loss=True): KL loss + accuracy straight from the padded logits, no fp32 (B,T,V) tensor
             c = self.criterion_att
@@ -244,15 +250,22 @@ class ESPnetASRModel(torch.nn.Module):
         return loss_att, acc_att, None, None, loss_cs
 
     def forward(self, speech: torch.Tensor, speech_lengths: torch.Tensor, text: torch.Tensor,
-                text_lengths: torch.Tensor, **kwargs):
-        """:534-710 (attention-decoder branch): returns (loss, stats, weight)."""
+                text_lengths: torch.Tensor, valid_samples: Optional[torch.Tensor] = None, **kwargs):
+        """:534-710 (attention-decoder branch): returns (loss, stats, weight).
+
+        ``valid_samples`` (device int32 scalar, not in the reference): ``speech`` is zero-padded to a static bucket length
+        and this is the batch's true padded length — what the reference's collate_fn would have produced.  The log-mel
+        frontend, the conv stem, the encoder self attention and the decoder cross attention then compute exactly the
+        unpadded batch (graphed.BucketedTrainStep)."""
         assert text_lengths.dim() == 1, text_lengths.shape
         assert speech.shape[0] == speech_lengths.shape[0] == text.shape[0] == text_lengths.shape[0]
         batch_size = speech.shape[0]
         if not self.static_shapes:
             text = text[:, : text_lengths.max()]  # "for data-parallel" (:566); needs a host sync
-        encoder_out, encoder_out_lens = self.encode(speech, speech_lengths)
-        loss_att, acc_att, cer_att, wer_att, loss_cs = self._calc_att_loss(encoder_out, encoder_out_lens, text, text_lengths)
+        encoder_out, encoder_out_lens = self.encode(speech, speech_lengths, valid_samples)
+        memory_len = None if valid_samples is None else self.encoder.encoder_frames(valid_samples)
+        loss_att, acc_att, cer_att, wer_att, loss_cs = self._calc_att_loss(encoder_out, encoder_out_lens, text, text_lengths,
+                                                                           memory_len=memory_len)
         loss = loss_att
         stats = dict()
         if self.cs_weight != 0.0:

@@ -60,14 +60,26 @@ class OpenAIWhisperEncoder(torch.nn.Module):
             array = F.pad(array, pad)
         return array
 
-    def log_mel_spectrogram(self, audio: torch.Tensor, ilens: torch.Tensor = None):
-        """whisper_encoder.py:105-135 -> one fused CUDA pass (csrc/logmel.cu)."""
-        return ops.log_mel_spectrogram(audio, ilens, n_mels=self.n_mels)
+    def log_mel_spectrogram(self, audio: torch.Tensor, ilens: torch.Tensor = None, valid_samples: torch.Tensor = None):
+        """whisper_encoder.py:105-135 -> one fused CUDA pass (csrc/logmel_tc.cu; csrc/logmel.cu for non-banded filterbanks)."""
+        return ops.log_mel_spectrogram(audio, ilens, n_mels=self.n_mels, valid_samples=valid_samples)
 
-    def whisper_encode(self, input: torch.Tensor, ilens: torch.Tensor = None):
-        """whisper_encoder.py:137-222 (no side network)."""
+    @staticmethod
+    def encoder_frames(valid_samples: torch.Tensor) -> torch.Tensor:
+        """Encoder output frames of ``valid_samples`` audio samples (conv2: k 3, stride 2, pad 1), as a device int32 scalar."""
+        mel = valid_samples.to(torch.int64) // ops.HOP_LENGTH
+        return ((mel - 1) // 2 + 1).to(torch.int32)
+
+    def whisper_encode(self, input: torch.Tensor, ilens: torch.Tensor = None, valid_samples: torch.Tensor = None):
+        """whisper_encoder.py:137-222 (no side network).  ``valid_samples``: the batch is zero-padded to a static bucket
+        length (graphed.BucketedTrainStep); frames past the true length are never attended to."""
         enc = self.encoders
-        x = enc.stem(input)  # conv1 + GELU + conv2 + GELU, token-major
+        kv_len = None
+        if valid_samples is None:
+            x = enc.stem(input)  # conv1 + GELU + conv2 + GELU, token-major
+        else:
+            x = enc.stem(input, valid_frames=valid_samples.to(torch.int64) // ops.HOP_LENGTH)
+            kv_len = self.encoder_frames(valid_samples)
         n_frames, max_pos = x.size(1), enc.positional_embedding.size(0)
         if n_frames <= max_pos:
             x = (x + enc.positional_embedding[:n_frames, :]).to(x.dtype)
@@ -76,7 +88,7 @@ class OpenAIWhisperEncoder(torch.nn.Module):
         x = self.dropout(x)
         last = len(enc.blocks) - 1
         for layer, block in enumerate(enc.blocks):
-            x, _ = block(x)
+            x, _ = block(x, kv_len=kv_len)
             if layer < last:
                 x = self.dropout(x)
         x = enc.ln_post(x)
@@ -87,14 +99,14 @@ class OpenAIWhisperEncoder(torch.nn.Module):
             olens = None
         return x, olens
 
-    def forward(self, xs_pad: torch.Tensor, ilens: torch.Tensor, prev_states: torch.Tensor = None
-                ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    def forward(self, xs_pad: torch.Tensor, ilens: torch.Tensor, prev_states: torch.Tensor = None,
+                valid_samples: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
         if self.do_pad_trim:
             xs_pad = self.pad_or_trim(xs_pad, self.pad_samples)
-        feats, feats_lens = self.log_mel_spectrogram(xs_pad, ilens)
+        feats, feats_lens = self.log_mel_spectrogram(xs_pad, ilens, valid_samples)
         if self.specaug is not None and self.encoders.training:
             feats, feats_lens = self.specaug(feats, feats_lens)
-        xs_pad, olens = self.whisper_encode(feats, feats_lens)
+        xs_pad, olens = self.whisper_encode(feats, feats_lens, valid_samples)
         return xs_pad, olens, None
 
 
@@ -203,8 +215,10 @@ class OpenAIWhisperDecoder(torch.nn.Module):
             block.attn.export = (self.export_kind, (1, 3) if mode == "compact" else None) if on else None
 
     def forward(self, hs_pad: torch.Tensor, hlens: torch.Tensor, ys_in_pad: torch.Tensor, ys_in_lens: torch.Tensor,
-                side_encoder_output: torch.Tensor = None) -> Tuple[torch.Tensor, Any]:
-        """whisper_decoder.py:89-170.  hlens / ys_in_lens are ignored exactly as in the reference (no key padding)."""
+                side_encoder_output: torch.Tensor = None, memory_len: torch.Tensor = None) -> Tuple[torch.Tensor, Any]:
+        """whisper_decoder.py:89-170.  hlens / ys_in_lens are ignored exactly as in the reference (no key padding).
+        ``memory_len`` (device int32 scalar): encoder frames that really exist when ``hs_pad`` is zero-padded to a static
+        bucket length (graphed.BucketedTrainStep) — the cross attention then sees exactly the unpadded memory."""
         dec = self.decoders
         tgt = dec.token_embedding(ys_in_pad) + dec.positional_embedding[: ys_in_pad.size(1)]
         x = self.dropout(tgt).to(hs_pad.dtype)
@@ -212,7 +226,7 @@ class OpenAIWhisperDecoder(torch.nn.Module):
         attention_scores: List[torch.Tensor] = []
         last = len(dec.blocks) - 1
         for layer, block in enumerate(dec.blocks):
-            x, attention_map = block(x, hs_pad, mask=dec.mask)
+            x, attention_map = block(x, hs_pad, mask=dec.mask, xa_len=memory_len)
             if layer < last:
                 x = self.dropout(x)
             if self.whisper_cs and layer >= self.src_layer:

@@ -58,7 +58,9 @@ class GuardedUpdate:
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, bucket, example_batch: Sequence[torch.Tensor],
                  max_grad_norm: float = 1.0, amp_dtype: Optional[torch.dtype] = torch.bfloat16, warmup: int = 3,
-                 accum_grad: int = 1):
+                 accum_grad: int = 1, warmup_updates: bool = True):
+        """``warmup_updates=False``: the warm-up passes before capture run forward + backward only — no optimizer step, so
+        capturing a graph in the middle of training (BucketedTrainStep) does not change the training state."""
         self.model, self.opt, self.bucket = model, optimizer, bucket
         self.max_grad_norm, self.amp_dtype = max_grad_norm, amp_dtype
         self.accum_grad = max(1, int(accum_grad))
@@ -74,7 +76,8 @@ class GraphedTrainStep:
             for _ in range(warmup):
                 for m in range(self.accum_grad):
                     self._fwd_bwd(m)
-                self.update()
+                if warmup_updates:
+                    self.update()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         # the closing micro-step: backward (+ all-reduce under it) + clip + optimizer, ONE graph
@@ -200,10 +203,19 @@ class BucketedTrainStep:
         self.model, self.opt, self.bucket = model, optimizer, bucket
         self.frame_buckets = tuple(sorted(int(f) for f in frame_buckets))
         self.text_multiple, self.ignore_id = int(text_multiple), ignore_id
-        self.kw = dict(max_grad_norm=max_grad_norm, amp_dtype=amp_dtype, warmup=warmup)
+        self.kw = dict(max_grad_norm=max_grad_norm, amp_dtype=amp_dtype, warmup=max(1, warmup), warmup_updates=False)
         self.max_graphs = max_graphs
         self.cache: Dict[Tuple[int, int, int], GraphedTrainStep] = {}
         self.captures = 0
+        # the optimizer's lazily created state must exist before the first capture: one SKIPPED step (found_inf = 1, what
+        # a non-finite gradient norm triggers) creates it without touching parameters, moments or step counts
+        if _is_fused(optimizer) and not optimizer.state:
+            for p in bucket.params:
+                p.grad = bucket.views[bucket._index[id(p)]]
+            bucket.flat.zero_()
+            optimizer.found_inf = torch.ones((), dtype=torch.float32, device=bucket.flat.device)
+            optimizer.step()
+            optimizer.found_inf = None
 
     def bucket_of(self, B: int, N: int, L: int) -> Tuple[int, int, int]:
         frames = N // 160

@@ -100,48 +100,35 @@ def mel_filters(device, n_mels: int = 80) -> torch.Tensor:
     return _FILTER_CACHE[key]
 
 
-def _packed_filters(filters: torch.Tensor):
-    """(algo, packed device buffer) for a filterbank tensor, cached.  algo "tc": banded filterbank (the stock Slaney
-    triangles), packed for the tensor-core frontend (csrc/logmel_tc.cu); "simt": any other matrix, packed for the general
-    CUDA-core kernel (csrc/logmel.cu).  The choice depends on the filterbank's structure only, never on the device or the
-    environment."""
-    key = (filters.data_ptr(), filters._version, tuple(filters.shape), str(filters.device))
+def _packed_filters(filters: torch.Tensor, algo: str) -> torch.Tensor:
+    """The filterbank packed for one of the two frontends (cached per tensor): "simt" — the banded form of
+    csrc/logmel.cu, any matrix; "tc" — mel bands + DFT tables of csrc/logmel_tc.cu, banded filterbanks only (the stock
+    Slaney triangles): AgaError otherwise."""
+    key = (filters.data_ptr(), filters._version, tuple(filters.shape), str(filters.device), algo)
     hit = _PACKED_CACHE.get(key)
     if hit is not None:
         return hit
     lib = L.lib()
     n_mels = filters.shape[0]
-    host = np.ascontiguousarray(filters.detach().cpu().numpy(), dtype=np.float32)  # once per filterbank
-    hptr = C.c_void_p(host.ctypes.data)
     nbytes = C.c_size_t()
-    if lib.aga_logmel_filters_banded(hptr, n_mels) == 1:
+    if algo == "tc":
+        host = np.ascontiguousarray(filters.detach().cpu().numpy(), dtype=np.float32)  # once per filterbank
+        hptr = C.c_void_p(host.ctypes.data)
+        if lib.aga_logmel_filters_banded(hptr, n_mels) != 1:
+            raise L.AgaError("the tensor-core frontend needs a banded filterbank (at most two adjacent filters per bin)")
         L.check(lib.aga_logmel_tc_packed_bytes(n_mels, C.byref(nbytes)), "aga_logmel_tc_packed_bytes")
         packed = torch.empty(nbytes.value, dtype=torch.uint8, device=filters.device)
         L.check(lib.aga_logmel_tc_pack(hptr, n_mels, _ptr(packed), nbytes.value, _stream_ptr(filters.device)),
                 "aga_logmel_tc_pack")
-        entry = ("tc", packed)
     else:
         L.check(lib.aga_logmel_packed_filter_bytes(n_mels, C.byref(nbytes)), "aga_logmel_packed_filter_bytes")
         packed = torch.empty(nbytes.value, dtype=torch.uint8, device=filters.device)
         L.check(lib.aga_logmel_pack_filters(_ptr(filters), n_mels, _ptr(packed), nbytes.value,
                                             _stream_ptr(filters.device)), "aga_logmel_pack_filters")
-        entry = ("simt", packed)
     if len(_PACKED_CACHE) > 16:
         _PACKED_CACHE.clear()
-    _PACKED_CACHE[key] = entry
+    _PACKED_CACHE[key] = packed
     packed._aga_keepalive = filters
-    return entry
-
-
-def _packed_filters_simt(filters: torch.Tensor) -> torch.Tensor:
-    """The general kernel's packing of any filterbank (tests compare the two frontends on the stock banks)."""
-    lib = L.lib()
-    n_mels = filters.shape[0]
-    nbytes = C.c_size_t()
-    L.check(lib.aga_logmel_packed_filter_bytes(n_mels, C.byref(nbytes)), "aga_logmel_packed_filter_bytes")
-    packed = torch.empty(nbytes.value, dtype=torch.uint8, device=filters.device)
-    L.check(lib.aga_logmel_pack_filters(_ptr(filters), n_mels, _ptr(packed), nbytes.value, _stream_ptr(filters.device)),
-            "aga_logmel_pack_filters")
     return packed
 
 
@@ -155,9 +142,14 @@ def log_mel_spectrogram(audio: torch.Tensor, ilens: Optional[torch.Tensor] = Non
 
     Same contract as OpenAIWhisperEncoder.log_mel_spectrogram (espnet2/asr/encoder/whisper_encoder.py:105-135).
     ``valid_samples`` (device int32 scalar): the batch's true common length when ``audio`` has been zero-padded to a
-    static bucket length (graphed.BucketedTrainStep) — frames past it come back as zeros.  ``algo`` ("tc" / "simt")
-    forces a kernel for tests; by default banded filterbanks run on the tensor cores.
+    static bucket length (graphed.BucketedTrainStep) — frames past it come back as zeros.
+    ``algo``: "simt" = the CUDA-core kernel (csrc/logmel.cu), "tc" = the tensor-core kernel (csrc/logmel_tc.cu; banded
+    filterbanks only; the one that serves ``valid_samples``).  Default (None): the FASTER one as measured on B200 —
+    the CUDA-core kernel (54 us vs 72 us at B = 16 x 30 s inside the training step: the tensor-core kernel's epilogue,
+    not its GEMMs, bounds it — DESIGN.md §4); "tc" when ``valid_samples`` is given.
     """
+    if algo is None:
+        algo = "tc" if valid_samples is not None else "simt"
     _require_cuda(audio, "audio")
     if audio.dim() != 2:
         raise L.AgaError("audio must be (B, N)")
@@ -175,14 +167,12 @@ def log_mel_spectrogram(audio: torch.Tensor, ilens: Optional[torch.Tensor] = Non
         n_mels = filters.shape[0]
     if filters.shape != (n_mels, N_FREQ):
         raise L.AgaError(f"filters must be ({n_mels}, {N_FREQ})")
-    lib = L.lib()
-    kind, packed = _packed_filters(filters)
-    if algo == "simt" and kind == "tc":
-        kind, packed = "simt", _packed_filters_simt(filters)
-    elif algo == "tc" and kind != "tc":
-        raise L.AgaError("the tensor-core frontend needs a banded filterbank")
-    if valid_samples is not None and kind != "tc":
+    if algo not in ("tc", "simt"):
+        raise L.AgaError("algo must be 'tc', 'simt' or None")
+    if valid_samples is not None and algo != "tc":
         raise L.AgaError("valid_samples is served by the tensor-core frontend (banded filterbanks) only")
+    kind = algo
+    packed = _packed_filters(filters, algo)
     F = N // HOP_LENGTH
     if valid_samples is not None:
         valid_samples = valid_samples.to(device=audio.device, dtype=torch.int32).reshape(())

@@ -151,11 +151,14 @@ class MultiHeadAttention(nn.Module):
         self.impl = "auto"
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
-                kv_cache: Optional[dict] = None, residual: Optional[Tensor] = None):
+                kv_cache: Optional[dict] = None, residual: Optional[Tensor] = None, kv_len: Optional[Tensor] = None):
         """``residual``: when given, the first return value is ``residual + out`` (the block's `x = x + attn(...)`, with
-        the add folded into the output projection's GEMM)."""
+        the add folded into the output projection's GEMM).  ``kv_len`` (device int32 scalar): number of keys that really
+        exist when the key sequence is zero-padded to a static length (graphed.BucketedTrainStep); non-causal only."""
         if kv_cache is None and _native(x) and self._frozen():
-            return self._forward_packed(x, xa, mask, residual)
+            return self._forward_packed(x, xa, mask, residual, kv_len)
+        if kv_len is not None:
+            raise ops.L.AgaError("kv_len needs the fused CUDA path (frozen projections, CUDA tensors)")
         q = self.query(x)
         if kv_cache is None or xa is None or self.key not in kv_cache:
             src = x if xa is None else xa
@@ -186,20 +189,22 @@ class MultiHeadAttention(nn.Module):
             self.__dict__.setdefault("_packed_cache", {})[with_q] = c
         return c[1], c[2]
 
-    def _forward_packed(self, x: Tensor, xa: Optional[Tensor], mask: Optional[Tensor], residual: Optional[Tensor] = None):
+    def _forward_packed(self, x: Tensor, xa: Optional[Tensor], mask: Optional[Tensor], residual: Optional[Tensor] = None,
+                        kv_len: Optional[Tensor] = None):
         kind, cols = self.export if self.export is not None else (None, None)
         if xa is None:
             w, b = self._packed_weights(x.dtype, True)
             qkv = F.linear(x, w, b)
             causal = mask is not None
             out, _lse, second = ops.qkv_attention_packed(qkv, self.n_head, causal=causal, export=kind, export_cols=cols,
-                                                         head_sel=self.head_sel, impl=self.impl)
+                                                         head_sel=self.head_sel, impl=self.impl,
+                                                         kv_len=None if causal else kv_len)
         else:
             w, b = self._packed_weights(x.dtype, False)
             q = self.query(x)
             kv = F.linear(xa.to(x.dtype), w, b)
             out, _lse, second = ops.qkv_attention_packed(kv, self.n_head, q=q, causal=False, export=kind, export_cols=cols,
-                                                         head_sel=self.head_sel, impl=self.impl)
+                                                         head_sel=self.head_sel, impl=self.impl, kv_len=kv_len)
         return (self.out(out) if residual is None else linear_plus_residual(self.out, out, residual)), second
 
     def step(self, x: Tensor, past_k: Optional[Tensor] = None, past_v: Optional[Tensor] = None,
@@ -266,14 +271,15 @@ class ResidualAttentionBlock(nn.Module):
             self.adapter_mlp_ln = LayerNorm(n_state)
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
-                kv_cache: Optional[dict] = None):
+                kv_cache: Optional[dict] = None, kv_len: Optional[Tensor] = None, xa_len: Optional[Tensor] = None):
+        """``kv_len`` / ``xa_len``: true lengths of x / xa when they are zero-padded to static shapes (device scalars)."""
         y, x = self.attn_ln.with_residual(x)
-        x, second = self.attn(y, mask=mask, kv_cache=kv_cache, residual=x)  # x + attn(...)
+        x, second = self.attn(y, mask=mask, kv_cache=kv_cache, residual=x, kv_len=kv_len)  # x + attn(...)
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)  # post-LN replaces x (:234-236)
         if self.cross_attn is not None:
             y, x = self.cross_attn_ln.with_residual(x)
-            x = self.cross_attn(y, xa, kv_cache=kv_cache, residual=x)[0]
+            x = self.cross_attn(y, xa, kv_cache=kv_cache, residual=x, kv_len=xa_len)[0]
         y, x = self.mlp_ln.with_residual(x)
         x = self._mlp_residual(y, x)  # x + mlp(...)
         if self.adapter_flag:
@@ -350,7 +356,7 @@ class AudioEncoder(nn.Module):
             self.__dict__["_stem_cache"] = (sig, ws)
         return ws
 
-    def stem(self, x: Tensor) -> Tensor:
+    def stem(self, x: Tensor, valid_frames: Optional[Tensor] = None) -> Tensor:
         """gelu(conv2(gelu(conv1(x)))).permute(0, 2, 1) (whisper/model.py:277-279): (B, n_mels, T) -> (B, T', D).
 
         On a CUDA device both convolutions run as ONE cuBLAS GEMM each on token-major activations (k=3 windows are
@@ -367,6 +373,10 @@ class AudioEncoder(nn.Module):
             h = F.gelu(F.linear(cols, w1, b1))                                   # (B, T, D)
             T2 = (T - 1) // 2 + 1
             hp = F.pad(h, (0, 0, 1, 1))                                          # zero rows at t = -1 and t = T
+            if valid_frames is not None:
+                # the batch is zero-padded past `valid_frames` mel frames: conv2's window of the last real output reads
+                # conv1-output frame `valid_frames`, which the reference's own zero padding supplies as 0
+                hp.index_fill_(1, (valid_frames.to(torch.int64) + 1).reshape(1), 0.0)
             # window t = rows 2t, 2t+1, 2t+2 of hp = 3 D CONTIGUOUS elements: one strided copy of overlapping windows
             # (a cat of three row-strided slices ran at a sixth of the copy bandwidth); columns (k, c)
             D = hp.shape[2]

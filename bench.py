@@ -368,6 +368,7 @@ def main():
     n_mels = model.encoder.n_mels
     with torch.no_grad():
         mel_ms = graph_time_ms(lambda: ops.log_mel_spectrogram(resident[0], n_mels=n_mels))
+        mel_tc_ms = graph_time_ms(lambda: ops.log_mel_spectrogram(resident[0], n_mels=n_mels, algo="tc"))
     mel_bytes = args.batch * (N_SAMPLES * 4 + n_mels * (N_SAMPLES // 160) * 4)
 
     if args.no_graph:
@@ -437,6 +438,11 @@ def main():
                          "GB/s": mel_bytes / mel_ms / 1e6, "frac_of_hbm_peak": mel_bytes / mel_ms / 1e6 / hbm_peak,
                          "bound": "fp32 issue (400-point DFT on CUDA cores), not HBM: see DESIGN.md",
                          "timed_in": "10 calls captured in one CUDA graph"}
+    summary["logmel_tc"] = {"us_per_call": mel_tc_ms * 1e3, "GB/s": mel_bytes / mel_tc_ms / 1e6,
+                            "frac_of_hbm_peak": mel_bytes / mel_tc_ms / 1e6 / hbm_peak,
+                            "what": "the tensor-core frontend (csrc/logmel_tc.cu: fp16 split-precision DFT GEMMs on tcgen05), not "
+                                    "the default: its epilogue (mel projection out of single-buffered TMEM accumulators) bounds it",
+                            "timed_in": "10 calls captured in one CUDA graph"}
 
     gpu_eager = None
     if world == 1 and not args.no_gpu_eager:

@@ -20,8 +20,9 @@ sys.path.insert(0, _HERE)
 import aga_oracle as O  # noqa: E402
 
 
-def log_mel_spectrogram(audio, ilens=None, n_mels=80, filters=None):
+def log_mel_spectrogram(audio, ilens=None, n_mels=80, filters=None, valid_samples=None, algo=None):
     """espnet2/asr/encoder/whisper_encoder.py:105-135, verbatim sequence of torch ops."""
+    assert valid_samples is None, "the reference has no static-shape padding"
     window = torch.hann_window(400).to(audio.device)
     stft = torch.stft(audio, 400, 160, window=window, return_complex=True)
     magnitudes = stft[..., :-1].abs() ** 2
@@ -34,7 +35,7 @@ def log_mel_spectrogram(audio, ilens=None, n_mels=80, filters=None):
     return (log_spec + 4.0) / 4.0, olens
 
 
-def qkv_attention(q, k, v, n_head, causal=False, export=None, export_cols=None, head_sel=None, impl="auto"):
+def qkv_attention(q, k, v, n_head, causal=False, export=None, export_cols=None, head_sel=None, impl="auto", kv_len=None):
     """whisper/whisper/model.py:93-109: materialised scores, fp32 softmax, always returns the full qk."""
     n_batch, n_ctx, n_state = q.shape
     scale = (n_state // n_head) ** -0.25
@@ -56,7 +57,7 @@ def qkv_attention(q, k, v, n_head, causal=False, export=None, export_cols=None, 
     return out, None, second
 
 
-def qkv_attention_packed(x, n_head, q=None, causal=False, export=None, export_cols=None, head_sel=None, impl="auto"):
+def qkv_attention_packed(x, n_head, q=None, causal=False, export=None, export_cols=None, head_sel=None, impl="auto", kv_len=None):
     """The same attention on a packed [q|k|v] (or [k|v] + q) projection: slices, then the reference op sequence."""
     D = n_head * 64
     if q is None:

@@ -170,3 +170,32 @@ def test_tc_causal_export_backward_vs_oracle(A, B, H, T, cols, sel):
         np.testing.assert_allclose(got.float().cpu().numpy(), ref, rtol=2e-2, atol=2e-2 * scale, err_msg=name)
         np.testing.assert_allclose(got.float().cpu().numpy(), alt.float().cpu().numpy(), rtol=2e-2, atol=2e-2 * scale,
                                    err_msg=name + " vs simt")
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk_true,Tk_pad", [(2, 3, 300, 700, 1000), (2, 2, 64, 900, 1500), (1, 2, 128, 129, 512),
+                                                  (2, 2, 1000, 650, 1000), (1, 1, 64, 64, 1500)])
+def test_tc_kv_len_equals_unpadded(A, B, H, Tq, Tk_true, Tk_pad):
+    """Static launch shape for a shorter batch (graphed.BucketedTrainStep): K / V zero-padded... no, GARBAGE-padded to Tk_pad
+    with the true key count as a DEVICE scalar.  Forward output / lse and dQ equal the unpadded call, dK / dV equal it on
+    the real keys and are exactly zero on the padded ones (encoder self attention, decoder cross attention incl. the
+    one-query-tile kernel, a partial last key tile, a single key tile)."""
+    q, k, v = _mk(B, Tq, Tk_true, H, 1.0, seed=Tq + Tk_true)
+    g = torch.Generator().manual_seed(2)
+    kp = torch.randn(B, Tk_pad, H * 64, generator=g).bfloat16()
+    vp = torch.randn(B, Tk_pad, H * 64, generator=g).bfloat16()
+    kp[:, :Tk_true], vp[:, :Tk_true] = k, v
+    do = torch.randn(B, Tq, H * 64, generator=g).bfloat16().cuda()
+    kv = torch.tensor(Tk_true, dtype=torch.int32).cuda()
+    res = {}
+    for name, (kk, vv, kw) in {"ref": (k, v, {}), "pad": (kp, vp, {"kv_len": kv})}.items():
+        qd, kd, vd = (x.cuda().requires_grad_() for x in (q, kk, vv))
+        out, lse, _ = A.qkv_attention(qd, kd, vd, H, impl="tcgen05", **kw)
+        out.backward(do)
+        res[name] = (out.detach(), lse, qd.grad, kd.grad, vd.grad)
+    o_r, l_r, dq_r, dk_r, dv_r = res["ref"]
+    o_p, l_p, dq_p, dk_p, dv_p = res["pad"]
+    assert torch.equal(o_p, o_r) and torch.equal(l_p, l_r)
+    for a, b2 in ((dq_p, dq_r), (dk_p[:, :Tk_true], dk_r), (dv_p[:, :Tk_true], dv_r)):
+        scale = float(b2.float().abs().max())
+        assert float((a.float() - b2.float()).abs().max()) <= 1e-2 * scale  # fp32 atomics order only
+    assert not dk_p[:, Tk_true:].any() and not dv_p[:, Tk_true:].any()
