@@ -33,6 +33,7 @@ class AttnParams(C.Structure):
         ("o_stride_b", C.c_int64), ("o_stride_t", C.c_int64),
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
         ("lse", C.c_void_p), ("head_sel", C.c_void_p), ("export_buf", C.c_void_p), ("kv_len", C.c_void_p),
+        ("guided_pattern", C.c_void_p), ("guided_part", C.c_void_p), ("guided_early", C.c_int32),
     ]
 
 
@@ -40,7 +41,7 @@ class AttnBwdParams(C.Structure):
     _fields_ = [
         ("fwd", AttnParams),
         ("dout", C.c_void_p), ("d_export", C.c_void_p),
-        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("d_guided_part", C.c_void_p),
     ]
 
 

@@ -25,6 +25,8 @@ int validate(const aga_attn_params* p) {
   if (p->dtype != AGA_F32 && p->dtype != AGA_BF16) return AGA_ERR_INVALID_ARGUMENT;
   if (p->causal && p->Tq != p->Tk) return AGA_ERR_INVALID_ARGUMENT;
   if (p->kv_len && (p->causal || p->export_kind != AGA_EXPORT_NONE)) return AGA_ERR_UNSUPPORTED;
+  if ((p->guided_pattern != nullptr) != (p->guided_part != nullptr)) return AGA_ERR_INVALID_ARGUMENT;
+  if (p->guided_part && (!p->causal || p->Tq > 128 || p->Tq < 3)) return AGA_ERR_UNSUPPORTED;
   if (p->B > 65535 || p->H > 65535) return AGA_ERR_UNSUPPORTED;
   if (p->export_kind != AGA_EXPORT_NONE) {
     if (p->export_kind != AGA_EXPORT_LOGITS && p->export_kind != AGA_EXPORT_PROBS) return AGA_ERR_INVALID_ARGUMENT;
@@ -64,7 +66,7 @@ extern "C" int aga_attn_fwd_workspace_bytes(const aga_attn_params* p, size_t* by
   int st = validate(p);
   if (st != AGA_OK) return st;
   if (!bytes) return AGA_ERR_INVALID_ARGUMENT;
-  if ((p->impl == AGA_ATTN_TCGEN05 || p->kv_len) && !use_tc(*p)) return AGA_ERR_UNSUPPORTED;
+  if ((p->impl == AGA_ATTN_TCGEN05 || p->kv_len || p->guided_part) && !use_tc(*p)) return AGA_ERR_UNSUPPORTED;
   *bytes = use_tc(*p) ? attn_tc_fwd_workspace(*p) : 0;
   return AGA_OK;
 }
@@ -95,7 +97,8 @@ extern "C" int aga_attn_bwd_workspace_bytes(const aga_attn_bwd_params* p, size_t
   const void* ptrs[] = {p->dout, p->dq, p->dk, p->dv};
   for (const void* x : ptrs)
     if (reinterpret_cast<uintptr_t>(x) & 15) return AGA_ERR_UNSUPPORTED;
-  if ((p->fwd.impl == AGA_ATTN_TCGEN05 || p->fwd.kv_len) && !use_tc_bwd(p->fwd)) return AGA_ERR_UNSUPPORTED;
+  if ((p->fwd.impl == AGA_ATTN_TCGEN05 || p->fwd.kv_len || p->d_guided_part) && !use_tc_bwd(p->fwd)) return AGA_ERR_UNSUPPORTED;
+  if (p->d_guided_part && !p->fwd.guided_pattern) return AGA_ERR_INVALID_ARGUMENT;
   *bytes = use_tc_bwd(p->fwd) ? attn_tc_bwd_workspace(p->fwd) : attn_simt_bwd_workspace(p->fwd);
   return AGA_OK;
 }

@@ -117,7 +117,27 @@ struct FwdArgs {
   float* export_buf;           // (B, H, Tq, hi - lo) fp32 or nullptr
   const uint8_t* head_sel;     // (H) or nullptr: heads whose columns are exported
   const int32_t* kv_len;       // nullptr, or device scalar: only keys [0, min(*kv_len, Tk)) exist (zero-padded static shapes)
+  // guided-loss reduction in the epilogue (aga_attn_params::guided_*): causal, one query tile
+  const float* g_pattern;      // (B, Tq, 2) or nullptr
+  float* g_part;               // (B, H, 4, 2)
+  int g_early;
 };
+
+// One row's term of the guided loss (espnet_model.py:496-509) from the scaled logits of key columns 1, 2 (-inf where the
+// causal mask hides them) and the row's target pattern: returns r and the two residuals (S~ - c) the gradient needs
+// (zero where the reference zeroes the entry: hidden by the mask, or a pad row of a late layer).
+__device__ __forceinline__ float guided_row(float s1, float s2, float2 pt, int early, float& res1, float& res2) {
+  const bool h1 = isinf(s1), h2 = isinf(s2);
+  float a1 = h1 ? 0.f : s1, a2 = h2 ? 0.f : s2;   // A[isinf(A)] = 0 (:497)
+  float t1 = pt.x, t2 = pt.y;
+  bool z = false;
+  if (early) { t1 = 0.f; t2 = 0.f; }             // early layers: all-zero target in columns 1:3, pad rows are kept (:479-481)
+  else if (isinf(pt.x) || isinf(pt.y)) { a1 = a2 = t1 = t2 = 0.f; z = true; }  // pad row: A and P zeroed (:496, :498)
+  const float e1 = a1 - t1, e2 = a2 - t2;
+  res1 = (h1 || z) ? 0.f : e1;                   // a zeroed entry is a constant: no gradient
+  res2 = (h2 || z) ? 0.f : e2;
+  return e1 * e1 + e2 * e2;
+}
 
 // effective key count of a launch whose key length is padded to a static Tk (aga_attn_params::kv_len)
 __device__ __forceinline__ int effective_tk(const int32_t* kv_len, int Tk) {
@@ -616,6 +636,20 @@ attn_fwd_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             if (key >= a.export_lo && key < a.export_hi) erow[key] = __uint_as_float(sr[c][i]) * 0.125f;
           }
       }
+      if (a.g_part != nullptr && kbase == 0) {
+        // guided loss, reduced here: this warp holds key columns 1, 2 of its 32 query rows
+        float r = 0.f, u1, u2;
+        if (row < a.Tq) {
+          const float2 pt = *reinterpret_cast<const float2*>(a.g_pattern + (int64_t(b) * a.Tq + row) * 2);
+          r = guided_row(__uint_as_float(sr[0][1]) * 0.125f, __uint_as_float(sr[0][2]) * 0.125f, pt, a.g_early, u1, u2);
+        }
+        const float rs = warp_sum(r), rc = warp_sum(r != 0.f ? 1.f : 0.f);
+        if (lane == 0) {
+          float* dst = a.g_part + ((int64_t(b) * a.H + h) * 4 + quad) * 2;
+          dst[0] = rs;
+          dst[1] = rc;
+        }
+      }
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -760,7 +794,7 @@ int attn_tc_fwd(const aga_attn_params& p, void*, cudaStream_t s) {
   const bool exporting = p.export_kind == AGA_EXPORT_LOGITS && p.export_buf != nullptr;
   FwdArgs a{p.B, p.H, p.Tq, p.Tk, p.o_stride_b, p.o_stride_t, static_cast<__nv_bfloat16*>(p.out), p.lse, p.causal,
             exporting ? p.export_lo : 0, exporting ? p.export_hi : 0, exporting ? p.export_buf : nullptr,
-            exporting ? p.head_sel : nullptr, p.kv_len};
+            exporting ? p.head_sel : nullptr, p.kv_len, p.guided_pattern, p.guided_part, p.guided_early};
 #ifdef AGA_FWD_TWO_TILES  // one CTA per SM, two query tiles sharing each K/V tile
   constexpr int NT = 2;
 #else                     // two independent single-tile CTAs per SM (measured faster: see DESIGN.md)
@@ -843,6 +877,12 @@ struct BwdArgs {
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
   const int32_t* kv_len;  // nullptr, or device scalar: keys at or past it do not exist (their P is forced to 0; key tiles past it are skipped)
+  // decoder self attention with more than one query tile (Tq = Tk in (128, 448], whisper/model.py:322): causal mask, and
+  // the gradient of the exported logit columns [lo, hi) (the guided loss, espnet_model.py:463-530) added to dS
+  int causal;
+  int export_lo, export_hi;
+  const float* d_export;      // (B, H, Tq, hi - lo) fp32 or nullptr
+  const uint8_t* head_sel;    // (H) or nullptr
 };
 
 // MN-major operand spanning two 64-element panels along M (dS^T rows as the A of dQ): LBO = panel stride
@@ -1120,11 +1160,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int it = 0; it < my_items; ++it) {
       // keys past the effective length (kv_len inside a static Tk) keep P^T = 0: this lane's key is masked for the item
       uint32_t keep = 0xffffffffu;
-      if (a.kv_len) {
-        int kt_i, h_i, b_i;
-        decode(it, kt_i, h_i, b_i);
-        keep = (kt_i * kBlockN + r < Tk) ? 0xffffffffu : 0u;
-      }
+      int kt_i = 0, h_i = 0, b_i = 0;
+      if (a.kv_len || a.causal) decode(it, kt_i, h_i, b_i);
+      if (a.kv_len) keep = (kt_i * kBlockN + r < Tk) ? 0xffffffffu : 0u;
+      const int key_g = kt_i * kBlockN + r;  // this lane's key (causal / export paths)
+      // gradient of the exported logits of this key (one of the columns [lo, hi)): row `query` of (B, H, Tq, W)
+      const float* gcol = (a.d_export && key_g >= a.export_lo && key_g < a.export_hi && (a.head_sel == nullptr || a.head_sel[h_i] != 0))
+                              ? a.d_export + (int64_t(b_i) * a.H + h_i) * a.Tq * (a.export_hi - a.export_lo) + (key_g - a.export_lo)
+                              : nullptr;
       for (int i = 0; i < n_qt; ++i, ++c) {
         const uint32_t par = c & 1;
         TL(20);
@@ -1178,6 +1221,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
           for (int e = 0; e < 16; ++e) pk[e] &= keep;
         }
+        // causal (Tq = Tk): query q sees key k iff k <= q.  Query tiles above the diagonal (i < kt) are walked with P = 0
+        // (the decoder's maps are at most 448 x 448: 6 wasted tile pairs of 16), the diagonal tile is masked per element.
+        const int q0 = i * kBlockM + g * 64 + sub * 32;  // first query of this warp's 32-column slice
+        if (a.causal && q0 < key_g) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const uint32_t lo_ok = (q0 + 2 * e >= key_g) ? 0x0000ffffu : 0u, hi_ok = (q0 + 2 * e + 1 >= key_g) ? 0xffff0000u : 0u;
+            pk[e] &= lo_ok | hi_ok;
+          }
+        }
         tmem_st16(t_s, pk);  // 32 queries as bf16 pairs over the first 16 of this slice's S^T columns
         tmem_wait_st();
         tc_fence_before();
@@ -1208,8 +1261,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                                          make_float2(-D.x, -D.y));
             const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(dv[4 * e4 + 2]), __uint_as_float(dv[4 * e4 + 3])),
                                          make_float2(-D.z, -D.w));
-            const float2 d0 = __fmul2_rn(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), a0);
-            const float2 d1 = __fmul2_rn(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), a1);
+            float2 d0 = __fmul2_rn(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), a0);
+            float2 d1 = __fmul2_rn(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), a1);
+            if (gcol != nullptr) {  // (two lanes of key tile 0 only) the exported columns' gradient adds to dS on visible entries
+              const int W = a.export_hi - a.export_lo;
+              const int q = q0 + 4 * e4;
+              const int qmin = a.causal ? key_g : 0;
+              if (q >= qmin && q < a.Tq) d0.x += gcol[int64_t(q) * W];
+              if (q + 1 >= qmin && q + 1 < a.Tq) d0.y += gcol[int64_t(q + 1) * W];
+              if (q + 2 >= qmin && q + 2 < a.Tq) d1.x += gcol[int64_t(q + 2) * W];
+              if (q + 3 >= qmin && q + 3 < a.Tq) d1.y += gcol[int64_t(q + 3) * W];
+            }
             __nv_bfloat162 h0 = __floats2bfloat162_rn(d0.x, d0.y), h1 = __floats2bfloat162_rn(d1.x, d1.y);
             dd[2 * e4] = *reinterpret_cast<uint32_t*>(&h0);
             dd[2 * e4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
@@ -1436,6 +1498,9 @@ struct QrArgs {
   const float* stats;  // (B, H, 1, 2, 128): lse * log2(e) | delta, zero past Tq
   float* dq_accum;     // (B, H, 1, 2, 128, 32) fp32, zero-initialised, chunk-swizzled like the persistent kernel's
   const int32_t* kv_len;  // as BwdArgs::kv_len
+  const float* g_pattern; // guided loss fused into the forward epilogue: (B, Tq, 2) pattern,
+  const float* g_dpart;   //   (B, H, 4, 2) gradient of the per-row-group partial sums, or nullptr
+  int g_early;
 };
 
 __global__ void __launch_bounds__(kQrThreads, 1)
@@ -1646,6 +1711,7 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     for (int jj = 0; jj < n_my; ++jj) {
       const uint32_t par = jj & 1;
       uint32_t pk[16], dd[16];
+      float gg1 = 0.f, gg2 = 0.f;  // fused guided loss: gradient on the scaled logits of keys 1, 2 of this row
       TL(20);
       mbar_wait(&sb->s_full, par);
       TL(21);
@@ -1666,6 +1732,15 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             for (int i = 0; i < 32; ++i)
               if (i >= vis) sv[i] = 0xff800000u;
           }
+        }
+        if (a.g_dpart != nullptr && kt0 + jj == 0 && cs == 0 && row < a.Tq) {
+          // d loss / d S~[row, 1..2] of the fused guided loss: 2 (S~ - c) * d(sum of the row's group)
+          const float2 pt = *reinterpret_cast<const float2*>(a.g_pattern + (int64_t(b) * a.Tq + row) * 2);
+          float u1, u2;
+          guided_row(__uint_as_float(sv[1]) * 0.125f, __uint_as_float(sv[2]) * 0.125f, pt, a.g_early, u1, u2);
+          const float gsum = 2.0f * a.g_dpart[((int64_t(b) * a.H + h) * 4 + (row >> 5)) * 2];
+          gg1 = gsum * u1;
+          gg2 = gsum * u2;
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -1694,6 +1769,8 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             if (key >= a.export_lo && key < lim) d.x += grow[key];
             if (key + 1 >= a.export_lo && key + 1 < lim) d.y += grow[key + 1];
           }
+          if (i == 0) d.y += gg1;  // key 1  (gg1 / gg2 are zero unless this warp holds keys 0..31 of key tile 0)
+          if (i == 1) d.x += gg2;  // key 2
           __nv_bfloat162 hb = __floats2bfloat162_rn(d.x, d.y);
           dd[i] = *reinterpret_cast<uint32_t*>(&hb);
         }
@@ -1787,7 +1864,6 @@ attn_bwd_tc_qres_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 // decoder self attention of a training step); longer causal sequences take the CUDA-core path
 bool attn_tc_bwd_supported(const aga_attn_params& p) {
   if (!attn_tc_supported(p)) return false;
-  if ((p.causal || p.export_kind != AGA_EXPORT_NONE) && p.Tq > kBlockM) return false;
 #ifdef AGA_BWD_NO_QRES
   if (p.causal || p.export_kind != AGA_EXPORT_NONE) return false;
 #endif
@@ -1834,7 +1910,8 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
     const int n_chunks = (n_kt + per - 1) / per;
     const bool dexp = p.export_kind == AGA_EXPORT_LOGITS && bp.d_export != nullptr;
     QrArgs qa{p.B, p.H, p.Tq, p.Tk, per, p.causal, dexp ? p.export_lo : 0, dexp ? p.export_hi : 0,
-              dexp ? bp.d_export : nullptr, dexp ? p.head_sel : nullptr, stats, dq_acc, p.kv_len};
+              dexp ? bp.d_export : nullptr, dexp ? p.head_sel : nullptr, stats, dq_acc, p.kv_len,
+              bp.d_guided_part ? p.guided_pattern : nullptr, bp.d_guided_part, p.guided_early};
     CUtensorMap mdk, mdv;  // 32-row boxes: one store per drain warp
     if ((st = make_map(&mdk, bp.dk, p.B, p.H, p.Tk, p.k_stride_b, p.k_stride_t, 32)) != AGA_OK) return st;
     if ((st = make_map(&mdv, bp.dv, p.B, p.H, p.Tk, p.v_stride_b, p.v_stride_t, 32)) != AGA_OK) return st;
@@ -1845,8 +1922,10 @@ int attn_tc_bwd(const aga_attn_bwd_params& bp, void* ws, cudaStream_t s) {
 #endif
   {
   const int n_items = p.B * p.H * n_kt;
+  const bool dexp_p = p.export_kind == AGA_EXPORT_LOGITS && bp.d_export != nullptr;
   BwdArgs a{p.B, p.H, p.Tq, p.Tk, n_items, p.k_stride_b, p.k_stride_t, p.v_stride_b, p.v_stride_t, stats, dq_acc,
-            static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv), p.kv_len};
+            static_cast<__nv_bfloat16*>(bp.dk), static_cast<__nv_bfloat16*>(bp.dv), p.kv_len, p.causal,
+            dexp_p ? p.export_lo : 0, dexp_p ? p.export_hi : 0, dexp_p ? bp.d_export : nullptr, dexp_p ? p.head_sel : nullptr};
   AGA_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBwdSmemBytes)));
   const unsigned grid = unsigned(std::min(n_items, n_sm));  // persistent: one CTA per SM walks the items
   CUtensorMap mdk, mdv;

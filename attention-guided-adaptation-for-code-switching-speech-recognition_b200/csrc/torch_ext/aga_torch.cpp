@@ -60,7 +60,8 @@ Tensor logmel(const Tensor& audio, const Tensor& packed, int64_t n_mels, const o
 // ------------------------------------------------------------------------------------------------ attention
 void fill(aga_attn_params& p, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out, const Tensor& lse,
           int64_t n_head, bool causal, int64_t kind, int64_t lo, int64_t hi, const optional<Tensor>& head_sel,
-          const void* export_buf, int64_t impl, const optional<Tensor>& kv_len) {
+          const void* export_buf, int64_t impl, const optional<Tensor>& kv_len, const optional<Tensor>& guided_pattern = c10::nullopt,
+          void* guided_part = nullptr, bool guided_early = false) {
   p.dtype = dtype_of(q);
   p.impl = int(impl);
   p.B = int(q.size(0));
@@ -80,11 +81,15 @@ void fill(aga_attn_params& p, const Tensor& q, const Tensor& k, const Tensor& v,
   p.head_sel = static_cast<const uint8_t*>(ptr(head_sel));
   p.export_buf = static_cast<float*>(const_cast<void*>(export_buf));
   p.kv_len = static_cast<const int32_t*>(ptr(kv_len));
+  p.guided_pattern = static_cast<const float*>(ptr(guided_pattern));
+  p.guided_part = static_cast<float*>(guided_part);
+  p.guided_early = guided_early ? 1 : 0;
 }
 
-std::tuple<Tensor, Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, int64_t n_head, bool causal,
-                                            int64_t kind, int64_t lo, int64_t hi, const optional<Tensor>& head_sel, int64_t impl,
-                                            const optional<Tensor>& kv_len) {
+std::tuple<Tensor, Tensor, Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, int64_t n_head, bool causal,
+                                                    int64_t kind, int64_t lo, int64_t hi, const optional<Tensor>& head_sel,
+                                                    int64_t impl, const optional<Tensor>& kv_len,
+                                                    const optional<Tensor>& guided_pattern, bool guided_early) {
   need_cuda(q, "q");
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.dim() == 3 && q.size(2) == n_head * 64, "head dim must be 64 (every Whisper size)");
@@ -97,26 +102,35 @@ std::tuple<Tensor, Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, co
     auto o = q.options().dtype(at::kFloat);
     exp = head_sel.has_value() ? at::zeros({B, n_head, Tq, hi - lo}, o) : at::empty({B, n_head, Tq, hi - lo}, o);
   }
+  const bool guided = guided_pattern.has_value() && guided_pattern->defined();
+  // per-(b, h, 32-row group) partial sums of the guided loss, written (not accumulated) by the attention epilogue
+  Tensor part = guided ? at::zeros({B, n_head, 4, 2}, q.options().dtype(at::kFloat)) : at::empty({0}, q.options().dtype(at::kFloat));
   aga_attn_params p{};
-  fill(p, q, k, v, out, lse, n_head, causal, kind, lo, hi, head_sel, exp.defined() ? exp.data_ptr() : nullptr, impl, kv_len);
+  fill(p, q, k, v, out, lse, n_head, causal, kind, lo, hi, head_sel, exp.defined() ? exp.data_ptr() : nullptr, impl, kv_len,
+       guided_pattern, guided ? part.data_ptr() : nullptr, guided_early);
   size_t nbytes = 0;
   check(aga_attn_fwd_workspace_bytes(&p, &nbytes), "aga_attn_fwd_workspace_bytes");
   Tensor ws = scratch(nbytes, q);
   check(aga_attn_fwd(&p, ws.data_ptr(), nbytes < 16 ? 16 : nbytes, stream_of(q)), "aga_attn_fwd");
-  return {out, lse, exp.defined() ? exp : at::empty({0}, q.options().dtype(at::kFloat))};
+  return {out, lse, exp.defined() ? exp : at::empty({0}, q.options().dtype(at::kFloat)), part};
 }
 
 void attn_bwd(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out, const Tensor& lse, const Tensor& dout,
               const optional<Tensor>& dexport, const optional<Tensor>& probs, Tensor dq, Tensor dk, Tensor dv, int64_t n_head,
               bool causal, int64_t kind, int64_t lo, int64_t hi, const optional<Tensor>& head_sel, int64_t impl,
-              const optional<Tensor>& kv_len) {
+              const optional<Tensor>& kv_len, const optional<Tensor>& guided_pattern, const optional<Tensor>& d_part,
+              bool guided_early) {
   need_cuda(q, "q");
   c10::cuda::CUDAGuard guard(q.device());
   aga_attn_bwd_params bp{};
   const bool has_de = dexport.has_value() && dexport->defined();
   const void* ebuf = probs.has_value() && probs->defined() && probs->numel() ? probs->data_ptr() : nullptr;
   if (has_de && kind == AGA_EXPORT_LOGITS) ebuf = dexport->data_ptr();  // logits export: only the gradient is needed (non-null marker)
-  fill(bp.fwd, q, k, v, out, lse, n_head, causal, has_de ? kind : int64_t(AGA_EXPORT_NONE), lo, hi, head_sel, ebuf, impl, kv_len);
+  const bool guided = guided_pattern.has_value() && guided_pattern->defined() && d_part.has_value() && d_part->defined();
+  // (guided_part itself is not read by the backward; any non-null pointer satisfies the "both or none" check)
+  fill(bp.fwd, q, k, v, out, lse, n_head, causal, has_de ? kind : int64_t(AGA_EXPORT_NONE), lo, hi, head_sel, ebuf, impl, kv_len,
+       guided ? guided_pattern : c10::nullopt, guided ? d_part->data_ptr() : nullptr, guided_early);
+  bp.d_guided_part = guided ? d_part->data_ptr<float>() : nullptr;
   bp.dout = dout.data_ptr();
   bp.d_export = has_de ? dexport->data_ptr<float>() : nullptr;
   bp.dq = dq.data_ptr(); bp.dk = dk.data_ptr(); bp.dv = dv.data_ptr();
@@ -282,10 +296,10 @@ int64_t launch_count() { return int64_t(aga_launch_count()); }
 TORCH_LIBRARY(aga, m) {
   m.def("logmel(Tensor audio, Tensor packed, int n_mels, Tensor? valid, bool tensor_core) -> Tensor");
   m.def("attn_fwd(Tensor q, Tensor k, Tensor v, int n_head, bool causal, int kind, int lo, int hi, Tensor? head_sel, int impl, "
-        "Tensor? kv_len) -> (Tensor, Tensor, Tensor)");
+        "Tensor? kv_len, Tensor? guided_pattern, bool guided_early) -> (Tensor, Tensor, Tensor, Tensor)");
   m.def("attn_bwd(Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, Tensor dout, Tensor? dexport, Tensor? probs, Tensor(a!) dq, "
-        "Tensor(b!) dk, Tensor(c!) dv, int n_head, bool causal, int kind, int lo, int hi, Tensor? head_sel, int impl, Tensor? kv_len) "
-        "-> ()");
+        "Tensor(b!) dk, Tensor(c!) dv, int n_head, bool causal, int kind, int lo, int hi, Tensor? head_sel, int impl, Tensor? kv_len, "
+        "Tensor? guided_pattern, Tensor? d_part, bool guided_early) -> ()");
   m.def("layernorm_fwd(Tensor x, Tensor? residual, Tensor gamma, Tensor beta, float eps, bool want_sum) -> (Tensor, Tensor, Tensor, Tensor)");
   m.def("layernorm_bwd(Tensor dy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool need_params, bool need_dxsum, Tensor? dres) "
         "-> (Tensor, Tensor)");

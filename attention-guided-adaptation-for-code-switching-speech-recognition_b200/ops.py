@@ -199,8 +199,6 @@ def _impl_name(q, causal, kind, impl, bwd=False, cols=(0, 0)) -> str:
     profiling tags only."""
     narrow = kind == L.EXPORT_NONE or (kind == L.EXPORT_LOGITS and cols[1] - cols[0] <= 16)
     tc = impl != L.ATTN_SIMT and q.dtype == torch.bfloat16 and narrow
-    if bwd and (causal or kind != L.EXPORT_NONE):
-        tc = tc and q.shape[1] <= 128
     return "tc" if tc else "simt"
 
 
@@ -210,20 +208,22 @@ def _prep(t: torch.Tensor) -> torch.Tensor:
     return t if ok else t.contiguous()
 
 
-def _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl, kv_len=None):
-    """One aga_attn_fwd call on (possibly strided) q (B,Tq,D), k, v (B,Tk,D) -> (out, lse, export_buf or None)."""
+def _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl, kv_len=None, guided=None):
+    """One aga_attn_fwd call on (possibly strided) q (B,Tq,D), k, v (B,Tk,D) -> (out, lse, export_buf or None, part or None)."""
     B, Tq, D = q.shape
     if D != n_head * 64:
         raise L.AgaError("head dim must be 64 (every Whisper size)")
     lo, hi = cols if kind != L.EXPORT_NONE else (0, 0)
     flops = 4.0 * B * n_head * Tq * k.shape[1] * 64 * (0.5 if causal else 1.0)
     tm = _Timed(f"attn_fwd_{_impl_name(q, causal, kind, impl, cols=cols)}_{Tq}x{k.shape[1]}", flops, q.device)
-    out, lse, export_buf = L.torch_ops().attn_fwd(q, k, v, n_head, causal, kind, lo, hi, head_sel, impl, kv_len)
+    g_pat, g_early = guided if guided is not None else (None, False)
+    out, lse, export_buf, part = L.torch_ops().attn_fwd(q, k, v, n_head, causal, kind, lo, hi, head_sel, impl, kv_len, g_pat,
+                                                        bool(g_early))
     tm.done(q.device)
-    return out, lse, (export_buf if kind != L.EXPORT_NONE else None)
+    return out, lse, (export_buf if kind != L.EXPORT_NONE else None), (part if guided is not None else None)
 
 
-def _attn_backward(q, k, v, out, lse, head_sel, probs, cfg, dout, dexport, dq, dk, dv, kv_len=None):
+def _attn_backward(q, k, v, out, lse, head_sel, probs, cfg, dout, dexport, dq, dk, dv, kv_len=None, guided=None, dpart=None):
     """One aga_attn_bwd call; dq / dk / dv are caller-allocated and share the strides of q / k / v."""
     n_head, causal, kind, cols, impl, has_sel = cfg
     if dout is None:
@@ -238,8 +238,10 @@ def _attn_backward(q, k, v, out, lse, head_sel, probs, cfg, dout, dexport, dq, d
     tm = _Timed(f"attn_bwd_{_impl_name(q, causal, kind if dexport is not None else L.EXPORT_NONE, impl, bwd=True, cols=cols)}"
                 f"_{q.shape[1]}x{k.shape[1]}", flops, q.device)
     lo, hi = cols if kind != L.EXPORT_NONE else (0, 0)
+    g_pat, g_early = guided if (guided is not None and dpart is not None) else (None, False)
     L.torch_ops().attn_bwd(q, k, v, out, lse, dout, dexport, probs if probs.numel() else None, dq, dk, dv, n_head, causal, kind,
-                           lo, hi, head_sel if has_sel else None, impl, kv_len)
+                           lo, hi, head_sel if has_sel else None, impl, kv_len, g_pat,
+                           None if g_pat is None else dpart.float().contiguous(), bool(g_early))
     tm.done(q.device)
 
 
@@ -260,7 +262,7 @@ class _AttnFn(torch.autograd.Function):
         k = k.to(q.dtype)
         v = v.to(q.dtype)
         q, k, v = _prep(q), _prep(k), _prep(v)
-        out, lse, export_buf = _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl, kv_len)
+        out, lse, export_buf, _ = _attn_forward(q, k, v, n_head, causal, kind, cols, head_sel, impl, kv_len)
         _save(ctx, (q, k, v), out, lse, head_sel, export_buf, n_head, causal, kind, cols, impl)
         ctx.kv_len = kv_len
         return out, lse, export_buf
@@ -283,7 +285,7 @@ class _AttnPackedFn(torch.autograd.Function):
     one packed gradient, so the projection's backward is a single GEMM with no gradient-accumulation adds."""
 
     @staticmethod
-    def forward(ctx, q, x, n_head, causal, kind, cols, head_sel, impl, kv_len=None):
+    def forward(ctx, q, x, n_head, causal, kind, cols, head_sel, impl, kv_len=None, guided_pattern=None, guided_early=False):
         _require_cuda(x, "packed projection")
         if x.dtype not in _DTYPES:
             raise L.AgaError(f"attention supports fp32 and bf16, got {x.dtype}")
@@ -294,14 +296,16 @@ class _AttnPackedFn(torch.autograd.Function):
             qv, kv, vv = x[..., :D], x[..., D:2 * D], x[..., 2 * D:]
         else:
             qv, kv, vv = _prep(q.to(x.dtype)), x[..., :D], x[..., D:]
-        out, lse, export_buf = _attn_forward(qv, kv, vv, n_head, causal, kind, cols, head_sel, impl, kv_len)
+        guided = None if guided_pattern is None else (guided_pattern, guided_early)
+        out, lse, export_buf, part = _attn_forward(qv, kv, vv, n_head, causal, kind, cols, head_sel, impl, kv_len, guided)
         _save(ctx, (qv if q is not None else torch.empty(0), x), out, lse, head_sel, export_buf, n_head, causal, kind, cols, impl)
         ctx.packed_q = q is None
         ctx.kv_len = kv_len
-        return out, lse, export_buf
+        ctx.guided = guided
+        return out, lse, export_buf, part
 
     @staticmethod
-    def backward(ctx, dout, _dlse, dexport):
+    def backward(ctx, dout, _dlse, dexport, dpart):
         qs, x, out, lse, head_sel, probs = ctx.saved_tensors
         D = ctx.cfg[0] * 64
         dx = torch.empty_like(x) if ctx.kv_len is None else torch.zeros_like(x)  # rows past kv_len are never visited
@@ -312,8 +316,8 @@ class _AttnPackedFn(torch.autograd.Function):
             q, k, v = qs, x[..., :D], x[..., D:]
             dq = torch.empty_strided(q.shape, q.stride(), dtype=q.dtype, device=q.device)
             dk, dv = dx[..., :D], dx[..., D:]
-        _attn_backward(q, k, v, out, lse, head_sel, probs, ctx.cfg, dout, dexport, dq, dk, dv, ctx.kv_len)
-        return (None if ctx.packed_q else dq), dx, None, None, None, None, None, None, None
+        _attn_backward(q, k, v, out, lse, head_sel, probs, ctx.cfg, dout, dexport, dq, dk, dv, ctx.kv_len, ctx.guided, dpart)
+        return (None if ctx.packed_q else dq), dx, None, None, None, None, None, None, None, None, None
 
 
 def qkv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int, causal: bool = False,
@@ -341,9 +345,15 @@ def qkv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int
 
 def qkv_attention_packed(x: torch.Tensor, n_head: int, q: Optional[torch.Tensor] = None, causal: bool = False,
                          export: Optional[str] = None, export_cols: Optional[Tuple[int, int]] = None,
-                         head_sel: Optional[torch.Tensor] = None, impl: str = "auto", kv_len: Optional[torch.Tensor] = None):
+                         head_sel: Optional[torch.Tensor] = None, impl: str = "auto", kv_len: Optional[torch.Tensor] = None,
+                         guided: Optional[Tuple[torch.Tensor, bool]] = None):
     """``qkv_attention`` on a packed projection: x = [q | k | v] (B,T,3D), or x = [k | v] (B,Tk,2D) with ``q`` given.
-    Same results as :func:`qkv_attention` on the three column slices; one packed gradient comes back."""
+    Same results as :func:`qkv_attention` on the three column slices; one packed gradient comes back.
+
+    ``guided = (pattern (B,T,2), early)`` (decoder self attention: causal, bf16, T <= 128): the per-(utterance, head) part
+    of the guided loss (espnet_model.py:496-512) is reduced inside the attention kernel's epilogue; the third return value
+    is then ``GuidedParts`` (B,H,4,2) — per 32-row group [sum_t r_t, #{t: r_t != 0}] — instead of an exported slab, and
+    nothing of size (T, T) or (T, 2) is written."""
     kind = _KINDS[export]
     Tk = x.shape[1]
     if kind != L.EXPORT_NONE and export_cols is None:
@@ -353,7 +363,14 @@ def qkv_attention_packed(x: torch.Tensor, n_head: int, q: Optional[torch.Tensor]
     empty_cols = export_cols if export_cols is not None else (0, 0)
     if kv_len is not None:
         kv_len = kv_len.to(device=x.device, dtype=torch.int32).reshape(())
-    return _AttnPackedFn.apply(q, x, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl], kv_len)
+    if guided is not None:
+        pat = guided[0].to(device=x.device, dtype=torch.float32).contiguous()
+        out, lse, _, part = _AttnPackedFn.apply(q, x, int(n_head), bool(causal), L.EXPORT_NONE, (0, 0), None, _IMPLS[impl], kv_len,
+                                                pat, bool(guided[1]))
+        return out, lse, GuidedParts(part)
+    out, lse, exported, _ = _AttnPackedFn.apply(q, x, int(n_head), bool(causal), kind, tuple(empty_cols), head_sel, _IMPLS[impl],
+                                                kv_len)
+    return out, lse, exported
 
 
 # ------------------------------------------------------------------------------------------------
@@ -749,6 +766,28 @@ class _GuidedLossFn(torch.autograd.Function):
     def backward(ctx, g):
         d = ctx.d_slab
         return (None if d is None else d * g), None, None, None
+
+
+class GuidedParts:
+    """Per-(utterance, head, 32-row group) partial sums of the guided loss as the attention epilogue left them:
+    ``t`` (..., B, H, 4, 2) = [sum_t r_t, #{t: r_t != 0}].  ``stack`` joins the layers; ``guided_loss_from_parts``
+    finishes the loss."""
+
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+
+    @staticmethod
+    def stack(parts):
+        return GuidedParts(torch.stack([p.t for p in parts]))
+
+
+def guided_loss_from_parts(parts: GuidedParts, head_mask: torch.Tensor) -> torch.Tensor:
+    """The tail of calculate_cs_loss (espnet_model.py:509-530) on the fused partial sums (L,B,H,4,2): mean over the
+    non-zero rows (0/0 = NaN as in the reference), selected-head mask, sum over (layer, head), mean over the batch."""
+    t = parts.t
+    m = t[..., 0].sum(-1) / t[..., 1].sum(-1)                      # (L,B,H)
+    masked = head_mask.to(device=t.device, dtype=torch.float32)[:, None, :] * m
+    return masked.sum(dim=(0, 2)).mean()
 
 
 def guided_loss(slab: torch.Tensor, pattern: torch.Tensor, head_mask: torch.Tensor, n_early: int = 2) -> torch.Tensor:

@@ -58,7 +58,11 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch (reference op sequence) leg on the GPU")
     ap.add_argument("--accum-grad", type=int, default=1, help="micro-batches per optimizer step (recipe: 4); a 'step' stays one micro-batch")
-    ap.add_argument("--comm-chunks", type=int, default=6, help="gradient all-reduce chunks launched from inside the backward pass")
+    ap.add_argument("--comm-chunks", type=int, default=1, help="gradient all-reduce chunks")
+    ap.add_argument("--comm-overlap", action="store_true",
+                    help="launch each chunk's all-reduce from inside the backward pass (measured SLOWER on this step: the "
+                         "persistent attention kernels own all 148 SMs and wait for the SMs NCCL occupies; default: one "
+                         "all-reduce after the backward pass, inside the same CUDA graph)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     args.model = args.model or cfg["model"]
@@ -286,7 +290,7 @@ def main():
     torch.manual_seed(2022)
     model = build_model(args.model, dev, specaug=args.specaug)
     params = [p for p in model.parameters() if p.requires_grad]
-    bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16, n_chunks=args.comm_chunks)
+    bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16, n_chunks=args.comm_chunks, overlap=args.comm_overlap)
     opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01, fused=True,
                             capturable=not args.no_graph)
 
@@ -392,8 +396,7 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world)
         return
 
     ms_per_step = total_ms / args.steps
@@ -478,14 +481,28 @@ def main():
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": summary,
         "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager,
-        "comm": {"chunks": bucket.n_chunks, "chunks_all_reduced_inside_backward": bucket.chunks_reduced_in_backward > 0,
+        "comm": {"chunks": bucket.n_chunks, "overlap_with_backward": bool(args.comm_overlap),
+                 "chunks_all_reduced_inside_backward": bucket.chunks_reduced_in_backward > 0,
                  "one_graph": not args.no_graph},
         "skipped_steps": float(step.skipped_steps), "allreduce_bytes_per_step": bucket.nbytes if world > 1 else 0,
         "step_driver": "python-eager" if args.no_graph else "cuda-graph replay", "eager_ms_per_step": eager_ms / args.steps,
     }
     emit(line)
+    leave(world)
+
+
+def leave(world):
+    """End of a rank.  The captured step holds NCCL kernels: tearing the communicator down under live CUDA graphs (or
+    letting interpreter shutdown order their destructors) hung the 2-GPU run after the result line had been printed, so
+    multi-rank processes synchronise, flush and leave without running destructors."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if _REAL_STDOUT is not None:
+            _REAL_STDOUT.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

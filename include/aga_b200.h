@@ -132,6 +132,14 @@ typedef struct aga_attn_params {
   const int32_t* kv_len;    /* NULL, or a DEVICE scalar: only keys [0, min(*kv_len, Tk)) exist (non-causal attention on a batch
                              * zero-padded to a static Tk for CUDA-graph replay; the reference never computes the padded keys).
                              * Backward: dk / dv rows at or past *kv_len are written as zeros.  tcgen05 path only. */
+  /* Guided-loss reduction fused into the attention epilogue (decoder self attention: causal, Tq <= 128, tcgen05 path).
+   * Replaces the per-(utterance, layer, head) part of ESPnetASRModel.calculate_cs_loss (E2/asr/espnet_model.py:496-512):
+   * r_t = sum_{j in {1,2}} (S~[t,j] - c[t,j])^2 with the reference's zeroing rules (-inf -> 0; pad rows -> 0 unless
+   * guided_early), then guided_part[b,h,g,0] = sum_t r_t and guided_part[b,h,g,1] = #{t : r_t != 0} over the 32 query
+   * rows t of row group g = t / 32 (no atomics: deterministic).  The (L,B,H,T,2) slab need not be exported at all. */
+  const float* guided_pattern; /* NULL, or (B, Tq, 2) fp32 from aga_attention_pattern (+inf rows = padding) */
+  float* guided_part;          /* (B, H, 4, 2) fp32, zero-initialised by the caller */
+  int32_t guided_early;        /* 1: layer uses the all-zero "early" target and keeps pad rows (espnet_model.py:479-481) */
 } aga_attn_params;
 
 AGA_API int aga_attn_fwd_workspace_bytes(const aga_attn_params* p, size_t* bytes);
@@ -144,6 +152,8 @@ typedef struct aga_attn_bwd_params {
   void* dq;                 /* strides as q */
   void* dk;                 /* strides as k */
   void* dv;                 /* strides as v */
+  const float* d_guided_part; /* NULL, or (B, H, 4, 2): gradient w.r.t. fwd.guided_part ([...,0] is used); the kernel adds
+                               * 2 (S~ - c) d_guided_part[b,h,t/32,0] to dS on the visible, non-zeroed entries of columns 1, 2 */
 } aga_attn_bwd_params;
 
 AGA_API int aga_attn_bwd_workspace_bytes(const aga_attn_bwd_params* p, size_t* bytes);

@@ -140,10 +140,15 @@ def test_tc_causal_export_forward_vs_oracle(A, B, H, T, cols, sel):
 
 
 @pytest.mark.parametrize("B,H,T,cols,sel", [(2, 3, 64, (1, 3), None), (1, 2, 128, (1, 3), [0, 1]), (2, 2, 37, (0, 5), None),
-                                            (16, 12, 64, (1, 3), None)])
+                                            (16, 12, 64, (1, 3), None),
+                                            # more than one query tile (the decoder's context is 448, whisper/model.py:322):
+                                            # the persistent kernel with the causal mask and the exported columns' gradient
+                                            (1, 2, 300, (1, 3), None), (1, 1, 448, (1, 3), None), (2, 2, 200, (0, 5), [1, 0]),
+                                            (1, 2, 129, (1, 3), None)])
 def test_tc_causal_export_backward_vs_oracle(A, B, H, T, cols, sel):
-    """dQ/dK/dV of the causal one-query-tile kernel with a gradient on the exported columns (the guided loss'
-    gradient, espnet_model.py:463-530) vs the fp64 oracle, and agreement with the CUDA-core path."""
+    """dQ/dK/dV of the causal tcgen05 kernels (one query tile: Q-resident kernel; more: persistent kernel) with a gradient
+    on the exported columns (the guided loss' gradient, espnet_model.py:463-530) vs the fp64 oracle, and agreement with the
+    CUDA-core path."""
     q, k, v = _mk(B, T, T, H, 1.0, seed=T * 5 + 1)
     g = torch.Generator().manual_seed(3)
     do = torch.randn(B, T, H * 64, generator=g).bfloat16()
