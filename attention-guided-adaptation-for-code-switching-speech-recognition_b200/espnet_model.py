@@ -207,6 +207,8 @@ class ESPnetASRModel(torch.nn.Module):
                           attention_default: float = 0.6) -> torch.Tensor:
         """attention_maps: (L,B,H,T,T) full maps (reference layout) or the compact (L,B,H,T,2) export of key
         columns 1:3; ground_truth_token = ys_in_pad (B,T).  (:463-530)"""
+        if isinstance(attention_maps, ops.GuidedParts):  # decoder(export_mode="fused"): the reduction over t is already done
+            return ops.guided_loss_from_parts(attention_maps, self.cs_head_mask)
         slab = attention_maps if attention_maps.shape[-1] == 2 and attention_maps.shape[-2] != 2 \
             else attention_maps[..., 1:3]
         pattern = self.create_attention_pattern(ground_truth_token, attention_default)
@@ -232,6 +234,10 @@ class ESPnetASRModel(torch.nn.Module):
         else:
             ys_in_pad, ys_out_pad = add_sos_eos(ys_pad, self.sos, self.eos, self.ignore_id)
         ys_in_lens = ys_pad_lens + 1
+        if getattr(self.decoder, "export_mode", None) == "fused" and self.cs_weight != 0:
+            # the attention epilogue reduces the guided loss: it needs the target pattern of this batch
+            self.decoder.guided_pattern = self.create_attention_pattern(ys_in_pad, self.c_val_attention)
+            self.decoder.n_early_layers = self.n_early_layers
         if memory_len is None:
             decoder_out, att_map = self.decoder(encoder_out, encoder_out_lens, ys_in_pad, ys_in_lens)
         else:

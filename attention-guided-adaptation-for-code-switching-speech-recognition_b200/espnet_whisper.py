@@ -170,6 +170,11 @@ class OpenAIWhisperDecoder(torch.nn.Module):
                             with -inf above the diagonal (or probabilities with ``export_kind="probs"``)
       export_mode="compact" only key columns 1:3 (the <|zh|>, <|en|> prompt tokens, the only ones the guided loss
                             reads, espnet_model.py:506): (L_sel,B,H,T,2)
+      export_mode="fused"   nothing is exported: the guided loss' reduction over the target positions runs in the
+                            attention kernel's epilogue and ``att_maps`` is an ``ops.GuidedParts`` (L_sel,B,H,4,2) of
+                            partial sums that ``ESPnetASRModel.calculate_cs_loss`` finishes.  Needs ``guided_pattern``
+                            (set by ESPnetASRModel before the call), bf16 activations and T <= 128; longer targets and
+                            fp32 runs use the compact export for that call.
     """
 
     def __init__(self, vocab_size: int, encoder_output_size: int, dropout_rate: float = 0.0,
@@ -205,14 +210,21 @@ class OpenAIWhisperDecoder(torch.nn.Module):
         self.c_val_attention = c_val_attention
         if estimate_c:
             self.decoders.estimated_c_val = torch.nn.Parameter(torch.Tensor([c_val_attention]))
-        assert export_mode in ("full", "compact") and export_kind in ("logits", "probs")
+        assert export_mode in ("full", "compact", "fused") and export_kind in ("logits", "probs")
         self.export_mode, self.export_kind = export_mode, export_kind
+        self.guided_pattern: Optional[torch.Tensor] = None  # (B,T,2) target pattern of the current batch (export_mode "fused")
+        self.n_early_layers = 2
 
-    def _set_export(self, enabled: bool, mode: Optional[str] = None) -> None:
+    def _set_export(self, enabled: bool, mode: Optional[str] = None, guided: Optional[torch.Tensor] = None) -> None:
         mode = mode or self.export_mode
         for layer, block in enumerate(self.decoders.blocks):
             on = enabled and layer >= self.src_layer
-            block.attn.export = (self.export_kind, (1, 3) if mode == "compact" else None) if on else None
+            if on and mode == "fused":
+                block.attn.export = None
+                block.attn.guided = (guided, layer < self.n_early_layers)
+            else:
+                block.attn.guided = None
+                block.attn.export = (self.export_kind, (1, 3) if mode == "compact" else None) if on else None
 
     def forward(self, hs_pad: torch.Tensor, hlens: torch.Tensor, ys_in_pad: torch.Tensor, ys_in_lens: torch.Tensor,
                 side_encoder_output: torch.Tensor = None, memory_len: torch.Tensor = None) -> Tuple[torch.Tensor, Any]:
@@ -222,7 +234,13 @@ class OpenAIWhisperDecoder(torch.nn.Module):
         dec = self.decoders
         tgt = dec.token_embedding(ys_in_pad) + dec.positional_embedding[: ys_in_pad.size(1)]
         x = self.dropout(tgt).to(hs_pad.dtype)
-        self._set_export(self.whisper_cs)
+        mode = self.export_mode
+        if mode == "fused":
+            act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+            usable = (self.guided_pattern is not None and act == torch.bfloat16 and 3 <= ys_in_pad.size(1) <= 128
+                      and self.export_kind == "logits" and x.is_cuda and dec.blocks[0].attn._frozen())
+            mode = "fused" if usable else "compact"
+        self._set_export(self.whisper_cs, mode, self.guided_pattern)
         attention_scores: List[torch.Tensor] = []
         last = len(dec.blocks) - 1
         for layer, block in enumerate(dec.blocks):
@@ -234,6 +252,8 @@ class OpenAIWhisperDecoder(torch.nn.Module):
         x = dec.ln(x)
         logits = dec.vocab_logits(x, lazy=self.fused_loss)
         if self.whisper_cs:
+            if mode == "fused":
+                return logits, ops.GuidedParts.stack(attention_scores)
             return logits, torch.stack(attention_scores)
         return logits, attention_scores
 

@@ -147,6 +147,7 @@ class MultiHeadAttention(nn.Module):
         self.value = Linear(n_state, n_state)
         self.out = Linear(n_state, n_state)
         self.export: Optional[Tuple[str, Optional[Tuple[int, int]]]] = None
+        self.guided: Optional[Tuple[Tensor, bool]] = None  # (pattern (B,T,2), early layer): fuse the guided loss' reduction
         self.head_sel: Optional[Tensor] = None
         self.impl = "auto"
 
@@ -198,7 +199,8 @@ class MultiHeadAttention(nn.Module):
             causal = mask is not None
             out, _lse, second = ops.qkv_attention_packed(qkv, self.n_head, causal=causal, export=kind, export_cols=cols,
                                                          head_sel=self.head_sel, impl=self.impl,
-                                                         kv_len=None if causal else kv_len)
+                                                         kv_len=None if causal else kv_len,
+                                                         guided=self.guided if causal else None)
         else:
             w, b = self._packed_weights(x.dtype, False)
             q = self.query(x)

@@ -90,7 +90,7 @@ RECIPE_SPECAUG = dict(apply_time_warp=True, time_warp_window=5, time_warp_mode="
                       num_time_mask=2)
 
 
-def build_model(name, device, export_mode="compact", specaug=False):
+def build_model(name, device, export_mode="fused", specaug=False):
     import aga_b200  # noqa: F401
     from aga_b200 import espnet_model as EM, espnet_whisper as EW, whisper_model as W
 
@@ -237,7 +237,8 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, batch=None, world=None, export="decoder self-attn cols 1:3 (compact)", note=None):
+def workload_config(args, batch=None, world=None, export="none: guided-loss reduction fused into the decoder self-attention "
+                    "epilogue (cols 1:3 of the scaled logits)", note=None):
     batch = args.batch if batch is None else batch
     world = args.gpus if world is None else world
     cfg = {"workload": f"Whisper-{args.model} attention-guided adaptation training step "

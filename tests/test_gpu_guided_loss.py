@@ -83,3 +83,41 @@ def test_head_selection_end_to_end(A):
     dec, cnt = A.head_vote(probs)
     ref = O.new_check_attention_language(probs.cpu().numpy())
     assert np.array_equal(cnt.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("B,H,T,early", [(2, 3, 64, False), (3, 2, 37, False), (2, 2, 128, True), (1, 12, 5, False)])
+def test_guided_loss_fused_into_attention_epilogue(A, B, H, T, early):
+    """N1 (north star: "the guided-loss reduction is fused into the same epilogue"): the decoder self-attention kernel
+    reduces sum_t r_t and the non-zero count per (utterance, head) itself — no slab is exported.  Loss and the gradient
+    that reaches the packed QKV projection equal the two-kernel path (export columns 1:3 -> aga_guided_loss_fwd_bwd) and
+    the oracle (espnet_model.py:463-530), pad rows / causal zeros / early layers included."""
+    from aga_b200 import ops
+    g = torch.Generator().manual_seed(T * 7 + H)
+    x = torch.randn(B, T, 3 * H * 64, generator=g).bfloat16().cuda()
+    toks = torch.full((B, T), 50257, dtype=torch.long)
+    toks[:, :5] = torch.tensor([50258, 50260, 50259, 50359, 50363])
+    for b in range(B):
+        n = min(T - 5, 3 + 7 * b)
+        toks[b, 5:5 + n] = torch.randint(0, 50257, (n,), generator=g)
+    lid = torch.from_numpy(np.fromfile(LID, dtype=np.uint8))
+    pat = A.attention_pattern(toks.cuda(), lid, 0.6)
+    mask = (torch.rand(1, H, generator=g) < 0.7).float().cuda()
+    n_early = 1 if early else 0
+    do = torch.randn(B, T, H * 64, generator=g).bfloat16().cuda()
+    res = {}
+    for mode in ("fused", "slab"):
+        xd = x.clone().requires_grad_()
+        if mode == "fused":
+            out, _, parts = ops.qkv_attention_packed(xd, H, causal=True, guided=(pat, early), impl="tcgen05")
+            assert parts.t.shape == (B, H, 4, 2)
+            loss = ops.guided_loss_from_parts(ops.GuidedParts(parts.t[None]), mask)
+        else:
+            out, _, slab = ops.qkv_attention_packed(xd, H, causal=True, export="logits", export_cols=(1, 3), impl="tcgen05")
+            loss = A.guided_loss(slab[None], pat, mask, n_early=n_early)
+        torch.autograd.backward([out, loss * 3.0], [do, torch.ones((), device="cuda")])
+        res[mode] = (float(loss), xd.grad.float(), slab.detach() if mode == "slab" else None)
+    want = O.calculate_cs_loss(res["slab"][2].cpu().numpy()[None], pat.cpu().numpy(), mask.cpu().numpy(), n_early=n_early)
+    np.testing.assert_allclose(res["fused"][0], want, rtol=1e-5)
+    np.testing.assert_allclose(res["fused"][0], res["slab"][0], rtol=1e-5)
+    scale = float(res["slab"][1].abs().max())
+    torch.testing.assert_close(res["fused"][1], res["slab"][1], rtol=2e-2, atol=2e-3 * scale)
