@@ -37,6 +37,43 @@ def load_lid_table(path: Optional[str] = None) -> torch.Tensor:
     return torch.from_numpy(np.fromfile(path, dtype=np.uint8))
 
 
+def build_lid_table(tiktoken_path: str, vocab_size: int = 51865) -> torch.Tensor:
+    """The product's own generator of the language-id table (no test infrastructure involved): reads a Whisper BPE asset
+    (``whisper/assets/multilingual.tiktoken``: one ``base64(token bytes) rank`` pair per line) and classifies every token
+    id with the string tests of ESPnetASRModel.is_english / create_attention_pattern (espnet_model.py:234-258) on the
+    token's GPT-2 "bytes to unicode" spelling — what the reference gets from HF ``convert_ids_to_tokens``:
+    3 = <|endoftext|> (id = number of BPE ranks), 2 = only the space marker, 1 = ASCII letters only (English), 0 = other.
+    ``load_lid_table()`` reads the table shipped in ``data/`` (generated from the reference's own asset)."""
+    import base64
+    import string
+    ranks = {}
+    with open(tiktoken_path) as f:
+        for line in f:
+            if line.strip():
+                tok, rank = line.split()
+                ranks[int(rank)] = base64.b64decode(tok)
+    # GPT-2 byte -> printable unicode map: the space byte 0x20 becomes 'Ġ' (U+0120)
+    bs = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAC + 1)) + list(range(0xAE, 0xFF + 1))
+    cs, n = bs[:], 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b)
+            cs.append(256 + n)
+            n += 1
+    b2u = dict(zip(bs, (chr(c) for c in cs)))
+    letters = set(string.ascii_letters)
+    table = np.zeros(vocab_size, dtype=np.uint8)
+    for i in range(vocab_size):
+        if i == len(ranks):          # the first special id: <|endoftext|> (50257 for the multilingual vocabulary)
+            table[i] = 3
+            continue
+        if i > len(ranks):           # other specials ("<|...|>"): not letters-only -> class 0
+            continue
+        word = "".join(b2u[x] for x in ranks[i]).replace("\u0120", "")
+        table[i] = 2 if word == "" else (1 if all(ch in letters for ch in word) else 0)
+    return torch.from_numpy(table)
+
+
 def select_heads(attention_count: Dict[int, Dict[int, int]], head_percentage: float, n_layers: int, n_heads: int,
                  base: int = 110) -> torch.Tensor:
     """espnet_model.py:202-216: flatten in dict order, STABLE sort by count (desc), keep the first
