@@ -66,7 +66,8 @@ extern "C" int aga_attn_fwd_workspace_bytes(const aga_attn_params* p, size_t* by
   int st = validate(p);
   if (st != AGA_OK) return st;
   if (!bytes) return AGA_ERR_INVALID_ARGUMENT;
-  if ((p->impl == AGA_ATTN_TCGEN05 || p->kv_len || p->guided_part) && !use_tc(*p)) return AGA_ERR_UNSUPPORTED;
+  // (the CUDA-core forward serves kv_len too — the fp32 decoding step; the backward and the guided epilogue are tcgen05 only)
+  if ((p->impl == AGA_ATTN_TCGEN05 || p->guided_part) && !use_tc(*p)) return AGA_ERR_UNSUPPORTED;
   *bytes = use_tc(*p) ? attn_tc_fwd_workspace(*p) : 0;
   return AGA_OK;
 }

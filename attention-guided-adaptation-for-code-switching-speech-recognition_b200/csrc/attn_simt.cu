@@ -173,6 +173,7 @@ struct SimtArgs {
   void* dq;
   void* dk;
   void* dv;
+  const int32_t* kv_len;  // forward only: device scalar, keys at or past it do not exist (static-shape decoding step)
 };
 
 __device__ __forceinline__ bool head_selected(const SimtArgs& a, int h) {
@@ -207,13 +208,14 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_simt_kernel(const SimtArgs 
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   }
-  int n_kt = (a.Tk + kBN - 1) / kBN;
+  const int Tk = a.kv_len ? max(1, min(__ldg(a.kv_len), a.Tk)) : a.Tk;
+  int n_kt = (Tk + kBN - 1) / kBN;
   if (a.causal) n_kt = min(n_kt, qt + 1);
 
   for (int kt = 0; kt < n_kt; ++kt) {
     __syncthreads();  // previous tile's P V done (and Q visible on the first trip)
-    load_tile<T>(Ks, kg, a.k_st, kt * kBN, a.Tk, tid);
-    load_tile<T>(Vs, vg, a.v_st, kt * kBN, a.Tk, tid);
+    load_tile<T>(Ks, kg, a.k_st, kt * kBN, Tk, tid);
+    load_tile<T>(Vs, vg, a.v_st, kt * kBN, Tk, tid);
     __syncthreads();
     float s[4][4];
     micro_nt(Qs, Ks, ty, tx, s);
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_simt_kernel(const SimtArgs 
       for (int j = 0; j < 4; ++j) {
         const int col = kt * kBN + tx + 16 * j;
         float sv = s[i][j] * kScale;
-        if (col >= a.Tk || (a.causal && col > row)) sv = -INFINITY;
+        if (col >= Tk || (a.causal && col > row)) sv = -INFINITY;
         s[i][j] = sv;
         mx = fmaxf(mx, sv);
         if (exp_on && row < a.Tq && col >= a.export_lo && col < a.export_hi)
@@ -458,6 +460,7 @@ SimtArgs make_args(const aga_attn_params& p) {
   a.q_sb = p.q_stride_b; a.q_st = p.q_stride_t; a.k_sb = p.k_stride_b; a.k_st = p.k_stride_t;
   a.v_sb = p.v_stride_b; a.v_st = p.v_stride_t; a.o_sb = p.o_stride_b; a.o_st = p.o_stride_t;
   a.q = p.q; a.k = p.k; a.v = p.v; a.out = p.out; a.lse = p.lse; a.head_sel = p.head_sel; a.export_buf = p.export_buf;
+  a.kv_len = p.kv_len;
   return a;
 }
 

@@ -162,6 +162,100 @@ class WhisperFrontend(torch.nn.Module):
         return feats, feats_lens
 
 
+class GraphedGreedyDecoder:
+    """Greedy decoding as ONE captured CUDA graph per token (the next step after the KV cache).
+
+    The reference recomputes the whole prefix on every step and copies every layer's map to the host
+    (whisper_decoder.py:172-244); the KV-cached ``forward_one_step`` of this package is O(t) per token but still ~200
+    kernel launches from Python (8-9 ms per token).  Here every shape is static: the self-attention K / V live in
+    preallocated (n, max_len, D) buffers, the position is a DEVICE scalar (it indexes the positional embedding, the cache
+    row to write and — as ``kv_len`` — the number of keys the attention kernel may see), the arg-max token is fed back
+    on the device.  ``prefill`` runs the prompt through the normal KV-cached path; ``decode(n)`` replays the captured
+    step n times with no host round trip and returns (token ids (n_hyp, n), their log-probabilities).
+    Same tokens and log-probabilities as ``forward_one_step`` (tests/test_gpu_decode.py)."""
+
+    def __init__(self, decoder: "OpenAIWhisperDecoder", memory: torch.Tensor, max_len: int = 448):
+        self.dec, self.memory, self.max_len = decoder, memory, max_len
+        self.n = memory.size(0)
+        self.graph = None
+
+    @torch.no_grad()
+    def prefill(self, prompt: torch.Tensor) -> None:
+        """prompt (n, t0) int64: fills the caches with the prompt's keys / values and leaves the first generated token in
+        ``self.tok`` (as greedy ``forward_one_step`` on the prompt would)."""
+        d, dec = self.dec, self.dec.decoders
+        was = d.kv_cache
+        d.kv_cache = True
+        try:
+            logp, cache = d._forward_one_step_cached(prompt, self.memory, None)
+        finally:
+            d.kv_cache = was
+        dev, dt = self.memory.device, self.memory.dtype
+        D = dec.token_embedding.embedding_dim
+        t0 = prompt.size(1)
+        self.k = [torch.zeros(self.n, self.max_len, D, device=dev, dtype=dt) for _ in dec.blocks]
+        self.v = [torch.zeros(self.n, self.max_len, D, device=dev, dtype=dt) for _ in dec.blocks]
+        self.cross = []
+        for layer, (k, v, kc, vc) in enumerate(cache):
+            self.k[layer][:, :t0] = k
+            self.v[layer][:, :t0] = v
+            self.cross.append((kc.contiguous(), vc.contiguous()))
+        best = logp.max(dim=-1)
+        self.tok = best.indices.view(self.n, 1).clone()       # token at position t0 (not yet in the cache)
+        self.tok_logp = best.values.clone()
+        self.pos = torch.full((1,), t0, dtype=torch.int64, device=dev)
+        self.out_tok = torch.zeros(self.n, self.max_len, dtype=torch.int64, device=dev)
+        self.out_logp = torch.zeros(self.n, self.max_len, dtype=torch.float32, device=dev)
+        self.n_out = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.graph = None
+
+    def _step(self) -> None:
+        """Consume ``self.tok`` at position ``self.pos``; leave the next token in ``self.tok``."""
+        dec = self.dec.decoders
+        self.out_tok.index_copy_(1, self.n_out, self.tok)
+        self.out_logp.index_copy_(1, self.n_out, self.tok_logp.view(self.n, 1))
+        x = dec.token_embedding(self.tok) + dec.positional_embedding.index_select(0, self.pos)
+        x = x.to(self.memory.dtype)
+        kv_len = (self.pos + 1).to(torch.int32)
+        for layer, block in enumerate(dec.blocks):
+            x = block.step_static(x, self.k[layer], self.v[layer], self.pos, kv_len, self.cross[layer])
+        logp = torch.log_softmax(dec.vocab_logits(dec.ln(x[:, -1])), dim=-1)
+        best = logp.max(dim=-1)
+        self.tok.copy_(best.indices.view(self.n, 1))
+        self.tok_logp.copy_(best.values)
+        self.pos.add_(1)
+        self.n_out.add_(1)
+
+    @torch.no_grad()
+    def decode(self, n_tokens: int):
+        """Generate ``n_tokens`` more tokens (the first is the one ``prefill`` left pending).  Returns (ids, logp) of all
+        tokens generated so far, shapes (n_hyp, total)."""
+        if self.graph is None:
+            self.dec._set_export(False)
+            state = [t.clone() for t in (self.tok, self.tok_logp, self.pos, self.n_out, self.out_tok, self.out_logp)]
+            kv = [t.clone() for t in self.k + self.v]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._step()  # warm-up (lazy initialisation outside the capture)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step()
+            # the warm-up step and the capture changed nothing that matters, but restore the exact pre-step state anyway
+            for dst, src in zip((self.tok, self.tok_logp, self.pos, self.n_out, self.out_tok, self.out_logp), state):
+                dst.copy_(src)
+            for dst, src in zip(self.k + self.v, kv):
+                dst.copy_(src)
+        total = int(self.n_out.item()) + n_tokens
+        if int(self.pos.item()) + n_tokens > self.max_len:
+            raise ValueError("decoding past max_len")
+        for _ in range(n_tokens):
+            self.graph.replay()
+        return self.out_tok[:, :total].clone(), self.out_logp[:, :total].clone()
+
+
 class OpenAIWhisperDecoder(torch.nn.Module):
     """``forward`` returns ``(logits, att_maps)`` like the reference.  ``att_maps`` holds, per decoder layer
     ``>= src_layer-1``, the SELF-attention map the block returns (whisper/model.py:232,248):
@@ -312,6 +406,10 @@ class OpenAIWhisperDecoder(torch.nn.Module):
                 x = self.dropout(x)
         x = dec.ln(x[:, -1])
         return torch.log_softmax(dec.vocab_logits(x), dim=-1), new_cache
+
+    def greedy_decoder(self, memory: torch.Tensor, max_len: int = 448) -> "GraphedGreedyDecoder":
+        """A CUDA-graph greedy decoder over this module for the encoder output ``memory`` (n, Ta, D)."""
+        return GraphedGreedyDecoder(self, memory, max_len)
 
     def score(self, ys, state, x):
         if self.kv_cache and state is not None:

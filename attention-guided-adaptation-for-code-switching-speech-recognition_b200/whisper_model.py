@@ -228,6 +228,16 @@ class MultiHeadAttention(nn.Module):
         out, _, _ = ops.qkv_attention(q, k, v, self.n_head, causal=q.shape[1] > 1, impl=self.impl)
         return self.out(out), k, v
 
+    def step_static(self, x: Tensor, k_buf: Tensor, v_buf: Tensor, pos: Tensor, kv_len: Tensor) -> Tensor:
+        """One decoding step with STATIC shapes (graph-capturable): x (n, 1, D) is the new token's activation, ``k_buf`` /
+        ``v_buf`` (n, max_len, D) the preallocated self-attention cache, ``pos`` (1,) int64 the row the new key / value go
+        to, ``kv_len`` = pos + 1 as the device scalar the attention kernel masks with.  Same arithmetic as ``step``."""
+        q = self.query(x)
+        k_buf.index_copy_(1, pos, self.key(x))
+        v_buf.index_copy_(1, pos, self.value(x))
+        out, _, _ = ops.qkv_attention(q, k_buf, v_buf, self.n_head, causal=False, impl=self.impl, kv_len=kv_len)
+        return self.out(out)
+
     def qkv_attention(self, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor] = None):
         # The only mask the reference ever passes is TextDecoder.mask = triu(-inf) (whisper/model.py:322,103),
         # i.e. "mask is not None" <=> causal over equal-length q/k.
@@ -305,6 +315,17 @@ class ResidualAttentionBlock(nn.Module):
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x, (k, v, kc, vc)
+
+    def step_static(self, x: Tensor, k_buf: Tensor, v_buf: Tensor, pos: Tensor, kv_len: Tensor, cross_kv: Tuple[Tensor, Tensor]):
+        """``step`` on preallocated caches (see MultiHeadAttention.step_static): no shape depends on the position."""
+        x = x + self.attn.step_static(self.attn_ln(x), k_buf, v_buf, pos, kv_len)
+        if self.adapter_flag:
+            x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)
+        x = x + self.cross_attn.step(self.cross_attn_ln(x), cross_kv=cross_kv)
+        x = x + self.mlp(self.mlp_ln(x))
+        if self.adapter_flag:
+            x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
+        return x
 
     def _mlp_residual(self, y: Tensor, x: Tensor) -> Tensor:
         """``x + self.mlp(y)`` (whisper/model.py:242).  Frozen bf16 MLP on a CUDA device: two GEMMs and nothing else — the

@@ -131,7 +131,8 @@ typedef struct aga_attn_params {
   float* export_buf;        /* (B, H, Tq, hi-lo) fp32; rows of unselected heads are left untouched */
   const int32_t* kv_len;    /* NULL, or a DEVICE scalar: only keys [0, min(*kv_len, Tk)) exist (non-causal attention on a batch
                              * zero-padded to a static Tk for CUDA-graph replay; the reference never computes the padded keys).
-                             * Backward: dk / dv rows at or past *kv_len are written as zeros.  tcgen05 path only. */
+                             * Backward (tcgen05 path only): dk / dv rows of the partial key tile at or past *kv_len are written
+                             * as zeros, whole key tiles past it are not touched (zero-initialise dk / dv). */
   /* Guided-loss reduction fused into the attention epilogue (decoder self attention: causal, Tq <= 128, tcgen05 path).
    * Replaces the per-(utterance, layer, head) part of ESPnetASRModel.calculate_cs_loss (E2/asr/espnet_model.py:496-512):
    * r_t = sum_{j in {1,2}} (S~[t,j] - c[t,j])^2 with the reference's zeroing rules (-inf -> 0; pad rows -> 0 unless

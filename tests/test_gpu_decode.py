@@ -91,3 +91,44 @@ def test_kv_cached_decode_matches_recompute_and_reference(golden_dir):
         lpd, _ = dec.batch_score(nxt, [None, None], enc_out.expand(2, -1, -1))
         torch.testing.assert_close(lpc, lpd, rtol=1e-3, atol=1e-3)
         assert len(sc) == 2 and sc[0][0][0].shape == (8, 768)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_graphed_greedy_decode_matches_forward_one_step(golden_dir, dtype):
+    """GraphedGreedyDecoder: one captured CUDA graph per token on static shapes (preallocated K / V, position and key
+    count as device scalars).  fp32: the reference's greedy hypothesis and log-probabilities on the bundled utterance
+    (decode_seame.npz); bf16: the same tokens as the KV-cached forward_one_step in bf16."""
+    import aga_b200  # noqa: F401
+    from aga_b200 import espnet_whisper as EW
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = np.load(os.path.join(golden_dir, "decode_seame.npz"))
+    enc = EW.OpenAIWhisperEncoder(whisper_model="small", adapter=True).cuda().eval()
+    dec = EW.OpenAIWhisperDecoder(51865, 768, whisper_model="small", adapter=True, whisper_cs=True, src_layer=1,
+                                  kv_cache=True).cuda().eval()
+    speech = torch.from_numpy(g["pcm"].astype(np.float32) / 32768.0)[None].cuda()
+    n_tok = len(g["token_ids"])
+    prompt = torch.tensor([[50258, 50260, 50259, 50359, 50363]], device="cuda")
+    with torch.no_grad():
+        enc_out, _, _ = enc(speech, torch.tensor([41760], device="cuda"))
+        enc_out = enc_out.to(dtype)
+        gd = dec.greedy_decoder(enc_out, max_len=64)
+        gd.prefill(prompt)
+        ids, logp = gd.decode(n_tok)
+        # a second call continues where the first stopped, replaying the same graph
+        ids2, _ = gd.decode(3)
+        assert ids2.shape == (1, n_tok + 3) and torch.equal(ids2[:, :n_tok], ids)
+        # the Python-driven KV-cached path in the same dtype
+        ys, cache, ref_ids, ref_logp = prompt, None, [], []
+        for _ in range(n_tok + 3):
+            lp, cache = dec.forward_one_step(ys, torch.empty(0), enc_out, cache=cache)
+            nxt = lp.argmax(-1, keepdim=True)
+            ref_ids.append(int(nxt))
+            ref_logp.append(float(lp[0, int(nxt)]))
+            ys = torch.cat([ys, nxt], dim=1)
+    assert ids2[0].tolist() == ref_ids
+    if dtype == torch.float32:
+        assert ids[0].tolist() == g["token_ids"].tolist()
+        np.testing.assert_allclose(logp[0].cpu().numpy(), g["logp"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(logp[0].cpu().numpy(), np.array(ref_logp[:n_tok]), rtol=2e-3, atol=2e-3)

@@ -21,6 +21,18 @@ def run(dec, enc_out, steps, cached):
     torch.cuda.synchronize()
     return time.perf_counter() - t0, ys
 
+def run_graphed(dec, enc_out, steps):
+    ys = torch.tensor([[50258, 50260, 50259, 50359, 50363]], device="cuda")
+    gd = dec.greedy_decoder(enc_out, max_len=128)
+    gd.prefill(ys)
+    gd.decode(2)  # capture
+    gd.prefill(ys)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ids, _ = gd.decode(steps)
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0, ids
+
 def main():
     dec = EW.OpenAIWhisperDecoder(51865, 768, whisper_model="small", adapter=True, whisper_cs=True, src_layer=1).cuda().eval()
     for dtype in (torch.float32, torch.bfloat16):
@@ -29,6 +41,8 @@ def main():
             run(dec, enc_out, 5, cached)
             dt, ys = run(dec, enc_out, 60, cached)
             print(f"{str(dtype):16s} {'kv-cached ' if cached else 'recompute '} 60 steps: {dt * 1e3:7.1f} ms  {60 / dt:7.1f} tokens/s")
+        dt, ids = run_graphed(dec, enc_out, 60)
+        print(f"{str(dtype):16s} cuda-graph  60 steps: {dt * 1e3:7.1f} ms  {60 / dt:7.1f} tokens/s")
 
 if __name__ == "__main__":
     main()
