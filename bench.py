@@ -429,7 +429,7 @@ def main():
         except Exception:
             pass
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": traffic,
+                    "frac": ach / peak, "frac_of_burst_peak": ach / peaks.get("bf16_tflops", 1590.0), "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
                     "share_of_step": kern[dom]["ms_total"] / total_ms,
