@@ -10,6 +10,9 @@
 // TMA ring; tcgen05.mma M128 N256 K16 (128 clk each, 96 B/clk of shared-memory operand traffic); the fp32 accumulator is
 // double-buffered in TMEM (2 x 256 columns) so that the 8 epilogue warps (erf costs ~25 instructions per element)
 // work on tile i while the tensor core runs tile i+1; results leave through swizzled staging rows and TMA tile stores.
+// Default variant (kVar 2): clusters of two CTAs issue ONE tcgen05.mma.cta_group::2 M256 N256 K16 per K step — each CTA
+// stages its own 128 rows of A and HALF (128 rows) of the W tile, so the shared-memory traffic per SM drops from
+// 96 + 96 B/clk (operand reads + TMA fills, over the 128 B/clk an SM has) to 64 + 64 B/clk, and the ring deepens to 5.
 #include "aga_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -21,7 +24,9 @@ namespace {
 using namespace ptx;
 
 constexpr int kTM = 128, kTN = 256, kTK = 64;
-constexpr int kGStages = 3;
+constexpr int kGStages = 3;      // variants 0 / 1: A tile + whole W tile per stage
+constexpr int kGStages2 = 5;     // variant 2 (two-SM MMA): A tile + half W tile per stage
+constexpr int kGMaxStages = 5;
 constexpr int kATile = kTM * kTK * 2;   // 16 KiB
 constexpr int kBTile = kTN * kTK * 2;   // 32 KiB
 constexpr int kEpiWarps = 8;
@@ -30,7 +35,7 @@ constexpr int kGThreads = (kGEpiWarp0 + kEpiWarps) * 32;  // 384
 constexpr int kChunkBytes = 32 * 128;   // one warp's 32 rows x 64 bf16 columns
 
 struct GSmem {
-  uint64_t full[kGStages], empty[kGStages];
+  uint64_t full[kGMaxStages], empty[kGMaxStages];
   uint64_t acc_full[2], acc_empty[2];
   uint64_t h_ready[kEpiWarps];
   uint32_t tmem_base;
@@ -38,7 +43,8 @@ struct GSmem {
 };
 // stages | per epilogue warp: two 4 KiB staging chunks (h / g, or h_in / dh)
 constexpr size_t kGSmemBytes = 1024 + size_t(kGStages) * (kATile + kBTile) + size_t(kEpiWarps) * 2 * kChunkBytes + sizeof(GSmem);
-static_assert(kGSmemBytes <= 227 * 1024, "gemm_gelu exceeds the shared-memory limit");
+constexpr size_t kGSmemBytes2 = 1024 + size_t(kGStages2) * (kATile + kBTile / 2) + size_t(kEpiWarps) * 2 * kChunkBytes + sizeof(GSmem);
+static_assert(kGSmemBytes <= 227 * 1024 && kGSmemBytes2 <= 227 * 1024, "gemm_gelu exceeds the shared-memory limit");
 
 struct GArgs {
   int M, N, K;
@@ -75,6 +81,48 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// ---- two-SM (cta_group::2) forms: the leader CTA (cluster rank 0) issues the MMAs and owns the `full` / `acc_empty` barriers
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {  // shared::cta address -> the same offset in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// tile into THIS CTA's shared memory, bytes counted on a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// D[tmem of both CTAs: 128 lanes each] (+)= A[each CTA's 128 rows] * B[N/2 rows from each CTA]
+__device__ __forceinline__ void mma_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -125,18 +173,25 @@ __device__ __forceinline__ float2 dgelu_erf2(float2 x) {
 #endif
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-// kPair: clusters of two CTAs work on two vertically adjacent 128-row tiles of the same 256-column panel; each CTA
+// kVar 0: one CTA per 128 x 256 tile (M < 256).
+// kVar 1: clusters of two CTAs work on two vertically adjacent 128-row tiles of the same 256-column panel; each CTA
 // fetches HALF of the W tile and multicasts it into both CTAs' shared memory, so the L2 -> SM operand traffic per FLOP is
 // that of a 256 x 256 tile (the kernel is L2-bandwidth-bound with 128 x 256 tiles: 1.33 GB per Whisper-small MLP GEMM).
-template <bool kPair>
+// kVar 2: the same pairing, but the W halves stay where they land and the leader CTA issues cta_group::2 MMAs over both
+// CTAs' shared memory and TMEM: half the B-operand reads and half the TMA fill bytes per SM.
+template <int kVar>
 __global__ void __launch_bounds__(kGThreads, 1)
 gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_o, const GArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr bool kPair = kVar != 0;
+  constexpr bool kTwoSm = kVar == 2;
+  constexpr int kNStages = kTwoSm ? kGStages2 : kGStages;
+  constexpr int kBStage = kTwoSm ? kBTile / 2 : kBTile;  // bytes of W per stage in THIS CTA
   uint8_t* sA = smem;
-  uint8_t* sB = sA + kGStages * kATile;
-  uint8_t* sE = sB + kGStages * kBTile;  // epilogue staging: warp w -> [2][32 rows x 128 B]
+  uint8_t* sB = sA + kNStages * kATile;
+  uint8_t* sE = sB + kNStages * kBStage;  // epilogue staging: warp w -> [2][32 rows x 128 B]
   GSmem* sb = reinterpret_cast<GSmem*>(sE + kEpiWarps * 2 * kChunkBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -152,20 +207,25 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGStages; ++s) {
-      mbar_init(&sb->full[s], 1);
-      mbar_init(&sb->empty[s], kPair ? 2 : 1);  // pair: both CTAs' MMA warps release a stage (its W half lives in both)
+    for (int s = 0; s < kNStages; ++s) {
+      mbar_init(&sb->full[s], kTwoSm ? 2 : 1);  // two-SM: both CTAs' producers announce their bytes on the leader's barrier
+      mbar_init(&sb->empty[s], kVar == 1 ? 2 : 1);  // multicast pair: both CTAs' MMA warps release a stage (its W half lives in both)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->acc_full[i], 1);
-      mbar_init(&sb->acc_empty[i], kEpiWarps);
+      mbar_init(&sb->acc_empty[i], kTwoSm ? 2 * kEpiWarps : kEpiWarps);  // two-SM: the leader waits for both CTAs' epilogues
     }
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(&sb->h_ready[w], 1);
     fence_barrier_init();
   }
   if (warp == kGMmaWarp) {
-    tmem_alloc(&sb->tmem_base, 512);
-    tmem_relinquish();
+    if (kTwoSm) {  // the same warp of both CTAs takes part; both get the same columns
+      tmem_alloc_2sm(&sb->tmem_base, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(&sb->tmem_base, 512);
+      tmem_relinquish();
+    }
   }
   if (warp == kGTmaWarp && lane == 0) {
     prefetch_tensormap(&map_a);
@@ -186,9 +246,16 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int mt, nt;
       tile_of(u, mt, nt);
       for (int k = 0; k < n_k; ++k, ++it) {
-        const int s = it % kGStages;
-        mbar_wait(&sb->empty[s], ((it / kGStages) & 1) ^ 1);
+        const int s = it % kNStages;
+        mbar_wait(&sb->empty[s], ((it / kNStages) & 1) ^ 1);
         if (elect_one()) {
+          if (kTwoSm) {  // own A rows + own half of the W tile, counted on the leader's barrier
+            const uint32_t full_leader = mapa_rank(smem_u32(&sb->full[s]), 0);
+            mbar_arrive_expect_tx_cluster(full_leader, kATile + kBTile / 2);
+            tma_load_2d_2sm(sA + s * kATile, &map_a, full_leader, k * kTK, mt * kTM);
+            tma_load_2d_2sm(sB + s * kBStage, &map_w, full_leader, k * kTK, nt * kTN + rank * (kTN / 2));
+            continue;
+          }
           mbar_arrive_expect_tx(&sb->full[s], kATile + kBTile);
           tma_load_2d(sA + s * kATile, &map_a, &sb->full[s], k * kTK, mt * kTM);
           if (kPair) {  // this CTA's half of the W tile (128 of its 256 rows), delivered to both CTAs
@@ -203,24 +270,31 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == kGMmaWarp) {
     // ============================== MMA issuer ==============================
-    constexpr uint32_t idesc = make_idesc_bf16(kTM, kTN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(kTwoSm ? 2 * kTM : kTM, kTN, 0, 0);
     int it = 0, tile_i = 0;
-    for (int u = unit0; u < n_units; u += unit_step, ++tile_i) {
+    for (int u = unit0; u < n_units && !(kTwoSm && rank != 0); u += unit_step, ++tile_i) {  // two-SM: the leader issues for the pair
       const int buf = tile_i & 1;
       mbar_wait(&sb->acc_empty[buf], ((tile_i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
       tc_fence_after();
       for (int k = 0; k < n_k; ++k, ++it) {
-        const int s = it % kGStages;
-        mbar_wait(&sb->full[s], (it / kGStages) & 1);
+        const int s = it % kNStages;
+        mbar_wait(&sb->full[s], (it / kNStages) & 1);
         tc_fence_after();
         const uint64_t da = make_smem_desc_sw128(smem_u32(sA + s * kATile));
-        const uint64_t db = make_smem_desc_sw128(smem_u32(sB + s * kBTile));
+        const uint64_t db = make_smem_desc_sw128(smem_u32(sB + s * kBStage));
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kTK / 16; ++kk)
-            mma_ss(tmem + buf * kTN, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
-          if (kPair) tc_commit_multicast(&sb->empty[s], uint16_t(3)); else tc_commit(&sb->empty[s]);
-          if (k == n_k - 1) tc_commit(&sb->acc_full[buf]);
+          for (int kk = 0; kk < kTK / 16; ++kk) {
+            if (kTwoSm) mma_ss_2sm(tmem + buf * kTN, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            else mma_ss(tmem + buf * kTN, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          if (kTwoSm) {  // both CTAs' producers / epilogues wait on their own copies of these barriers
+            tc_commit_2sm(&sb->empty[s], uint16_t(3));
+            if (k == n_k - 1) tc_commit_2sm(&sb->acc_full[buf], uint16_t(3));
+          } else {
+            if (kPair) tc_commit_multicast(&sb->empty[s], uint16_t(3)); else tc_commit(&sb->empty[s]);
+            if (k == n_k - 1) tc_commit(&sb->acc_full[buf]);
+          }
         }
         __syncwarp();
       }
@@ -267,7 +341,9 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (c == 1) {  // both chunks of this warp are in registers: hand the accumulator back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sb->acc_empty[buf]);
+          if (lane == 0) {
+            if (kTwoSm) mbar_arrive_cluster(mapa_rank(smem_u32(&sb->acc_empty[buf]), 0)); else mbar_arrive(&sb->acc_empty[buf]);
+          }
         }
         if (a.mode == 1) {
           mbar_wait(&sb->h_ready[ew], hph & 1);
@@ -323,7 +399,9 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (kPair) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
-  if (warp == kGMmaWarp) tmem_dealloc(tmem, 512);
+  if (warp == kGMmaWarp) {
+    if (kTwoSm) tmem_dealloc_2sm(tmem, 512); else tmem_dealloc(tmem, 512);
+  }
 }
 
 PFN_cuTensorMapEncodeTiled encode_fn() {
@@ -353,10 +431,22 @@ int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, 
   return r == CUDA_SUCCESS ? AGA_OK : AGA_ERR_INVALID_ARGUMENT;
 }
 
+#ifndef AGA_GEMM_VARIANT
+#define AGA_GEMM_VARIANT 2
+#endif
+int g_gemm_variant = AGA_GEMM_VARIANT;  // 0 single CTA, 1 multicast pair, 2 two-SM MMA (see the kernel's comment)
+
 }  // namespace
 }  // namespace aga
 
 using namespace aga;
+
+// measurement hook (tools/bench_gemm_gelu.py): choose the kernel variant for M >= 256; returns the previous one
+extern "C" __attribute__((visibility("default"))) int aga_debug_set_gemm_variant(int variant) {
+  const int prev = g_gemm_variant;
+  if (variant >= 0 && variant <= 2) g_gemm_variant = variant;
+  return prev;
+}
 
 // mode 0: h (M,N) = bf16(a (M,K) @ w (N,K)^T + bias (N)),  out (M,N) = bf16(gelu(h));  h is an OUTPUT
 // mode 1: out (M,N) = bf16(bf16(a @ w^T) * gelu'(h));                                   h is an INPUT, bias ignored
@@ -381,15 +471,17 @@ extern "C" int aga_gemm_gelu(const void* a, const void* w, const void* bias, voi
     return n > 0 ? n : 148;
   }();
   const int n_mt = int((M + kTM - 1) / kTM), n_nt = (N + kTN - 1) / kTN;
-#ifndef AGA_GEMM_NO_PAIR
-  if (n_mt >= 2) {
+  if (n_mt >= 2 && g_gemm_variant != 0) {
+    const bool two_sm = g_gemm_variant == 2;
     const int n_units = ((n_mt + 1) / 2) * n_nt;
     const int n_clusters = std::max(1, std::min(n_units, n_sm / 2));
-    AGA_CUDA_TRY(cudaFuncSetAttribute(gemm_gelu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)));
+    auto kern = two_sm ? gemm_gelu_kernel<2> : gemm_gelu_kernel<1>;
+    const size_t smem_bytes = two_sm ? kGSmemBytes2 : kGSmemBytes;
+    AGA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(2 * n_clusters));
     cfg.blockDim = dim3(kGThreads);
-    cfg.dynamicSmemBytes = kGSmemBytes;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -398,13 +490,12 @@ extern "C" int aga_gemm_gelu(const void* a, const void* w, const void* bias, voi
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AGA_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_gelu_kernel<true>, ma, mw, mh, mo, ga));
+    AGA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mw, mh, mo, ga));
     AGA_AFTER_LAUNCH();
     return AGA_OK;
   }
-#endif
-  AGA_CUDA_TRY(cudaFuncSetAttribute(gemm_gelu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)));
-  gemm_gelu_kernel<false><<<std::min(n_mt * n_nt, n_sm), kGThreads, kGSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mw, mh, mo, ga);
+  AGA_CUDA_TRY(cudaFuncSetAttribute(gemm_gelu_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)));
+  gemm_gelu_kernel<0><<<std::min(n_mt * n_nt, n_sm), kGThreads, kGSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mw, mh, mo, ga);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }

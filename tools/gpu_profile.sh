@@ -21,7 +21,7 @@ python tools/profile_step.py > $OUT/${TAG}_torch_profile.txt 2>&1
 head -3 $OUT/${TAG}_torch_profile.txt
 
 # ncu launch list of the bench command (Python-driven launches so every kernel is its own launch)
-BENCH="python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline"
+BENCH="python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-gpu-eager"
 $BENCH > $OUT/${TAG}_plain_bench.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv \
     --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_ncu_bench.log 2>&1

@@ -5,7 +5,7 @@
 TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline"
+BENCH="python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-gpu-eager"
 $BENCH > $OUT/${TAG}_plain_bench.log 2>&1 || { echo "plain bench failed"; tail -5 $OUT/${TAG}_plain_bench.log; exit 1; }
 # model build + 3 warm-up steps come first: skip them, then list a bit more than two steps
 timeout 700 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip ${SKIP:-4000} -c ${COUNT:-3600} --csv \
