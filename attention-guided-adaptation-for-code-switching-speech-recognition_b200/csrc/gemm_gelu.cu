@@ -10,13 +10,35 @@
 // TMA ring; tcgen05.mma M128 N256 K16 (128 clk each, 96 B/clk of shared-memory operand traffic); the fp32 accumulator is
 // double-buffered in TMEM (2 x 256 columns) so that the 8 epilogue warps (erf costs ~25 instructions per element)
 // work on tile i while the tensor core runs tile i+1; results leave through swizzled staging rows and TMA tile stores.
-// Default variant (kVar 2): clusters of two CTAs issue ONE tcgen05.mma.cta_group::2 M256 N256 K16 per K step — each CTA
-// stages its own 128 rows of A and HALF (128 rows) of the W tile, so the shared-memory traffic per SM drops from
-// 96 + 96 B/clk (operand reads + TMA fills, over the 128 B/clk an SM has) to 64 + 64 B/clk, and the ring deepens to 5.
+// What bounds it is the L2 -> SM operand stream: the MMA warp spends 46 % of its time waiting for `full` and 3 % waiting
+// for the epilogue (tools/gemm_waits.py), and this kernel, its variants and cuBLAS's 256x256 nvjet kernel all settle at
+// ~36 B/clk per SM of TMA requests out of L2 (~8.7 TB/s chip-wide); FLOP per requested byte decides the rest.  CTAs are
+// therefore clustered and share loads by TMA multicast.  Variants (bit-identical results, profiles/r2_gemm_gelu.md):
+//   1 (default) multicast pair, 256 x 256 per cluster, 128 FLOP/B                      934 TFLOP/s
+//   2 one tcgen05.mma.cta_group::2 M256 N256 per pair, W halves not duplicated, 5 stages   856 - 904 TFLOP/s
+//   3 multicast quad 2 x 2, 256 x 512 per cluster, 171 FLOP/B (cuBLAS's ratio); only 33 four-CTA clusters
+//     (132 of 148 SMs) are co-resident                                                     888 - 898 TFLOP/s
 #include "aga_common.cuh"
 #include "tc_ptx.cuh"
 
 #include <cudaTypedefs.h>
+
+// Debug build (-DAGA_TIMELINE, tools/gemm_waits.py): every CTA adds up the clock64() cycles its producer, MMA and first
+// epilogue warp spend inside their mbarrier waits; 16 int64 slots per CTA in a buffer set with aga_debug_set_gemm_waits().
+#ifdef AGA_TIMELINE
+__device__ long long* g_gemm_waits = nullptr;
+extern "C" __attribute__((visibility("default"))) int aga_debug_set_gemm_waits(long long* p) {
+  return cudaMemcpyToSymbol(g_gemm_waits, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
+#define GW_DECL() long long gw_acc[3] = {0, 0, 0}; const long long gw_t0 = clock64()
+#define GW_WAIT(slot, stmt) do { const long long gw_a = clock64(); stmt; gw_acc[slot] += clock64() - gw_a; } while (0)
+#define GW_STORE(base, n) do { if (g_gemm_waits && lane == 0) { long long* r = g_gemm_waits + (long long)blockIdx.x * 16 + (base); \
+    for (int i_ = 0; i_ < (n); ++i_) r[i_] = gw_acc[i_]; r[n] = clock64() - gw_t0; } } while (0)
+#else
+#define GW_DECL() do { } while (0)
+#define GW_WAIT(slot, stmt) stmt
+#define GW_STORE(base, n) do { } while (0)
+#endif
 
 namespace aga {
 namespace {
@@ -179,14 +201,20 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // that of a 256 x 256 tile (the kernel is L2-bandwidth-bound with 128 x 256 tiles: 1.33 GB per Whisper-small MLP GEMM).
 // kVar 2: the same pairing, but the W halves stay where they land and the leader CTA issues cta_group::2 MMAs over both
 // CTAs' shared memory and TMEM: half the B-operand reads and half the TMA fill bytes per SM.
+// kVar 3: clusters of four CTAs = 2 m-tiles x 2 n-tiles.  CTA (r, c) loads rows [64c, +64) of ITS m-tile's A tile and
+// multicasts them to its row mate, loads rows [128r, +128) of ITS n-tile's W tile and multicasts them to its column mate:
+// 24 KiB from L2 per CTA and K step instead of 32.
 template <int kVar>
 __global__ void __launch_bounds__(kGThreads, 1)
-gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_o, const GArgs a) {
+gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a64,
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h,
+                 const __grid_constant__ CUtensorMap map_o, const GArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr bool kPair = kVar != 0;
+  constexpr bool kPair = kVar != 0;  // any clustered variant
   constexpr bool kTwoSm = kVar == 2;
+  constexpr bool kQuad = kVar == 3;
+  constexpr int kCluster = kQuad ? 4 : (kPair ? 2 : 1);
   constexpr int kNStages = kTwoSm ? kGStages2 : kGStages;
   constexpr int kBStage = kTwoSm ? kBTile / 2 : kBTile;  // bytes of W per stage in THIS CTA
   uint8_t* sA = smem;
@@ -196,20 +224,26 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_mt = (a.M + kTM - 1) / kTM, n_nt = (a.N + kTN - 1) / kTN, n_k = (a.K + kTK - 1) / kTK;
-  // work units: tiles, or (pair of m-tiles, n-tile) per cluster; `rank` selects this CTA's m-tile of the pair
-  const int rank = kPair ? int(cluster_ctarank()) : 0;
-  const int n_units = kPair ? ((n_mt + 1) / 2) * n_nt : n_mt * n_nt;
-  const int unit0 = kPair ? int(blockIdx.x >> 1) : int(blockIdx.x);
-  const int unit_step = kPair ? int(gridDim.x >> 1) : int(gridDim.x);
+  // work units: tiles, (pair of m-tiles, n-tile) per pair, or (pair of m-tiles, pair of n-tiles) per quad;
+  // `rank` (pairs) / `qr`, `qc` (quads) select this CTA's tile of the unit
+  const int crank = kPair ? int(cluster_ctarank()) : 0;
+  const int rank = kQuad ? 0 : crank;
+  const int qr = crank >> 1, qc = crank & 1;
+  const int n_nu = kQuad ? (n_nt + 1) / 2 : n_nt;  // units along n
+  const int n_units = kPair ? ((n_mt + 1) / 2) * n_nu : n_mt * n_nt;
+  const int unit0 = int(blockIdx.x) / kCluster;
+  const int unit_step = int(gridDim.x) / kCluster;
   auto tile_of = [&](int u, int& mt, int& nt) {
-    nt = u % n_nt;  // n fastest: neighbouring CTAs share the A rows in L2
-    mt = kPair ? 2 * (u / n_nt) + rank : u / n_nt;
+    nt = u % n_nu;  // n fastest: neighbouring CTAs share the A rows in L2
+    mt = kPair ? 2 * (u / n_nu) + (kQuad ? qr : rank) : u / n_nu;
+    if (kQuad) nt = 2 * nt + qc;
   };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNStages; ++s) {
-      mbar_init(&sb->full[s], kTwoSm ? 2 : 1);  // two-SM: both CTAs' producers announce their bytes on the leader's barrier
-      mbar_init(&sb->empty[s], kVar == 1 ? 2 : 1);  // multicast pair: both CTAs' MMA warps release a stage (its W half lives in both)
+      mbar_init(&sb->full[s], 1);  // two-SM: the leader's producer announces both CTAs' bytes on its barrier
+      // multicast variants: every CTA that writes into a stage waits for the MMA warps of all CTAs it writes to
+      mbar_init(&sb->empty[s], kVar == 1 ? 2 : (kQuad ? 3 : 1));
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->acc_full[i], 1);
@@ -228,7 +262,7 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   }
   if (warp == kGTmaWarp && lane == 0) {
-    prefetch_tensormap(&map_a);
+    prefetch_tensormap(kQuad ? &map_a64 : &map_a);
     prefetch_tensormap(&map_w);
     prefetch_tensormap(&map_h);
     prefetch_tensormap(&map_o);
@@ -242,21 +276,29 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == kGTmaWarp) {
     // ============================== TMA producer ==============================
     int it = 0;
+    GW_DECL();
     for (int u = unit0; u < n_units; u += unit_step) {
       int mt, nt;
       tile_of(u, mt, nt);
       for (int k = 0; k < n_k; ++k, ++it) {
         const int s = it % kNStages;
-        mbar_wait(&sb->empty[s], ((it / kNStages) & 1) ^ 1);
+        GW_WAIT(0, mbar_wait(&sb->empty[s], ((it / kNStages) & 1) ^ 1));
         if (elect_one()) {
-          if (kTwoSm) {  // own A rows + own half of the W tile, counted on the leader's barrier
+          if (kTwoSm) {  // own A rows + own half of the W tile, counted on the leader's barrier (which expects both CTAs' bytes)
             const uint32_t full_leader = mapa_rank(smem_u32(&sb->full[s]), 0);
-            mbar_arrive_expect_tx_cluster(full_leader, kATile + kBTile / 2);
+            if (rank == 0) mbar_arrive_expect_tx(&sb->full[s], 2 * (kATile + kBTile / 2));
             tma_load_2d_2sm(sA + s * kATile, &map_a, full_leader, k * kTK, mt * kTM);
             tma_load_2d_2sm(sB + s * kBStage, &map_w, full_leader, k * kTK, nt * kTN + rank * (kTN / 2));
             continue;
           }
           mbar_arrive_expect_tx(&sb->full[s], kATile + kBTile);
+          if (kQuad) {  // half of the A tile to the row mates, half of the W tile to the column mates
+            tma_load_2d_multicast(sA + s * kATile + qc * (kATile / 2), &map_a64, &sb->full[s], k * kTK, mt * kTM + qc * (kTM / 2),
+                                  uint16_t(3u << (2 * qr)));
+            tma_load_2d_multicast(sB + s * kBTile + qr * (kBTile / 2), &map_w, &sb->full[s], k * kTK, nt * kTN + qr * (kTN / 2),
+                                  uint16_t(5u << qc));
+            continue;
+          }
           tma_load_2d(sA + s * kATile, &map_a, &sb->full[s], k * kTK, mt * kTM);
           if (kPair) {  // this CTA's half of the W tile (128 of its 256 rows), delivered to both CTAs
             tma_load_2d_multicast(sB + s * kBTile + rank * (kBTile / 2), &map_w, &sb->full[s], k * kTK,
@@ -268,17 +310,19 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
+    GW_STORE(0, 1);  // [0] wait empty, [1] producer total
   } else if (warp == kGMmaWarp) {
     // ============================== MMA issuer ==============================
     constexpr uint32_t idesc = make_idesc_bf16(kTwoSm ? 2 * kTM : kTM, kTN, 0, 0);
     int it = 0, tile_i = 0;
+    GW_DECL();
     for (int u = unit0; u < n_units && !(kTwoSm && rank != 0); u += unit_step, ++tile_i) {  // two-SM: the leader issues for the pair
       const int buf = tile_i & 1;
-      mbar_wait(&sb->acc_empty[buf], ((tile_i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+      GW_WAIT(0, mbar_wait(&sb->acc_empty[buf], ((tile_i >> 1) & 1) ^ 1));  // the epilogue has drained this accumulator
       tc_fence_after();
       for (int k = 0; k < n_k; ++k, ++it) {
         const int s = it % kNStages;
-        mbar_wait(&sb->full[s], (it / kNStages) & 1);
+        GW_WAIT(1, mbar_wait(&sb->full[s], (it / kNStages) & 1));
         tc_fence_after();
         const uint64_t da = make_smem_desc_sw128(smem_u32(sA + s * kATile));
         const uint64_t db = make_smem_desc_sw128(smem_u32(sB + s * kBStage));
@@ -292,13 +336,16 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_commit_2sm(&sb->empty[s], uint16_t(3));
             if (k == n_k - 1) tc_commit_2sm(&sb->acc_full[buf], uint16_t(3));
           } else {
-            if (kPair) tc_commit_multicast(&sb->empty[s], uint16_t(3)); else tc_commit(&sb->empty[s]);
+            if (kQuad) tc_commit_multicast(&sb->empty[s], uint16_t((3u << (2 * qr)) | (5u << qc)));  // self, row mate, column mate
+            else if (kPair) tc_commit_multicast(&sb->empty[s], uint16_t(3));
+            else tc_commit(&sb->empty[s]);
             if (k == n_k - 1) tc_commit(&sb->acc_full[buf]);
           }
         }
         __syncwarp();
       }
     }
+    GW_STORE(2, 2);  // [2] wait acc_empty, [3] wait full, [4] MMA warp total
   } else if (warp >= kGEpiWarp0) {
     // ============================== epilogue: warp = (row quadrant, column half) ==============================
     const int ew = warp - kGEpiWarp0;
@@ -308,6 +355,7 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint8_t* st1 = st0 + kChunkBytes;           // g (mode 0) / dh  (mode 1)
     const uint32_t row0_addr = smem_u32(st0 + lane * 128), row1_addr = smem_u32(st1 + lane * 128);
     int tile_i = 0, hph = 0;
+    GW_DECL();
     for (int u = unit0; u < n_units; u += unit_step, ++tile_i) {
       int mt, nt;
       tile_of(u, mt, nt);
@@ -320,14 +368,13 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         sb->bias[ew * 32 + lane] = (a.bias && n < a.N) ? __bfloat162float(a.bias[n]) : 0.f;
         named_bar_sync(1, kEpiWarps * 32);
       }
-      mbar_wait(&sb->acc_full[buf], (tile_i >> 1) & 1);
+      GW_WAIT(0, mbar_wait(&sb->acc_full[buf], (tile_i >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {  // two 64-column chunks per warp
         const int col0 = half * 128 + c * 64;         // column inside the tile
         const int gcol = nt * kTN + col0;
-        if (lane == 0) bulk_wait_group_read0();       // the previous chunk's stores have read the staging rows
-        __syncwarp();
+        GW_WAIT(1, if (lane == 0) bulk_wait_group_read0(); __syncwarp());  // the previous chunk's stores have read the staging rows
         if (a.mode == 1) {
           if (lane == 0) {
             mbar_arrive_expect_tx(&sb->h_ready[ew], kChunkBytes);
@@ -335,9 +382,8 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         uint32_t v[2][32];
-        tmem_ld32(tmem + (lane_base << 16) + buf * kTN + col0, v[0]);
-        tmem_ld32(tmem + (lane_base << 16) + buf * kTN + col0 + 32, v[1]);
-        tmem_wait_ld();
+        GW_WAIT(2, tmem_ld32(tmem + (lane_base << 16) + buf * kTN + col0, v[0]);
+                   tmem_ld32(tmem + (lane_base << 16) + buf * kTN + col0 + 32, v[1]); tmem_wait_ld());
         if (c == 1) {  // both chunks of this warp are in registers: hand the accumulator back
           tc_fence_before();
           __syncwarp();
@@ -395,6 +441,7 @@ gemm_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     if (lane == 0) bulk_wait_group_read0();
+    if (ew == 0) GW_STORE(5, 3);  // [5] wait acc_full, [6] wait store-read, [7] TMEM loads, [8] epilogue warp total
   }
   tc_fence_before();
   __syncthreads();
@@ -432,9 +479,37 @@ int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, 
 }
 
 #ifndef AGA_GEMM_VARIANT
-#define AGA_GEMM_VARIANT 2
+#define AGA_GEMM_VARIANT 1
 #endif
-int g_gemm_variant = AGA_GEMM_VARIANT;  // 0 single CTA, 1 multicast pair, 2 two-SM MMA (see the kernel's comment)
+int g_gemm_variant = AGA_GEMM_VARIANT;  // 0 single CTA, 1 multicast pair, 2 two-SM MMA, 3 multicast quad (see the kernel's comment)
+
+// how many 4-CTA clusters of the quad kernel the device can hold at once (GPC boundaries decide; 0 = cannot launch)
+int quad_clusters() {
+  static const int n = []() {
+    if (cudaFuncSetAttribute(gemm_gelu_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64);
+    cfg.blockDim = dim3(kGThreads);
+    cfg.dynamicSmemBytes = kGSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int c = 0;
+    if (cudaOccupancyMaxActiveClusters(&c, gemm_gelu_kernel<3>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return c;
+  }();
+  return n;
+}
 
 }  // namespace
 }  // namespace aga
@@ -444,9 +519,10 @@ using namespace aga;
 // measurement hook (tools/bench_gemm_gelu.py): choose the kernel variant for M >= 256; returns the previous one
 extern "C" __attribute__((visibility("default"))) int aga_debug_set_gemm_variant(int variant) {
   const int prev = g_gemm_variant;
-  if (variant >= 0 && variant <= 2) g_gemm_variant = variant;
+  if (variant >= 0 && variant <= 3) g_gemm_variant = variant;
   return prev;
 }
+extern "C" __attribute__((visibility("default"))) int aga_debug_gemm_quad_clusters() { return quad_clusters(); }
 
 // mode 0: h (M,N) = bf16(a (M,K) @ w (N,K)^T + bias (N)),  out (M,N) = bf16(gelu(h));  h is an OUTPUT
 // mode 1: out (M,N) = bf16(bf16(a @ w^T) * gelu'(h));                                   h is an INPUT, bias ignored
@@ -458,9 +534,10 @@ extern "C" int aga_gemm_gelu(const void* a, const void* w, const void* bias, voi
                         reinterpret_cast<uintptr_t>(out);
   if (all & 15) return AGA_ERR_UNSUPPORTED;
   if (M > 2147483647LL) return AGA_ERR_UNSUPPORTED;
-  CUtensorMap ma, mw, mh, mo;
+  CUtensorMap ma, ma64, mw, mh, mo;
   int st;
   if ((st = make_map_2d(&ma, a, M, K, K, kTM)) != AGA_OK) return st;
+  if ((st = make_map_2d(&ma64, a, M, K, K, kTM / 2)) != AGA_OK) return st;  // quads fetch A tiles as two 64-row halves
   if ((st = make_map_2d(&mw, w, N, K, K, kTN / 2)) != AGA_OK) return st;  // W tiles arrive as two 128-row halves
   if ((st = make_map_2d(&mh, h, M, N, N, 32)) != AGA_OK) return st;
   if ((st = make_map_2d(&mo, out, M, N, N, 32)) != AGA_OK) return st;
@@ -473,29 +550,31 @@ extern "C" int aga_gemm_gelu(const void* a, const void* w, const void* bias, voi
   const int n_mt = int((M + kTM - 1) / kTM), n_nt = (N + kTN - 1) / kTN;
   if (n_mt >= 2 && g_gemm_variant != 0) {
     const bool two_sm = g_gemm_variant == 2;
-    const int n_units = ((n_mt + 1) / 2) * n_nt;
-    const int n_clusters = std::max(1, std::min(n_units, n_sm / 2));
-    auto kern = two_sm ? gemm_gelu_kernel<2> : gemm_gelu_kernel<1>;
+    const bool quad = g_gemm_variant == 3 && n_nt >= 2 && quad_clusters() > 0;
+    const int csize = quad ? 4 : 2;
+    const int n_units = ((n_mt + 1) / 2) * (quad ? (n_nt + 1) / 2 : n_nt);
+    const int n_clusters = std::max(1, std::min(n_units, quad ? quad_clusters() : n_sm / 2));
+    auto kern = quad ? gemm_gelu_kernel<3> : (two_sm ? gemm_gelu_kernel<2> : gemm_gelu_kernel<1>);
     const size_t smem_bytes = two_sm ? kGSmemBytes2 : kGSmemBytes;
     AGA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(2 * n_clusters));
+    cfg.gridDim = dim3(unsigned(csize * n_clusters));
     cfg.blockDim = dim3(kGThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = unsigned(csize);
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AGA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mw, mh, mo, ga));
+    AGA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, ma64, mw, mh, mo, ga));
     AGA_AFTER_LAUNCH();
     return AGA_OK;
   }
   AGA_CUDA_TRY(cudaFuncSetAttribute(gemm_gelu_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemBytes)));
-  gemm_gelu_kernel<0><<<std::min(n_mt * n_nt, n_sm), kGThreads, kGSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mw, mh, mo, ga);
+  gemm_gelu_kernel<0><<<std::min(n_mt * n_nt, n_sm), kGThreads, kGSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, ma64, mw, mh, mo, ga);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }

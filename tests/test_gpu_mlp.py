@@ -34,6 +34,30 @@ def test_gemm_gelu_forward_and_backward_epilogues(M, K, N):
     torch.testing.assert_close(dh.float(), dh_ref.float(), rtol=2e-2, atol=2e-2 * scale)
 
 
+@pytest.mark.parametrize("M,K,N", [(24000, 768, 3072), (1100, 768, 3072 - 256), (300, 1024, 4096 + 8)])
+def test_gemm_gelu_cluster_variants_agree_bit_for_bit(M, K, N):
+    """The clustered variants of the kernel (multicast pair, two-SM MMA, multicast quad) differ only in how operand tiles
+    reach shared memory: every accumulator sees the same products in the same order, so h, gelu(h) and dh are identical.
+    Odd tile counts along M and N exercise the zero-filled / clipped mates of a cluster."""
+    import ctypes
+    from aga_b200 import ops, _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    x, w1, b1, g = _mk(M, K, N, M + N + 1)
+    w2t = (torch.randn(N, K, generator=g) / N ** 0.5).bfloat16().cuda()
+    dy = torch.randn(M, K, generator=g).bfloat16().cuda()
+    prev = lib.aga_debug_set_gemm_variant(1)
+    try:
+        h1, a1 = ops.gemm_gelu_fwd(x, w1, b1)
+        d1 = ops.gemm_gelu_bwd(dy, w2t, h1)
+        for variant in (2, 3, 0):
+            lib.aga_debug_set_gemm_variant(variant)
+            h, act = ops.gemm_gelu_fwd(x, w1, b1)
+            d = ops.gemm_gelu_bwd(dy, w2t, h1)
+            assert torch.equal(h, h1) and torch.equal(act, a1) and torch.equal(d, d1), f"variant {variant}"
+    finally:
+        lib.aga_debug_set_gemm_variant(prev)
+
+
 def test_mlp_residual_node_matches_reference_expression():
     from aga_b200 import ops
     M, D = 3000, 768

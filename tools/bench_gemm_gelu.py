@@ -22,7 +22,20 @@ def main():
     dy = torch.randn(M, K, generator=g).bfloat16().cuda()
     h = F.linear(x, w1, b1)
     fl = 2.0 * M * K * N
+    from aga_b200 import _lib
+    import ctypes
+    lib = ctypes.CDLL(os.environ.get("LD_PRELOAD") or _lib.LIB_PATH)  # the instance the extension's calls resolve to
+    ref_g = F.gelu(h.float()).bfloat16()
     with torch.no_grad():
+        print("quad clusters resident:", lib.aga_debug_gemm_quad_clusters())
+        for variant, name in ((1, "multicast pair"), (2, "two-SM MMA"), (3, "multicast quad")):
+            lib.aga_debug_set_gemm_variant(variant)
+            hh, gg = ops.gemm_gelu_fwd(x, w1, b1)
+            err = (gg.float() - ref_g.float()).abs().max().item()
+            t = graph_time(lambda: ops.gemm_gelu_fwd(x, w1, b1))
+            print(f"fwd fused [{name:14s}]: {t * 1e3:7.1f} us  {fl / t / 1e9:7.1f} TFLOP/s   max|g - ref| {err:.3e}")
+            t = graph_time(lambda: ops.gemm_gelu_bwd(dy, w2t, h))
+            print(f"bwd fused [{name:14s}]: {t * 1e3:7.1f} us  {fl / t / 1e9:7.1f} TFLOP/s")
         t = graph_time(lambda: ops.gemm_gelu_fwd(x, w1, b1))
         print(f"fwd fused   : {t * 1e3:7.1f} us  {fl / t / 1e9:7.1f} TFLOP/s")
         t = graph_time(lambda: F.gelu(F.linear(x, w1, b1)))
