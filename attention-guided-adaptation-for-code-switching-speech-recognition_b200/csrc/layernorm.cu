@@ -95,6 +95,14 @@ template <int V> __device__ __forceinline__ void load_f32(const float* p, float 
   }
 }
 
+template <int V> __device__ __forceinline__ void load_smem_f32(const float* p, float (&v)[V]) {
+#pragma unroll
+  for (int q = 0; q < V / 4; ++q) {
+    const float4 t = *(reinterpret_cast<const float4*>(p) + q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+
 // lane l owns columns {32*V*c + V*l .. + V-1 : c < NC}
 template <typename T> __device__ __forceinline__ float round_to(float v);
 template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
@@ -254,6 +262,129 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t 
   }
 }
 
+
+// The parameter-gradient variants (trainable adapter LayerNorms) carry 2-3 fp32 accumulators per owned column
+// (72 registers at D = 768), which leaves ONE 8-warp CTA per SM: with the loads of a row issued from registers that is
+// 24 KiB in flight per SM and 2.9 TB/s (ncu, round 2).  Here every lane streams its 16-byte pieces of the next kStages-1
+// rows into a private shared-memory ring with cp.async (no barriers: a lane only reads back what it copied itself), so
+// ~100 KiB per SM are in flight whatever the register budget.  The row is read from the ring twice (sums, then dx) instead of
+// being held unpacked in registers, which fits 12 warps beside the accumulators without spills.  One persistent CTA per SM.
+template <int kBytes>
+__device__ __forceinline__ void cp_async_piece(uint32_t smem_dst, const void* gsrc) {
+  if constexpr (kBytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_dst), "l"(gsrc), "n"(kBytes) : "memory");
+}
+template <typename T, int V, int NC, int kParamGrads, int kStages, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+layernorm_bwd_ring_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t rows, const float* __restrict__ gamma,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ dres,
+                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
+  static_assert(kParamGrads >= 1, "the ring kernel is the parameter-gradient path");
+  constexpr int D = NC * 32 * V;
+  constexpr int kRowBytes = D * int(sizeof(T));
+  constexpr int kPiece = V * int(sizeof(T));
+  extern __shared__ __align__(16) uint8_t ln_ring[];
+  __shared__ __align__(16) float sg[D];             // gamma
+  __shared__ float red[kWarps][32 * V];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_t = dres ? 3 : 2;  // row buffers per stage: x, dy (, dres)
+  uint8_t* my = ln_ring + size_t(warp) * kStages * n_t * kRowBytes;
+  const uint32_t my_addr = static_cast<uint32_t>(__cvta_generic_to_shared(my));
+  for (int i = threadIdx.x; i < D; i += kWarps * 32) sg[i] = gamma[i];
+  float ag[NC][V], ab[NC][V], ax[kParamGrads == 2 ? NC : 1][V];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      ag[c][e] = ab[c][e] = 0.f;
+      if (kParamGrads == 2) ax[c][e] = 0.f;
+    }
+  const int64_t stride = int64_t(gridDim.x) * kWarps;
+  const int64_t row0 = int64_t(blockIdx.x) * kWarps + warp;
+  auto issue = [&](int64_t row, int stage) {
+    if (row < rows) {
+      const uint32_t base = my_addr + uint32_t(stage * n_t * kRowBytes);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int off = (c * 32 * V + lane * V);
+        cp_async_piece<kPiece>(base + off * int(sizeof(T)), x + row * D + off);
+        cp_async_piece<kPiece>(base + kRowBytes + off * int(sizeof(T)), dy + row * D + off);
+        if (dres) cp_async_piece<kPiece>(base + 2 * kRowBytes + off * int(sizeof(T)), dres + row * D + off);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per row slot, empty past the end: uniform counting
+  };
+#pragma unroll
+  for (int p = 0; p < kStages - 1; ++p) issue(row0 + p * stride, p);
+  __syncthreads();  // gamma is in shared memory
+  int it = 0;
+  for (int64_t row = row0; row < rows; row += stride, ++it) {
+    issue(row + (kStages - 1) * stride, (it + kStages - 1) % kStages);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+    const float mu = mean[row], rs = rstd[row];
+    const T* sx = reinterpret_cast<const T*>(my + size_t(it % kStages) * n_t * kRowBytes);
+    const T* sdy = sx + D;
+    // pass 1 over the staged row: the two row sums and the parameter-gradient accumulators; nothing of the row is kept
+    // in registers (the accumulators need them), pass 2 reads the row from shared memory again
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float xv[V], dv[V], g[V];
+      Vec<T, V>::load(sx + c * 32 * V + lane * V, xv);
+      Vec<T, V>::load(sdy + c * 32 * V + lane * V, dv);
+      load_smem_f32<V>(sg + c * 32 * V + lane * V, g);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float xh = (xv[e] - mu) * rs;
+        const float gy = dv[e] * g[e];
+        s1 += gy;
+        s2 = fmaf(gy, xh, s2);
+        ag[c][e] = fmaf(dv[e], xh, ag[c][e]);
+        ab[c][e] += dv[e];
+      }
+    }
+    const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float xv[V], dv[V], g[V], o[V];
+      Vec<T, V>::load(sx + c * 32 * V + lane * V, xv);
+      Vec<T, V>::load(sdy + c * 32 * V + lane * V, dv);
+      load_smem_f32<V>(sg + c * 32 * V + lane * V, g);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float xh = (xv[e] - mu) * rs;
+        o[e] = rs * (dv[e] * g[e] - c1 - xh * c2);
+        if (kParamGrads == 2) ax[c][e] += o[e];
+      }
+      if (dres) {
+        float r[V];
+        Vec<T, V>::load(sdy + D + c * 32 * V + lane * V, r);
+#pragma unroll
+        for (int e = 0; e < V; ++e) o[e] = round_to<T>(o[e]) + r[e];
+      }
+      Vec<T, V>::store(dx + row * D + c * 32 * V + lane * V, o);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 1
+  for (int pass = 0; pass < (kParamGrads == 2 ? 3 : 2); ++pass) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+        red[warp][lane * V + e] = pass == 0 ? ag[c][e] : (pass == 1 ? ab[c][e] : ax[kParamGrads == 2 ? c : 0][e]);
+      __syncthreads();
+      for (int col = threadIdx.x; col < 32 * V; col += kWarps * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += red[w][col];
+        atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum)) + c * 32 * V + col, t);
+      }
+    }
+  }
+}
+
 template <typename T, int V, int NC>
 int launch_fwd(const void* x, const void* residual, int64_t rows, const float* gamma, const float* beta, float eps, void* y,
                void* sum_out, float* mean, float* rstd, cudaStream_t s) {
@@ -280,6 +411,31 @@ int launch_bwd(const void* dy, const void* x, int64_t rows, const float* gamma, 
       AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, D * sizeof(float), s));
       AGA_CUDA_TRY(cudaMemsetAsync(dbeta, 0, D * sizeof(float), s));
       if (dxsum) AGA_CUDA_TRY(cudaMemsetAsync(dxsum, 0, D * sizeof(float), s));
+    }
+    // ring kernel: 12 warps x 4 stages of (x, dy[, dres]) rows; rows too long for that keep the register-fed kernel
+    constexpr int kRingWarps = 12, kRing = 4;
+    const size_t ring_bytes = size_t(kRingWarps) * kRing * (dres ? 3 : 2) * D * sizeof(T);
+    constexpr size_t kRingStatic = (size_t(D) + kRingWarps * 32 * V) * sizeof(float);
+    if (ring_bytes + kRingStatic <= 224 * 1024 && rows >= 4096) {
+      static const int n_sm = []() {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n > 0 ? n : 148;
+      }();
+      const unsigned rgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>((rows + kRingWarps - 1) / kRingWarps, n_sm)));
+      if (dxsum) {
+        auto kern = layernorm_bwd_ring_kernel<T, V, NC, 2, kRing, kRingWarps>;
+        AGA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(224 * 1024 - kRingStatic)));
+        kern<<<rgrid, kRingWarps * 32, ring_bytes, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows, gamma, mean, rstd,
+                                                       static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, dxsum);
+      } else {
+        auto kern = layernorm_bwd_ring_kernel<T, V, NC, 1, kRing, kRingWarps>;
+        AGA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(224 * 1024 - kRingStatic)));
+        kern<<<rgrid, kRingWarps * 32, ring_bytes, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows, gamma, mean, rstd,
+                                                       static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, nullptr);
+      }
+      AGA_AFTER_LAUNCH();
+      return AGA_OK;
     }
     if (dxsum) {
       layernorm_bwd_kernel<T, V, NC, 2><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), rows,

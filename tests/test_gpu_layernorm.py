@@ -81,7 +81,7 @@ def _adapter_ref(x, w1, b1, w2, b2, gamma, beta):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("shape,D", [((4, 300), 768), ((2, 64), 1024)])
+@pytest.mark.parametrize("shape,D", [((4, 300), 768), ((2, 64), 1024), ((6, 1000), 768)])  # the last one runs the ring kernel
 def test_adapter_layer_norm_matches_reference_expression(A, dtype, tol, shape, D):
     g = torch.Generator().manual_seed(D + shape[1])
     Bn = D // 4
@@ -172,18 +172,19 @@ def test_linear_residual_matches_linear_plus_add(A, dtype, tol, rows, N, K, with
     assert torch.equal(r.grad, do)
 
 
+@pytest.mark.parametrize("rows_shape", [(3, 50), (5, 1000)])  # 5000 rows: the cp.async ring kernel with the residual gradient
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
-def test_layer_norm_residual_backward_adds_residual_gradient(A, dtype, tol):
+def test_layer_norm_residual_backward_adds_residual_gradient(A, dtype, tol, rows_shape):
     """ops.layer_norm_residual: (LN(x), x) whose backward adds the residual path's gradient inside the LayerNorm-backward
     kernel == layer_norm(x) used next to x itself (`x = x + f(ln(x))`, whisper/model.py:231-242)."""
     from aga_b200 import ops
     g = torch.Generator().manual_seed(5)
     D = 768
-    x0 = torch.randn(3, 50, D, generator=g).to(dtype).cuda()
+    x0 = torch.randn(*rows_shape, D, generator=g).to(dtype).cuda()
     w = (1 + 0.1 * torch.randn(D, generator=g)).cuda().requires_grad_()
     b = (0.1 * torch.randn(D, generator=g)).cuda().requires_grad_()
     m = torch.randn(D, D, generator=g).to(dtype).cuda() / D ** 0.5
-    do = torch.randn(3, 50, D, generator=g).to(dtype).cuda()
+    do = torch.randn(*rows_shape, D, generator=g).to(dtype).cuda()
     res = {}
     for fused in (True, False):
         x = x0.clone().requires_grad_()
