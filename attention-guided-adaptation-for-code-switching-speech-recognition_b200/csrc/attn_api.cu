@@ -68,7 +68,7 @@ extern "C" int aga_attn_fwd_workspace_bytes(const aga_attn_params* p, size_t* by
   if (!bytes) return AGA_ERR_INVALID_ARGUMENT;
   // (the CUDA-core forward serves kv_len too — the fp32 decoding step; the backward and the guided epilogue are tcgen05 only)
   if ((p->impl == AGA_ATTN_TCGEN05 || p->guided_part) && !use_tc(*p)) return AGA_ERR_UNSUPPORTED;
-  *bytes = use_tc(*p) ? attn_tc_fwd_workspace(*p) : 0;
+  *bytes = (use_tc(*p) && !attn_decode_shape(*p)) ? attn_tc_fwd_workspace(*p) : 0;
   return AGA_OK;
 }
 
@@ -78,6 +78,7 @@ extern "C" int aga_attn_fwd(const aga_attn_params* p, void* workspace, size_t wo
   if (st != AGA_OK) return st;
   if (need > 0 && (!workspace || workspace_bytes < need)) return AGA_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (attn_decode_shape(*p)) return attn_decode_fwd(*p, s);
   // (the tcgen05 kernel never skips key tile 0, so columns below 128 are always written by the kernel itself)
   const bool kernel_writes_all = use_tc(*p) && p->export_hi <= 128;
   if (p->causal && p->export_kind != AGA_EXPORT_NONE && !kernel_writes_all) {

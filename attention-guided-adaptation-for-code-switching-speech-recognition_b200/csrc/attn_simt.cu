@@ -14,6 +14,8 @@
 #include "aga_common.cuh"
 #include "attn_common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace aga {
 namespace {
 
@@ -266,6 +268,169 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_simt_kernel(const SimtArgs 
   }
 }
 
+// ------------------------------------------------------------------------------------------ single-query forward
+// Decoding step (Tq = 1 per hypothesis; whisper_decoder.py:172-244 recomputes the whole prefix instead): one query
+// row against Tk keys is far too little work for a query-tile kernel — 12 CTAs walk 1500 keys serially (12.4 us on
+// the tcgen05 kernel).  Here a CLUSTER of kDecSplit CTAs shares one (hypothesis, head): each CTA scans its slice of
+// the keys (a lane owns a key for the dot product, then a pair of output columns for P V), the per-CTA
+// (max, sum, out[64]) partials are combined by rank 0 through distributed shared memory.  No workspace, no atomics.
+constexpr int kDecSplit = 8;
+constexpr int kDecWarps = 4;
+
+// two adjacent elements as they sit in memory; converted only where they are used, so that a batch of loads is issued
+// back to back (a conversion right behind each load makes every load wait for the one before it)
+__device__ __forceinline__ float2 load2_raw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ uint32_t load2_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ float2 cvt2(float2 r) { return r; }
+__device__ __forceinline__ float2 cvt2(uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); }
+template <typename T> struct Raw2;
+template <> struct Raw2<float> { using type = float2; static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); } };
+template <> struct Raw2<__nv_bfloat16> { using type = uint32_t; static __device__ __forceinline__ uint32_t zero() { return 0u; } };
+template <typename T> __device__ __forceinline__ float dot64(const float (&q)[kD], const T* __restrict__ row);
+template <> __device__ __forceinline__ float dot64<float>(const float (&q)[kD], const float* __restrict__ row) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < kD / 4; ++c) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + c);
+    acc = fmaf(q[4 * c], v.x, acc); acc = fmaf(q[4 * c + 1], v.y, acc);
+    acc = fmaf(q[4 * c + 2], v.z, acc); acc = fmaf(q[4 * c + 3], v.w, acc);
+  }
+  return acc;
+}
+template <> __device__ __forceinline__ float dot64<__nv_bfloat16>(const float (&q)[kD], const __nv_bfloat16* __restrict__ row) {
+  uint4 raw[kD / 8];
+#pragma unroll
+  for (int c = 0; c < kD / 8; ++c) raw[c] = __ldg(reinterpret_cast<const uint4*>(row) + c);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < kD / 8; ++c) {
+    const uint32_t w[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = cvt2(w[e]);
+      acc = fmaf(q[8 * c + 2 * e], f.x, acc);
+      acc = fmaf(q[8 * c + 2 * e + 1], f.y, acc);
+    }
+  }
+  return acc;
+}
+__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T>
+__global__ void __cluster_dims__(kDecSplit, 1, 1) __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const SimtArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ __align__(16) float qs[kD];
+  __shared__ float wpart[kDecWarps][kD + 2];  // per warp: out[64], max, sum
+  __shared__ __align__(8) float cpart[kD + 2];  // this CTA's partial, read by rank 0 of the cluster
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rank = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const T* qg = static_cast<const T*>(a.q) + b * a.q_sb + h * kD;
+  const T* kg = static_cast<const T*>(a.k) + b * a.k_sb + h * kD;
+  const T* vg = static_cast<const T*>(a.v) + b * a.v_sb + h * kD;
+  if (threadIdx.x < kD) qs[threadIdx.x] = to_f32(qg[threadIdx.x]) * kScale;  // the exact 1/8 goes onto q
+  __syncthreads();
+  float q[kD];
+#pragma unroll
+  for (int c = 0; c < kD / 4; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(qs + 4 * c);
+    q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+  }
+  const int Tk = a.kv_len ? max(1, min(__ldg(a.kv_len), a.Tk)) : a.Tk;
+  const int chunk = ((Tk + kDecSplit - 1) / kDecSplit + 31) & ~31;  // whole 32-key blocks per CTA
+  const int k0 = rank * chunk, k1 = min(Tk, k0 + chunk);
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int kb = k0 + 32 * warp; kb < k1; kb += 32 * kDecWarps) {
+    const int key = kb + lane;
+    // the block's V rows (lane = column pair) are requested BEFORE the scores exist: all of a block's global loads are
+    // in flight together (a load per key behind the softmax cost 32 exposed latencies per block: 16.5 us per call)
+    typename Raw2<T>::type vv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      vv[j] = kb + j < k1 ? load2_raw(vg + int64_t(kb + j) * a.v_st + 2 * lane) : Raw2<T>::zero();
+    const float sv = key < k1 ? dot64<T>(q, kg + int64_t(key) * a.k_st) : -INFINITY;
+    const float m_new = fmaxf(m, warp_max_f(sv));  // finite: the block holds at least one key
+    const float alpha = exp2f((m - m_new) * kLog2e);
+    const float pv = exp2f((sv - m_new) * kLog2e);  // 0 for the lanes past the end
+    l = l * alpha + warp_sum(pv);
+    o0 *= alpha;
+    o1 *= alpha;
+    m = m_new;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, pv, j);  // 0 past the end
+      const float2 v2 = cvt2(vv[j]);
+      o0 = fmaf(pj, v2.x, o0);
+      o1 = fmaf(pj, v2.y, o1);
+    }
+  }
+  wpart[warp][2 * lane] = o0;
+  wpart[warp][2 * lane + 1] = o1;
+  if (lane == 0) {
+    wpart[warp][kD] = m;
+    wpart[warp][kD + 1] = l;
+  }
+  __syncthreads();
+  if (warp == 0) {  // the CTA's partial
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) M = fmaxf(M, wpart[w][kD]);
+    float L = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) {
+      const float mw = wpart[w][kD];
+      const float sc = mw == -INFINITY ? 0.f : exp2f((mw - M) * kLog2e);
+      L = fmaf(sc, wpart[w][kD + 1], L);
+      a0 = fmaf(sc, wpart[w][2 * lane], a0);
+      a1 = fmaf(sc, wpart[w][2 * lane + 1], a1);
+    }
+    cpart[2 * lane] = a0;
+    cpart[2 * lane + 1] = a1;
+    if (lane == 0) {
+      cpart[kD] = M;
+      cpart[kD + 1] = L;
+    }
+  }
+  cluster.sync();
+  if (rank == 0 && warp == 0) {
+    // all remote reads first (a distributed-shared-memory load is ~200 clk: 40 of them one after the other were the
+    // kernel's fixed cost), then the combination in registers
+    float mr[kDecSplit], lr[kDecSplit], p0[kDecSplit], p1[kDecSplit];
+#pragma unroll
+    for (int r = 0; r < kDecSplit; ++r) {
+      const float* pr = cluster.map_shared_rank(cpart, r);
+      mr[r] = pr[kD];
+      lr[r] = pr[kD + 1];
+      const float2 t = *reinterpret_cast<const float2*>(pr + 2 * lane);
+      p0[r] = t.x;
+      p1[r] = t.y;
+    }
+    float M = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < kDecSplit; ++r) M = fmaxf(M, mr[r]);
+    float L = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < kDecSplit; ++r) {
+      const float sc = mr[r] == -INFINITY ? 0.f : exp2f((mr[r] - M) * kLog2e);
+      L = fmaf(sc, lr[r], L);
+      a0 = fmaf(sc, p0[r], a0);
+      a1 = fmaf(sc, p1[r], a1);
+    }
+    const float inv = 1.0f / L;
+    store2(static_cast<T*>(a.out) + b * a.o_sb + h * kD + 2 * lane, a0 * inv, a1 * inv);
+    if (lane == 0 && a.lse) a.lse[int64_t(b) * a.H + h] = M + logf(L);
+  }
+  cluster.sync();  // nobody leaves while rank 0 may still read its shared memory
+}
+
 // probs export = exp(exported logits - lse), in place (-inf -> 0)
 __global__ void __launch_bounds__(256) export_logits_to_probs_kernel(const SimtArgs a) {
   const int W = a.export_hi - a.export_lo;
@@ -502,6 +667,18 @@ int launch_bwd(const aga_attn_bwd_params& bp, float* delta, cudaStream_t s) {
 
 }  // namespace
 
+bool attn_decode_shape(const aga_attn_params& p) {
+  return p.Tq == 1 && !p.causal && (p.export_kind == AGA_EXPORT_NONE || !p.export_buf) && !p.guided_part &&
+         p.impl != AGA_ATTN_TCGEN05;
+}
+int attn_decode_fwd(const aga_attn_params& p, cudaStream_t s) {
+  SimtArgs a = make_args(p);
+  const dim3 grid(kDecSplit, p.H, p.B);
+  if (p.dtype == AGA_BF16) attn_decode_kernel<__nv_bfloat16><<<grid, kDecWarps * 32, 0, s>>>(a);
+  else attn_decode_kernel<float><<<grid, kDecWarps * 32, 0, s>>>(a);
+  AGA_AFTER_LAUNCH();
+  return AGA_OK;
+}
 int attn_simt_fwd(const aga_attn_params& p, cudaStream_t s) {
   return p.dtype == AGA_BF16 ? launch_fwd<__nv_bfloat16>(p, s) : launch_fwd<float>(p, s);
 }

@@ -168,7 +168,7 @@ class GraphedGreedyDecoder:
     The reference recomputes the whole prefix on every step and copies every layer's map to the host
     (whisper_decoder.py:172-244); the KV-cached ``forward_one_step`` of this package is O(t) per token but still ~200
     kernel launches from Python (8-9 ms per token).  Here every shape is static: the self-attention K / V live in
-    preallocated (n, max_len, D) buffers, the position is a DEVICE scalar (it indexes the positional embedding, the cache
+    preallocated (n, max_len, 2D) [K | V] buffers, the position is a DEVICE scalar (it indexes the positional embedding, the cache
     row to write and — as ``kv_len`` — the number of keys the attention kernel may see), the arg-max token is fed back
     on the device.  ``prefill`` runs the prompt through the normal KV-cached path; ``decode(n)`` replays the captured
     step n times with no host round trip and returns (token ids (n_hyp, n), their log-probabilities).
@@ -193,21 +193,30 @@ class GraphedGreedyDecoder:
         dev, dt = self.memory.device, self.memory.dtype
         D = dec.token_embedding.embedding_dim
         t0 = prompt.size(1)
-        self.k = [torch.zeros(self.n, self.max_len, D, device=dev, dtype=dt) for _ in dec.blocks]
-        self.v = [torch.zeros(self.n, self.max_len, D, device=dev, dtype=dt) for _ in dec.blocks]
-        self.cross = []
-        for layer, (k, v, kc, vc) in enumerate(cache):
-            self.k[layer][:, :t0] = k
-            self.v[layer][:, :t0] = v
-            self.cross.append((kc.contiguous(), vc.contiguous()))
         best = logp.max(dim=-1)
-        self.tok = best.indices.view(self.n, 1).clone()       # token at position t0 (not yet in the cache)
-        self.tok_logp = best.values.clone()
-        self.pos = torch.full((1,), t0, dtype=torch.int64, device=dev)
-        self.out_tok = torch.zeros(self.n, self.max_len, dtype=torch.int64, device=dev)
-        self.out_logp = torch.zeros(self.n, self.max_len, dtype=torch.float32, device=dev)
-        self.n_out = torch.zeros((1,), dtype=torch.int64, device=dev)
-        self.graph = None
+        if self.graph is None:
+            self.kv = [torch.zeros(self.n, self.max_len, 2 * D, device=dev, dtype=dt) for _ in dec.blocks]  # [K | V] rows
+            self.cross = [(kc.contiguous(), vc.contiguous()) for (_, _, kc, vc) in cache]
+            self.tok = torch.zeros(self.n, 1, dtype=torch.int64, device=dev)
+            self.tok_logp = torch.zeros(self.n, dtype=torch.float32, device=dev)
+            self.pos = torch.zeros((1,), dtype=torch.int64, device=dev)
+            self.out_tok = torch.zeros(self.n, self.max_len, dtype=torch.int64, device=dev)
+            self.out_logp = torch.zeros(self.n, self.max_len, dtype=torch.float32, device=dev)
+            self.n_out = torch.zeros((1,), dtype=torch.int64, device=dev)
+        # a captured step stays valid across prompts: every buffer it reads is refilled IN PLACE
+        for layer, (k, v, kc, vc) in enumerate(cache):
+            self.kv[layer].zero_()
+            self.kv[layer][:, :t0, :D] = k
+            self.kv[layer][:, :t0, D:] = v
+            if self.graph is not None:
+                self.cross[layer][0].copy_(kc)
+                self.cross[layer][1].copy_(vc)
+        self.tok.copy_(best.indices.view(self.n, 1))          # token at position t0 (not yet in the cache)
+        self.tok_logp.copy_(best.values)
+        self.pos.fill_(t0)
+        self.out_tok.zero_()
+        self.out_logp.zero_()
+        self.n_out.zero_()
 
     def _step(self) -> None:
         """Consume ``self.tok`` at position ``self.pos``; leave the next token in ``self.tok``."""
@@ -218,7 +227,7 @@ class GraphedGreedyDecoder:
         x = x.to(self.memory.dtype)
         kv_len = (self.pos + 1).to(torch.int32)
         for layer, block in enumerate(dec.blocks):
-            x = block.step_static(x, self.k[layer], self.v[layer], self.pos, kv_len, self.cross[layer])
+            x = block.step_static(x, self.kv[layer], self.pos, kv_len, self.cross[layer])
         logp = torch.log_softmax(dec.vocab_logits(dec.ln(x[:, -1])), dim=-1)
         best = logp.max(dim=-1)
         self.tok.copy_(best.indices.view(self.n, 1))
@@ -233,7 +242,7 @@ class GraphedGreedyDecoder:
         if self.graph is None:
             self.dec._set_export(False)
             state = [t.clone() for t in (self.tok, self.tok_logp, self.pos, self.n_out, self.out_tok, self.out_logp)]
-            kv = [t.clone() for t in self.k + self.v]
+            kv = [t.clone() for t in self.kv]
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -246,7 +255,7 @@ class GraphedGreedyDecoder:
             # the warm-up step and the capture changed nothing that matters, but restore the exact pre-step state anyway
             for dst, src in zip((self.tok, self.tok_logp, self.pos, self.n_out, self.out_tok, self.out_logp), state):
                 dst.copy_(src)
-            for dst, src in zip(self.k + self.v, kv):
+            for dst, src in zip(self.kv, kv):
                 dst.copy_(src)
         total = int(self.n_out.item()) + n_tokens
         if int(self.pos.item()) + n_tokens > self.max_len:

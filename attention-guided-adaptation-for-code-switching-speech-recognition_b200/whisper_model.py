@@ -101,9 +101,15 @@ class Linear(nn.Linear):
         return F.linear(x, cast_param(self, "_w_cast", self.weight, x.dtype), cast_param(self, "_b_cast", self.bias, x.dtype))
 
 
+def _no_grad_needed(*params) -> bool:
+    """True when none of ``params`` will receive a gradient from this call: frozen (--freeze_param), or autograd is off
+    (inference / decoding under ``torch.no_grad()``)."""
+    return (not torch.is_grad_enabled()) or not any(p is not None and p.requires_grad for p in params)
+
+
 def linear_plus_residual(lin: "Linear", x: Tensor, residual: Tensor) -> Tensor:
     """``residual + lin(x)``; for a frozen Linear on a CUDA device the add rides the GEMM (ops.linear_residual)."""
-    frozen = not (lin.weight.requires_grad or (lin.bias is not None and lin.bias.requires_grad))
+    frozen = _no_grad_needed(lin.weight, lin.bias)
     if not (_native(x) and frozen):
         return residual + lin(x)
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
@@ -176,7 +182,7 @@ class MultiHeadAttention(nn.Module):
     #      result, one packed gradient -> one dgrad GEMM.  Same arithmetic as three F.linear calls on row blocks of
     #      the concatenated weight.
     def _frozen(self) -> bool:
-        return not any(p.requires_grad for p in (self.query.weight, self.key.weight, self.value.weight))
+        return _no_grad_needed(self.query.weight, self.query.bias, self.key.weight, self.value.weight, self.value.bias)
 
     def _packed_weights(self, dtype: torch.dtype, with_q: bool):
         mods = ([self.query] if with_q else []) + [self.key, self.value]
@@ -210,7 +216,7 @@ class MultiHeadAttention(nn.Module):
         return (self.out(out) if residual is None else linear_plus_residual(self.out, out, residual)), second
 
     def step(self, x: Tensor, past_k: Optional[Tensor] = None, past_v: Optional[Tensor] = None,
-             cross_kv: Optional[Tuple[Tensor, Tensor]] = None):
+             cross_kv: Optional[Tuple[Tensor, Tensor]] = None, residual: Optional[Tensor] = None):
         """Incremental attention for KV-cached decoding (the reference recomputes the whole prefix
         on every step, whisper_decoder.py:172-244).  Self attention (``cross_kv`` None): the keys / values of the new
         tokens ``x`` (n, t_new, D) are appended to ``past_k`` / ``past_v`` and returned; cross attention: the K / V of
@@ -219,7 +225,7 @@ class MultiHeadAttention(nn.Module):
         if cross_kv is not None:
             k, v = cross_kv
             out, _, _ = ops.qkv_attention(q, k, v, self.n_head, causal=False, impl=self.impl)
-            return self.out(out)
+            return self.out(out) if residual is None else linear_plus_residual(self.out, out, residual)
         k, v = self.key(x), self.value(x)
         if past_k is not None:
             k, v = torch.cat([past_k, k], dim=1), torch.cat([past_v, v], dim=1)
@@ -228,15 +234,18 @@ class MultiHeadAttention(nn.Module):
         out, _, _ = ops.qkv_attention(q, k, v, self.n_head, causal=q.shape[1] > 1, impl=self.impl)
         return self.out(out), k, v
 
-    def step_static(self, x: Tensor, k_buf: Tensor, v_buf: Tensor, pos: Tensor, kv_len: Tensor) -> Tensor:
-        """One decoding step with STATIC shapes (graph-capturable): x (n, 1, D) is the new token's activation, ``k_buf`` /
-        ``v_buf`` (n, max_len, D) the preallocated self-attention cache, ``pos`` (1,) int64 the row the new key / value go
-        to, ``kv_len`` = pos + 1 as the device scalar the attention kernel masks with.  Same arithmetic as ``step``."""
-        q = self.query(x)
-        k_buf.index_copy_(1, pos, self.key(x))
-        v_buf.index_copy_(1, pos, self.value(x))
-        out, _, _ = ops.qkv_attention(q, k_buf, v_buf, self.n_head, causal=False, impl=self.impl, kv_len=kv_len)
-        return self.out(out)
+    def step_static(self, x: Tensor, kv_buf: Tensor, pos: Tensor, kv_len: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+        """One decoding step with STATIC shapes (graph-capturable): x (n, 1, D) is the new token's activation, ``kv_buf``
+        (n, max_len, 2D) = [K | V] the preallocated self-attention cache, ``pos`` (1,) int64 the row the new key / value go
+        to, ``kv_len`` = pos + 1 as the device scalar the attention kernel masks with.  Same arithmetic as ``step``, in
+        four launches: one [q|k|v] GEMM, one cache-row write, the attention kernel on the packed cache, the output
+        projection with ``residual`` (if given) added inside the GEMM."""
+        D = x.shape[-1]
+        w, b = self._packed_weights(x.dtype, True)
+        qkv = F.linear(x, w, b)
+        kv_buf.index_copy_(1, pos, qkv[..., D:])
+        out, _, _ = ops.qkv_attention_packed(kv_buf, self.n_head, q=qkv[..., :D], causal=False, impl=self.impl, kv_len=kv_len)
+        return self.out(out) if residual is None else linear_plus_residual(self.out, out, residual)
 
     def qkv_attention(self, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor] = None):
         # The only mask the reference ever passes is TextDecoder.mask = triu(-inf) (whisper/model.py:322,103),
@@ -316,13 +325,14 @@ class ResidualAttentionBlock(nn.Module):
             x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x, (k, v, kc, vc)
 
-    def step_static(self, x: Tensor, k_buf: Tensor, v_buf: Tensor, pos: Tensor, kv_len: Tensor, cross_kv: Tuple[Tensor, Tensor]):
-        """``step`` on preallocated caches (see MultiHeadAttention.step_static): no shape depends on the position."""
-        x = x + self.attn.step_static(self.attn_ln(x), k_buf, v_buf, pos, kv_len)
+    def step_static(self, x: Tensor, kv_buf: Tensor, pos: Tensor, kv_len: Tensor, cross_kv: Tuple[Tensor, Tensor]):
+        """``step`` on a preallocated [K | V] cache (see MultiHeadAttention.step_static): no shape depends on the position,
+        and every residual add rides a GEMM (17 launches per block instead of 27)."""
+        x = self.attn.step_static(self.attn_ln(x), kv_buf, pos, kv_len, residual=x)
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)
-        x = x + self.cross_attn.step(self.cross_attn_ln(x), cross_kv=cross_kv)
-        x = x + self.mlp(self.mlp_ln(x))
+        x = self.cross_attn.step(self.cross_attn_ln(x), cross_kv=cross_kv, residual=x)
+        x = self._mlp_residual(self.mlp_ln(x), x)
         if self.adapter_flag:
             x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
         return x
@@ -331,9 +341,12 @@ class ResidualAttentionBlock(nn.Module):
         """``x + self.mlp(y)`` (whisper/model.py:242).  Frozen bf16 MLP on a CUDA device: two GEMMs and nothing else — the
         exact GELU in the first GEMM's epilogue (tcgen05, csrc/gemm_gelu.cu), the residual add in the second's."""
         l1, l2 = self.mlp[0], self.mlp[2]
-        frozen = not any(p.requires_grad for p in (l1.weight, l1.bias, l2.weight, l2.bias))
+        frozen = _no_grad_needed(l1.weight, l1.bias, l2.weight, l2.bias)
         dt = torch.get_autocast_dtype("cuda") if (y.is_cuda and torch.is_autocast_enabled("cuda")) else y.dtype
-        if not (_native(y) and frozen and dt == torch.bfloat16):
+        rows = y.numel() // y.shape[-1]
+        # (a handful of rows — a decoding step — is latency-bound: 12 CTAs of the tiled kernel walk K serially, 13.8 us
+        # against 8 us for cuBLAS's GEMV-shaped kernel + GELU)
+        if not (_native(y) and frozen and dt == torch.bfloat16 and rows >= 64):
             return linear_plus_residual(l2, self.mlp[1](l1(y)), x)
         w2 = cast_param(l2, "_w_cast", l2.weight, dt)
         c = self.__dict__.get("_w2t")
@@ -347,6 +360,13 @@ class ResidualAttentionBlock(nn.Module):
     def _adapter_ln(adapter: "Adapter", ln: "LayerNorm", x: Tensor) -> Tensor:
         """``ln(adapter(x))`` = LN(x + W2 gelu(W1 x)) as one fused autograd node."""
         m = adapter.model
+        if not torch.is_grad_enabled() and x.dtype != m[0].weight.dtype:
+            # inference / decoding: the low-precision copies of the adapter weights are made once, not per call
+            # (8 cast kernels per decoder block and token otherwise)
+            return ops.adapter_layer_norm(x, *(cast_param(lin, slot, t, x.dtype) for lin, slot, t in
+                                               ((m[0], "_w_cast", m[0].weight), (m[0], "_b_cast", m[0].bias),
+                                                (m[2], "_w_cast", m[2].weight), (m[2], "_b_cast", m[2].bias))),
+                                          ln.weight, ln.bias, ln.eps)
         return ops.adapter_layer_norm(x, m[0].weight, m[0].bias, m[2].weight, m[2].bias, ln.weight, ln.bias, ln.eps)
 
 

@@ -122,3 +122,41 @@ def test_attention_strided_qkv_views(A):
     out, _, _ = A.qkv_attention(q, k, v, H, impl="simt")
     o_ref, _, _ = O.qkv_attention(q.cpu().numpy(), k.cpu().numpy(), v.cpu().numpy(), H, False)
     np.testing.assert_allclose(out.cpu().numpy(), o_ref, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("B,H,Tk,kv_len", [(1, 12, 1500, None), (3, 2, 1, None), (2, 3, 33, None), (1, 12, 128, 7),
+                                           (2, 2, 448, 300), (1, 1, 200, 200), (5, 6, 131, 1)])
+def test_single_query_decode_kernel_vs_oracle(A, dtype, tol, B, H, Tk, kv_len):
+    """Tq = 1 (a KV-cached decoding step) takes the cluster-split single-query kernel: same out / lse as the oracle on the
+    keys that exist, through packed [K | V] cache rows and a q that is a column slice of a packed projection; its
+    gradients (the ordinary backward kernels work from out and lse) match as well."""
+    rng = np.random.default_rng(Tk * 7 + B)
+    D = H * 64
+    qkv = torch.from_numpy(rng.standard_normal((B, 1, 3 * D)).astype(np.float32)).cuda().to(dtype)
+    cache = torch.from_numpy(rng.standard_normal((B, Tk, 2 * D)).astype(np.float32)).cuda().to(dtype)
+    q, k, v = qkv[..., :D], cache[..., :D], cache[..., D:]
+    n = Tk if kv_len is None else kv_len
+    kl = None if kv_len is None else torch.tensor(kv_len, dtype=torch.int32, device="cuda")
+    out, lse, _ = A.qkv_attention(q, k, v, H, kv_len=kl)
+    ref_out, ref_qk, _ = O.qkv_attention(q.float().cpu().numpy(), k[:, :n].float().cpu().numpy(), v[:, :n].float().cpu().numpy(), H, False)
+    mx = ref_qk.max(-1)
+    ref_lse = mx + np.log(np.exp(ref_qk - mx[..., None]).sum(-1))
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref_out, rtol=tol, atol=tol)
+    np.testing.assert_allclose(lse.cpu().numpy(), ref_lse, rtol=1e-5, atol=1e-5)
+    if kv_len is None:  # same numbers as the query-tile kernel of the same dtype on a 2-row problem's first row
+        q2 = torch.cat([q, q], dim=1).contiguous()
+        out2, lse2, _ = A.qkv_attention(q2, k, v, H, impl="simt")
+        torch.testing.assert_close(out.float(), out2[:, :1].float(), rtol=tol, atol=tol)
+        torch.testing.assert_close(lse, lse2[..., :1], rtol=1e-5, atol=1e-5)
+        qg, kg, vg = (t.detach().clone().contiguous().requires_grad_() for t in (q, k, v))
+        o, _, _ = A.qkv_attention(qg, kg, vg, H)
+        do = torch.from_numpy(rng.standard_normal((B, 1, D)).astype(np.float32)).cuda().to(dtype)
+        o.backward(do)
+        q2g, k2g, v2g = (t.detach().clone().contiguous().requires_grad_() for t in (q2, k, v))
+        o2, _, _ = A.qkv_attention(q2g, k2g, v2g, H, impl="simt")
+        o2.backward(torch.cat([do, torch.zeros_like(do)], dim=1))
+        gtol = 1e-4 if dtype == torch.float32 else 2e-2
+        torch.testing.assert_close(qg.grad.float(), q2g.grad[:, :1].float(), rtol=gtol, atol=gtol)
+        torch.testing.assert_close(kg.grad.float(), k2g.grad.float(), rtol=gtol, atol=gtol)
+        torch.testing.assert_close(vg.grad.float(), v2g.grad.float(), rtol=gtol, atol=gtol)
