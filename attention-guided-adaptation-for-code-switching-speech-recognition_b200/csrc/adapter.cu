@@ -88,14 +88,14 @@ gelu_bwd_colsum_kernel(const T* __restrict__ dg, const T* __restrict__ h, int64_
 }
 
 template <typename T>
-int launch(const void* dg, const void* h, int64_t rows, int cols, void* dh, float* colsum, cudaStream_t s) {
+int launch(const void* dg, const void* h, int64_t rows, int cols, void* dh, float* colsum, bool accumulate, cudaStream_t s) {
   constexpr int V = Pack<T>::kVec;
   const int tpr = cols / V;
   if (cols % V != 0 || tpr > kThreads) return AGA_ERR_UNSUPPORTED;
   const int rpb = kThreads / tpr;
   const int64_t want = (rows + rpb - 1) / rpb;
   const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 4)));
-  AGA_CUDA_TRY(cudaMemsetAsync(colsum, 0, size_t(cols) * sizeof(float), s));
+  if (!accumulate) AGA_CUDA_TRY(cudaMemsetAsync(colsum, 0, size_t(cols) * sizeof(float), s));
   gelu_bwd_colsum_kernel<T><<<grid, kThreads, size_t(rpb) * cols * sizeof(float), s>>>(
       static_cast<const T*>(dg), static_cast<const T*>(h), rows, cols, tpr, rpb, static_cast<T*>(dh), colsum);
   AGA_AFTER_LAUNCH();
@@ -105,14 +105,25 @@ int launch(const void* dg, const void* h, int64_t rows, int cols, void* dh, floa
 }  // namespace
 }  // namespace aga
 
-extern "C" int aga_gelu_bwd_colsum(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh,
-                                   float* colsum, void* stream) {
+namespace {
+int gelu_bwd_colsum_impl(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh, float* colsum, bool accumulate,
+                         void* stream) {
   using namespace aga;
   if (!dg || !h || !dh || !colsum || rows <= 0 || cols <= 0) return AGA_ERR_INVALID_ARGUMENT;
   if (dtype != AGA_F32 && dtype != AGA_BF16) return AGA_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(dg) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dh)) & 15)
     return AGA_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return dtype == AGA_BF16 ? launch<__nv_bfloat16>(dg, h, rows, cols, dh, colsum, s)
-                           : launch<float>(dg, h, rows, cols, dh, colsum, s);
+  return dtype == AGA_BF16 ? launch<__nv_bfloat16>(dg, h, rows, cols, dh, colsum, accumulate, s)
+                           : launch<float>(dg, h, rows, cols, dh, colsum, accumulate, s);
+}
+}  // namespace
+
+extern "C" int aga_gelu_bwd_colsum(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh,
+                                   float* colsum, void* stream) {
+  return gelu_bwd_colsum_impl(dg, h, dtype, rows, cols, dh, colsum, false, stream);
+}
+extern "C" int aga_gelu_bwd_colsum_acc(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh,
+                                       float* colsum, void* stream) {
+  return gelu_bwd_colsum_impl(dg, h, dtype, rows, cols, dh, colsum, true, stream);
 }

@@ -398,14 +398,16 @@ int launch_fwd(const void* x, const void* residual, int64_t rows, const float* g
 
 template <typename T, int V, int NC>
 int launch_bwd(const void* dy, const void* x, int64_t rows, const float* gamma, const float* mean, const float* rstd,
-               const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, cudaStream_t s) {
+               const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, bool accumulate, cudaStream_t s) {
   constexpr int D = NC * 32 * V;
   const int64_t want = (rows + kLnWarps - 1) / kLnWarps;
   const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 4)));
   if (dgamma && dbeta) {
     // one memset node when the caller packed the parameter-gradient rows back to back (ops.py does)
     const bool packed = dbeta == dgamma + D && (!dxsum || dxsum == dbeta + D);
-    if (packed) {
+    if (accumulate) {
+      // the caller cleared the rows (one clear for a whole step's worth of them): nothing to do here
+    } else if (packed) {
       AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, (dxsum ? 3 : 2) * D * sizeof(float), s));
     } else {
       AGA_CUDA_TRY(cudaMemsetAsync(dgamma, 0, D * sizeof(float), s));
@@ -488,9 +490,10 @@ extern "C" int aga_layernorm_fwd(const void* x, const void* residual, int dtype,
   AGA_LN_DISPATCH(launch_fwd, x, residual, rows, gamma, beta, eps, y, sum_out, mean, rstd, s)
 }
 
-extern "C" int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
-                                 const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma,
-                                 float* dbeta, float* dxsum, void* stream) {
+namespace {
+int layernorm_bwd_impl(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* mean,
+                       const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, bool accumulate,
+                       void* stream) {
   int st = check(x, dx, dtype, rows, D);
   if (st != AGA_OK) return st;
   if (!dy || !gamma || !mean || !rstd || ((dgamma == nullptr) != (dbeta == nullptr)) || (dxsum && !dgamma))
@@ -498,5 +501,17 @@ extern "C" int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dres)) & 15) return AGA_ERR_UNSUPPORTED;
   const bool bf16 = dtype == AGA_BF16;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  AGA_LN_DISPATCH(launch_bwd, dy, x, rows, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, s)
+  AGA_LN_DISPATCH(launch_bwd, dy, x, rows, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, accumulate, s)
+}
+}  // namespace
+
+extern "C" int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
+                                 const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma,
+                                 float* dbeta, float* dxsum, void* stream) {
+  return layernorm_bwd_impl(dy, x, dtype, rows, D, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, false, stream);
+}
+extern "C" int aga_layernorm_bwd_acc(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
+                                     const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma,
+                                     float* dbeta, float* dxsum, void* stream) {
+  return layernorm_bwd_impl(dy, x, dtype, rows, D, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, true, stream);
 }

@@ -158,31 +158,37 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> layernorm_fwd(const Tensor& x2, const
 }
 
 std::tuple<Tensor, Tensor> layernorm_bwd(const Tensor& dy2, const Tensor& s2, const Tensor& gamma, const Tensor& mean,
-                                         const Tensor& rstd, bool need_params, bool need_dxsum, const optional<Tensor>& dres2) {
+                                         const Tensor& rstd, bool need_params, bool need_dxsum, const optional<Tensor>& dres2,
+                                         const optional<Tensor>& pg_zeroed) {
   need_cuda(s2, "x");
   c10::cuda::CUDAGuard guard(s2.device());
   const int64_t rows = s2.size(0), D = s2.size(1);
   Tensor dx = at::empty_like(s2);
   Tensor pg;  // rows: dgamma, dbeta (, dxsum): one buffer, cleared by the library with a single memset
   float *dg = nullptr, *db = nullptr, *dxs = nullptr;
+  // pg_zeroed: a (2 or 3, D) fp32 slice of the caller's once-per-step cleared arena -> the _acc entry point, no memset node
+  const bool acc = need_params && pg_zeroed.has_value() && pg_zeroed->defined();
   if (need_params) {
-    pg = at::empty({need_dxsum ? 3 : 2, D}, s2.options().dtype(at::kFloat));
+    pg = acc ? *pg_zeroed : at::empty({need_dxsum ? 3 : 2, D}, s2.options().dtype(at::kFloat));
+    TORCH_CHECK(pg.is_contiguous() && pg.scalar_type() == at::kFloat && pg.numel() == (need_dxsum ? 3 : 2) * D, "bad pg_zeroed");
     dg = pg.data_ptr<float>();
     db = dg + D;
     dxs = need_dxsum ? dg + 2 * D : nullptr;
   }
-  check(aga_layernorm_bwd(dy2.data_ptr(), s2.data_ptr(), dtype_of(s2), rows, int(D), gamma.data_ptr<float>(), mean.data_ptr<float>(),
+  check((acc ? aga_layernorm_bwd_acc : aga_layernorm_bwd)(dy2.data_ptr(), s2.data_ptr(), dtype_of(s2), rows, int(D), gamma.data_ptr<float>(), mean.data_ptr<float>(),
                           rstd.data_ptr<float>(), ptr(dres2), dx.data_ptr(), dg, db, dxs, stream_of(s2)),
         "aga_layernorm_bwd");
   return {dx, pg.defined() ? pg : at::empty({0}, s2.options().dtype(at::kFloat))};
 }
 
-std::tuple<Tensor, Tensor> gelu_bwd_colsum(const Tensor& dg, const Tensor& h) {
+std::tuple<Tensor, Tensor> gelu_bwd_colsum(const Tensor& dg, const Tensor& h, const optional<Tensor>& colsum_zeroed) {
   need_cuda(h, "h");
   c10::cuda::CUDAGuard guard(h.device());
   Tensor dh = at::empty_like(h);
-  Tensor colsum = at::empty({h.size(1)}, h.options().dtype(at::kFloat));
-  check(aga_gelu_bwd_colsum(dg.data_ptr(), h.data_ptr(), dtype_of(h), h.size(0), int(h.size(1)), dh.data_ptr(),
+  const bool acc = colsum_zeroed.has_value() && colsum_zeroed->defined();
+  Tensor colsum = acc ? *colsum_zeroed : at::empty({h.size(1)}, h.options().dtype(at::kFloat));
+  TORCH_CHECK(colsum.is_contiguous() && colsum.scalar_type() == at::kFloat && colsum.numel() == h.size(1), "bad colsum_zeroed");
+  check((acc ? aga_gelu_bwd_colsum_acc : aga_gelu_bwd_colsum)(dg.data_ptr(), h.data_ptr(), dtype_of(h), h.size(0), int(h.size(1)), dh.data_ptr(),
                             colsum.data_ptr<float>(), stream_of(h)),
         "aga_gelu_bwd_colsum");
   return {dh, colsum};
@@ -301,9 +307,9 @@ TORCH_LIBRARY(aga, m) {
         "Tensor(b!) dk, Tensor(c!) dv, int n_head, bool causal, int kind, int lo, int hi, Tensor? head_sel, int impl, Tensor? kv_len, "
         "Tensor? guided_pattern, Tensor? d_part, bool guided_early) -> ()");
   m.def("layernorm_fwd(Tensor x, Tensor? residual, Tensor gamma, Tensor beta, float eps, bool want_sum) -> (Tensor, Tensor, Tensor, Tensor)");
-  m.def("layernorm_bwd(Tensor dy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool need_params, bool need_dxsum, Tensor? dres) "
-        "-> (Tensor, Tensor)");
-  m.def("gelu_bwd_colsum(Tensor dg, Tensor h) -> (Tensor, Tensor)");
+  m.def("layernorm_bwd(Tensor dy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool need_params, bool need_dxsum, Tensor? dres, "
+        "Tensor? pg_zeroed) -> (Tensor, Tensor)");
+  m.def("gelu_bwd_colsum(Tensor dg, Tensor h, Tensor? colsum_zeroed) -> (Tensor, Tensor)");
   m.def("linear_residual(Tensor x, Tensor w, bool w_kn, Tensor? bias, Tensor residual, Tensor ws) -> Tensor");
   m.def("gemm_gelu_fwd(Tensor x, Tensor w, Tensor? bias) -> (Tensor, Tensor)");
   m.def("gemm_gelu_bwd(Tensor dy, Tensor w_t, Tensor h) -> Tensor");

@@ -100,6 +100,9 @@ class FlatGradBucket:
         self._accumulate, self._sync = bool(accumulate), bool(sync)
         for p in self.params:
             p.grad = None
+        if self.flat.is_cuda:
+            from . import ops
+            ops.ZeroArena.of(self.flat.device).reset()  # one clear for all the small atomically-accumulated outputs of this pass
         for c, (p0, p1, _, _) in enumerate(self.chunk_bounds):
             self._pending[c] = p1 - p0
             self._launched[c] = False
@@ -165,6 +168,9 @@ class FlatGradBucket:
         for c in range(self.n_chunks):
             self._flush_chunk(c)
         self.wait()
+        if self.flat.is_cuda:
+            from . import ops
+            ops.ZeroArena.of(self.flat.device).disarm()
 
     # kept for callers of the round-1 interface: one gather, one all-reduce
     def gather_(self) -> None:
@@ -173,6 +179,9 @@ class FlatGradBucket:
         for c in range(self.n_chunks):
             self._flush_chunk(c)
         self._sync = sync
+        if self.flat.is_cuda:
+            from . import ops
+            ops.ZeroArena.of(self.flat.device).disarm()
 
     def all_reduce_mean_async(self) -> None:
         """SUM over ranks then / world of the whole buffer (== DDP's gradient averaging).  Returns immediately."""

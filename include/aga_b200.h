@@ -208,6 +208,12 @@ AGA_API int aga_layernorm_fwd(const void* x, const void* residual, int dtype, in
 AGA_API int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
                       const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                       float* dxsum, void* stream);
+/* The same, but dgamma / dbeta / dxsum are ADDED TO: the caller zero-initialises them.  A training step has ~100 of these
+ * small outputs; carving them out of one buffer that is cleared once per step removes one memset node (and the
+ * dependency bubble behind it) per call from the captured step. */
+AGA_API int aga_layernorm_bwd_acc(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
+                      const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                      float* dxsum, void* stream);
 
 /* Backward of the Adapter's GELU fused with the bias gradient of its first Linear (W/model.py:181-194,
  * Adapter.model = Linear -> GELU -> Linear).  dh = dg * gelu'(h) (exact erf form, fp32 math,
@@ -215,6 +221,9 @@ AGA_API int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t 
  *   dg, h, dh : (rows, cols) contiguous, dtype AGA_F32 or AGA_BF16, 16-byte aligned; cols a multiple of 16 B / sizeof(dtype)
  *   colsum    : (cols) fp32, OVERWRITTEN */
 AGA_API int aga_gelu_bwd_colsum(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh, float* colsum,
+                        void* stream);
+/* The same with colsum ADDED TO (zero-initialised by the caller; see aga_layernorm_bwd_acc). */
+AGA_API int aga_gelu_bwd_colsum_acc(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh, float* colsum,
                         void* stream);
 
 /* Label-smoothing cross entropy + accuracy on the vocabulary logits, kept in the GEMM's dtype.
