@@ -194,6 +194,37 @@ std::tuple<Tensor, Tensor> gelu_bwd_colsum(const Tensor& dg, const Tensor& h, co
   return {dh, colsum};
 }
 
+// ------------------------------------------------------------------------------------------------ flat optimizer update
+void flat_grad_norm(const Tensor& g, Tensor norm_out, const optional<Tensor>& step, const optional<Tensor>& skipped, Tensor ws) {
+  need_cuda(g, "g");
+  c10::cuda::CUDAGuard guard(g.device());
+  TORCH_CHECK(g.scalar_type() == at::kFloat && g.is_contiguous() && norm_out.scalar_type() == at::kFloat, "flat_grad_norm: fp32");
+  check(aga_flat_grad_norm(g.data_ptr<float>(), g.numel(), norm_out.data_ptr<float>(),
+                           step.has_value() && step->defined() ? step->data_ptr<float>() : nullptr,
+                           skipped.has_value() && skipped->defined() ? skipped->data_ptr<float>() : nullptr, ws.data_ptr(),
+                           size_t(ws.numel()) * ws.element_size(), stream_of(g)),
+        "aga_flat_grad_norm");
+}
+
+void flat_adamw(Tensor p, const Tensor& g, Tensor m, Tensor v, const Tensor& lr, double beta1, double beta2, double eps,
+                double weight_decay, const Tensor& step, const optional<Tensor>& grad_norm, double max_norm,
+                const optional<Tensor>& shadow) {
+  need_cuda(p, "p");
+  c10::cuda::CUDAGuard guard(p.device());
+  TORCH_CHECK(p.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat &&
+                  v.scalar_type() == at::kFloat && lr.scalar_type() == at::kFloat && step.scalar_type() == at::kFloat,
+              "flat_adamw: fp32 buffers and scalars");
+  TORCH_CHECK(p.is_contiguous() && g.is_contiguous() && m.is_contiguous() && v.is_contiguous() && g.numel() == p.numel() &&
+                  m.numel() == p.numel() && v.numel() == p.numel(), "flat_adamw: flat buffers of one length");
+  const bool has_shadow = shadow.has_value() && shadow->defined();
+  if (has_shadow) TORCH_CHECK(shadow->scalar_type() == at::kBFloat16 && shadow->numel() == p.numel() && shadow->is_contiguous(), "flat_adamw: bf16 shadow");
+  check(aga_flat_adamw(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), p.numel(),
+                       lr.data_ptr<float>(), beta1, beta2, eps, weight_decay, step.data_ptr<float>(),
+                       grad_norm.has_value() && grad_norm->defined() ? grad_norm->data_ptr<float>() : nullptr, float(max_norm),
+                       has_shadow ? shadow->data_ptr() : nullptr, stream_of(p)),
+        "aga_flat_adamw");
+}
+
 // ------------------------------------------------------------------------------------------------ GEMMs with epilogues
 Tensor linear_residual(const Tensor& x2, const Tensor& w, bool w_kn, const optional<Tensor>& bias, const Tensor& r2, Tensor ws) {
   need_cuda(x2, "x");
@@ -310,6 +341,9 @@ TORCH_LIBRARY(aga, m) {
   m.def("layernorm_bwd(Tensor dy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool need_params, bool need_dxsum, Tensor? dres, "
         "Tensor? pg_zeroed) -> (Tensor, Tensor)");
   m.def("gelu_bwd_colsum(Tensor dg, Tensor h, Tensor? colsum_zeroed) -> (Tensor, Tensor)");
+  m.def("flat_grad_norm(Tensor g, Tensor(a!) norm_out, Tensor(b!)? step, Tensor(c!)? skipped, Tensor(d!) ws) -> ()");
+  m.def("flat_adamw(Tensor(a!) p, Tensor g, Tensor(b!) m, Tensor(c!) v, Tensor lr, float beta1, float beta2, float eps, float weight_decay, "
+        "Tensor step, Tensor? grad_norm, float max_norm, Tensor(d!)? shadow) -> ()");
   m.def("linear_residual(Tensor x, Tensor w, bool w_kn, Tensor? bias, Tensor residual, Tensor ws) -> Tensor");
   m.def("gemm_gelu_fwd(Tensor x, Tensor w, Tensor? bias) -> (Tensor, Tensor)");
   m.def("gemm_gelu_bwd(Tensor dy, Tensor w_t, Tensor h) -> Tensor");
@@ -328,6 +362,8 @@ TORCH_LIBRARY_IMPL(aga, CUDA, m) {
   m.impl("layernorm_fwd", layernorm_fwd);
   m.impl("layernorm_bwd", layernorm_bwd);
   m.impl("gelu_bwd_colsum", gelu_bwd_colsum);
+  m.impl("flat_grad_norm", flat_grad_norm);
+  m.impl("flat_adamw", flat_adamw);
   m.impl("linear_residual", linear_residual);
   m.impl("gemm_gelu_fwd", gemm_gelu_fwd);
   m.impl("gemm_gelu_bwd", gemm_gelu_bwd);

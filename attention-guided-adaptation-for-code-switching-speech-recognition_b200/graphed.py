@@ -39,8 +39,15 @@ class GuardedUpdate:
         self.skipped_steps = torch.zeros((), dtype=torch.float32, device=dev)
         self.last_norm = torch.zeros((), dtype=torch.float32, device=dev)
         self.fused = _is_fused(optimizer)
+        from .optim import FlatAdamW
+        self.flat = isinstance(optimizer, FlatAdamW)
+        if self.flat:  # norm, skip rule, clip, update and bf16 copies are two launches of the library; it owns the counters
+            self.skipped_steps, self.last_norm = optimizer.skipped, optimizer.grad_norm
 
     def __call__(self) -> None:
+        if self.flat:
+            self.opt.step(max_norm=self.max_grad_norm)
+            return
         total = self.bucket.clip_grad_norm_(self.max_grad_norm)
         self.last_norm.copy_(total)
         bad = (~torch.isfinite(total)).float()

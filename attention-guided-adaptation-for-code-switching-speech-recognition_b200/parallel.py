@@ -108,8 +108,10 @@ class FlatGradBucket:
             self._launched[c] = False
         self._armed = True
         if self.shadow_flat is not None and not accumulate:
-            with torch.no_grad():
-                torch._foreach_copy_(self.shadow_views, [p.detach() for p in self.params])
+            owner = getattr(self, "shadow_owner", None)  # optim.FlatAdamW writes the copies inside its update kernel
+            if owner is None or not owner.shadow_is_fresh():
+                with torch.no_grad():
+                    torch._foreach_copy_(self.shadow_views, [p.detach() for p in self.params])
             for p, v in zip(self.params, self.shadow_views):
                 p._aga_shadow = (p._version, v)
 

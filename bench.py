@@ -57,6 +57,7 @@ def parse_args():
                     help="leave out the recipe's SpecAug (graph-safe device variant; on by default, both arms)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch (reference op sequence) leg on the GPU")
+    ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused) + clip_grad_norm_ instead of optim.FlatAdamW")
     ap.add_argument("--accum-grad", type=int, default=1, help="micro-batches per optimizer step (recipe: 4); a 'step' stays one micro-batch")
     ap.add_argument("--comm-chunks", type=int, default=1, help="gradient all-reduce chunks")
     ap.add_argument("--comm-overlap", action="store_true",
@@ -223,7 +224,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # what THIS arm timed: a bounded sample (cpu_batch utterances, full maps exported as the reference does), one CPU
         # process whatever --gpus says — not the GPU arm's batch
-        "config": workload_config(args, batch=args.cpu_batch, world=1, export="decoder self-attn full (L,B,H,T,T) maps "
+        "config": workload_config(args, batch=args.cpu_batch, world=1, optimizer="AdamW(adapters): torch.optim.AdamW", export="decoder self-attn full (L,B,H,T,T) maps "
                                   "(the reference's export)", note=f"bounded sample of the GPU arm's workload "
                                   f"(batch_per_gpu {args.batch}); CPU port of the reference (oracle/torch_port.py inside the "
                                   "repo's mirror modules), 1 process"),
@@ -237,7 +238,7 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, batch=None, world=None, export="none: guided-loss reduction fused into the decoder self-attention "
+def workload_config(args, batch=None, world=None, optimizer=None, export="none: guided-loss reduction fused into the decoder self-attention "
                     "epilogue (cols 1:3 of the scaled logits)", note=None):
     batch = args.batch if batch is None else batch
     world = args.gpus if world is None else world
@@ -245,7 +246,7 @@ def workload_config(args, batch=None, world=None, export="none: guided-loss redu
                        f"({CONFIGS[args.config]['baseline_config']})",
            "batch_per_gpu": batch, "global_batch": batch * world, "audio_seconds": AUDIO_SECONDS,
            "text_len": args.text_len, "adapters": True, "export": export,
-           "optimizer": "AdamW(adapters)", "parallelism": f"dp{world}", "specaug": bool(args.specaug),
+           "optimizer": optimizer or ("AdamW(adapters): " + ("torch fused" if args.torch_adamw else "flat buffers, clip + update + bf16 copies in one pass")), "parallelism": f"dp{world}", "specaug": bool(args.specaug),
            "accum_grad": args.accum_grad,
            "l2_policy": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush"}
     if note:
@@ -292,8 +293,12 @@ def main():
     model = build_model(args.model, dev, specaug=args.specaug)
     params = [p for p in model.parameters() if p.requires_grad]
     bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16, n_chunks=args.comm_chunks, overlap=args.comm_overlap)
-    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01, fused=True,
-                            capturable=not args.no_graph)
+    if args.torch_adamw:  # stock optimizer chain (multi-tensor norm / clip / fused AdamW / bf16 re-casts), for comparison
+        opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01, fused=True,
+                                capturable=not args.no_graph)
+    else:  # the same update on flat buffers: two launches of the library (csrc/flat_adamw.cu)
+        from aga_b200.optim import FlatAdamW
+        opt = FlatAdamW(bucket, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01)
 
     host = synthetic_batch(args.batch, args.text_len, seed=2022 + rank)
     host = tuple(t.pin_memory() for t in host)

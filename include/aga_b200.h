@@ -226,6 +226,27 @@ AGA_API int aga_gelu_bwd_colsum(const void* dg, const void* h, int dtype, int64_
 AGA_API int aga_gelu_bwd_colsum_acc(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh, float* colsum,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer update of the trainable (adapter) parameters on FLAT buffers.
+ * Replaces the tail of Trainer.train_one_epoch's inner step (espnet2/train/trainer.py:649-716): clip_grad_norm_ over all
+ * trainable parameters, "skip the update when the norm is not finite", torch.optim.AdamW.step() (recipe: optim adamw),
+ * plus the fp32 -> bf16 re-cast of the updated parameters that autocast performs on their next use.
+ *   aga_flat_grad_norm: norm_out[0] = ||g||_2 (fp32, deterministic); then, by the last block, step[0] += 1 when the norm is
+ *     finite, skipped[0] += 1 otherwise (either may be NULL).  workspace: zero-initialised ONCE by the caller, 8-byte aligned,
+ *     aga_flat_grad_norm_workspace_bytes() bytes; left ready for the next call.
+ *   aga_flat_adamw: when grad_norm[0] is finite (or grad_norm is NULL): g' = g * min(1, max_norm / (grad_norm + 1e-6))
+ *     (max_norm <= 0 or grad_norm NULL: no clipping), then torch.optim.AdamW's update with bias corrections for step[0]
+ *     (already advanced), statement for statement the arithmetic of torch's fused kernel; shadow_bf16 (may be NULL) receives
+ *     bf16(p).  A non-finite norm leaves p, m, v, shadow untouched.  p, g, m, v: n fp32, 16-byte aligned; lr, step,
+ *     grad_norm: DEVICE scalars (a captured CUDA graph keeps following an LR schedule that writes lr in place).
+ * ------------------------------------------------------------------------------------------ */
+AGA_API int aga_flat_grad_norm_workspace_bytes(size_t* bytes);
+AGA_API int aga_flat_grad_norm(const float* g, int64_t n, float* norm_out, float* step, float* skipped, void* workspace,
+                       size_t workspace_bytes, void* stream);
+AGA_API int aga_flat_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, double beta1, double beta2,
+                   double eps, double weight_decay, const float* step, const float* grad_norm, float max_norm,
+                   void* shadow_bf16, void* stream);
+
 /* Label-smoothing cross entropy + accuracy on the vocabulary logits, kept in the GEMM's dtype.
  * Replaces `.float()` of the logits (E2/asr/decoder/whisper_decoder.py:164-166), LabelSmoothingLoss.forward
  * (espnet/nets/pytorch_backend/transformer/label_smoothing_loss.py:41-63) and th_accuracy
