@@ -194,6 +194,19 @@ std::tuple<Tensor, Tensor> gelu_bwd_colsum(const Tensor& dg, const Tensor& h, co
   return {dh, colsum};
 }
 
+// ------------------------------------------------------------------------------------------------ adapter weight gradients
+void wgrad(const Tensor& a, const Tensor& b, Tensor out_zeroed, bool transpose_out) {
+  need_cuda(a, "a");
+  c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && out_zeroed.scalar_type() == at::kFloat,
+              "wgrad: bf16 operands, fp32 output");
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && out_zeroed.is_contiguous() &&
+                  a.size(0) == b.size(0) && out_zeroed.numel() == a.size(1) * b.size(1), "wgrad: a (rows, M), b (rows, N), out M*N");
+  check(aga_wgrad_bf16(a.data_ptr(), b.data_ptr(), a.size(0), int(a.size(1)), int(b.size(1)), out_zeroed.data_ptr<float>(),
+                       transpose_out ? 1 : 0, stream_of(a)),
+        "aga_wgrad_bf16");
+}
+
 // ------------------------------------------------------------------------------------------------ flat optimizer update
 void flat_grad_norm(const Tensor& g, Tensor norm_out, const optional<Tensor>& step, const optional<Tensor>& skipped, Tensor ws) {
   need_cuda(g, "g");
@@ -341,6 +354,7 @@ TORCH_LIBRARY(aga, m) {
   m.def("layernorm_bwd(Tensor dy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool need_params, bool need_dxsum, Tensor? dres, "
         "Tensor? pg_zeroed) -> (Tensor, Tensor)");
   m.def("gelu_bwd_colsum(Tensor dg, Tensor h, Tensor? colsum_zeroed) -> (Tensor, Tensor)");
+  m.def("wgrad(Tensor a, Tensor b, Tensor(a!) out_zeroed, bool transpose_out) -> ()");
   m.def("flat_grad_norm(Tensor g, Tensor(a!) norm_out, Tensor(b!)? step, Tensor(c!)? skipped, Tensor(d!) ws) -> ()");
   m.def("flat_adamw(Tensor(a!) p, Tensor g, Tensor(b!) m, Tensor(c!) v, Tensor lr, float beta1, float beta2, float eps, float weight_decay, "
         "Tensor step, Tensor? grad_norm, float max_norm, Tensor(d!)? shadow) -> ()");
@@ -362,6 +376,7 @@ TORCH_LIBRARY_IMPL(aga, CUDA, m) {
   m.impl("layernorm_fwd", layernorm_fwd);
   m.impl("layernorm_bwd", layernorm_bwd);
   m.impl("gelu_bwd_colsum", gelu_bwd_colsum);
+  m.impl("wgrad", wgrad);
   m.impl("flat_grad_norm", flat_grad_norm);
   m.impl("flat_adamw", flat_adamw);
   m.impl("linear_residual", linear_residual);

@@ -415,6 +415,15 @@ class ZeroArena:
             a = cls._by_device[key] = cls(device)
         return a
 
+    def reserve(self, n_floats: int) -> None:
+        """Make room for ``n_floats`` per pass (FlatGradBucket asks for the size of its gradient buffer: the adapter weight
+        gradients live here until the bucket gathers them).  Only before any CUDA graph has captured slices of it."""
+        if n_floats > self.buf.numel():
+            self._retired = getattr(self, "_retired", []) + [self.buf]  # a graph captured earlier may still point into it
+            self.buf = torch.zeros(int(n_floats), dtype=torch.float32, device=self.buf.device)
+            self.off = self.high = 0
+            self.armed = False
+
     def reset(self) -> None:
         """Start of a backward-producing pass (FlatGradBucket.begin_step): clear everything any earlier pass used — its
         consumers (the gradient bucket's copy, the optimizer) are done by now — and start handing out slices.  Captured
@@ -547,6 +556,28 @@ def _wgrad(a_t: torch.Tensor, b: torch.Tensor, dtype: torch.dtype) -> torch.Tens
     return torch.mm(a_t, b, out_dtype=dtype)
 
 
+def adapter_wgrad(a: torch.Tensor, b: torch.Tensor, dtype: torch.dtype, transpose_out: bool = False) -> torch.Tensor:
+    """``a^T @ b`` (or its transpose) in the PARAMETER's dtype: the weight gradient of an adapter Linear, a (rows, M) and
+    b (rows, N) being activations / upstream gradients with rows = batch x frames.  bf16 operands of the adapter shapes
+    go to the tcgen05 kernel of the library (csrc/wgrad_tc.cu: MN-major operands straight from the row-major tensors,
+    K splits combined with atomics into a slice of the step's cleared arena) where it beats cuBLAS's split-K + reduce
+    pair (measured, profiles/r2_wgrad.txt: long contractions, Whisper-small / medium adapter shapes: 16 vs 23 us);
+    everything else is one GEMM whose fp32 accumulators are written as they are."""
+    rows, M = a.shape
+    N = b.shape[1]
+    if (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and dtype == torch.float32 and rows >= 8192
+            and M % 64 == 0 and N % 64 == 0 and max(M, N) <= 1024 and min(M, N) <= 256 and a.is_contiguous() and b.is_contiguous()
+            and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        out = ZeroArena.of(a.device).take(M * N)
+        if out is None:
+            out = torch.zeros(M * N, dtype=torch.float32, device=a.device)
+        tm = _Timed("adapter_wgrad", 2.0 * rows * M * N, a.device)
+        L.torch_ops().wgrad(a, b, out, bool(transpose_out))
+        tm.done(a.device)
+        return out.view(N, M) if transpose_out else out.view(M, N)
+    return _wgrad(b.t(), a, dtype) if transpose_out else _wgrad(a.t(), b, dtype)
+
+
 def gelu_bwd_colsum(dg: torch.Tensor, h: torch.Tensor):
     """(dg * gelu'(h), column sums of that product) in one pass — at::gelu_backward + sum(0) of the Adapter backward."""
     _require_cuda(dg, "dg")
@@ -589,9 +620,9 @@ class _AdapterLayerNormFn(torch.autograd.Function):
         dz2 = _rows(dz.to(x2.dtype), D)
         ds, dgamma, dbeta, db2 = _ln_bwd(dz2, s, g32, mean, rstd, True, need_dxsum=True)
         dg = ds @ w2c                                  # (rows, bottleneck)
-        dw2 = _wgrad(ds.t(), g, dts[2])                # (D, bottleneck)
+        dw2 = adapter_wgrad(ds, g, dts[2])                          # ds^T g: (D, bottleneck)
         dh1, db1 = gelu_bwd_colsum(dg, h1)
-        dw1 = _wgrad(dh1.t(), x2, dts[0])              # (bottleneck, D)
+        dw1 = adapter_wgrad(x2, dh1, dts[0], transpose_out=True)   # (x^T dh1)^T = dh1^T x: (bottleneck, D)
         dx = _linear_residual_raw(dh1, w1c, None, ds, w_kn=True)  # ds + dh1 @ W1: the residual branch's gradient rides the GEMM
         return (dx.view(ctx.shape), dw1, db1.to(dts[1]), dw2, db2.to(dts[3]), dgamma.to(dts[4]), dbeta.to(dts[5]), None)
 

@@ -67,6 +67,9 @@ class FlatGradBucket:
             self.shadow_flat = torch.empty(self.numel, dtype=shadow_dtype, device=dev)
             for p, off in zip(self.params, self.offsets):
                 self.shadow_views.append(self.shadow_flat[off: off + p.numel()].view_as(p))
+        if dev.type == "cuda":
+            from . import ops
+            ops.ZeroArena.of(dev).reserve(self.numel + (1 << 20))  # weight gradients + the small atomically-accumulated outputs
         self.group = process_group
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.overlap = bool(overlap)

@@ -226,6 +226,12 @@ AGA_API int aga_gelu_bwd_colsum(const void* dg, const void* h, int dtype, int64_
 AGA_API int aga_gelu_bwd_colsum_acc(const void* dg, const void* h, int dtype, int64_t rows, int cols, void* dh, float* colsum,
                         void* stream);
 
+/* Weight gradient of an adapter Linear (W/model.py:181-194; autograd of `Linear -> GELU -> Linear` with rows = batch x
+ * frames): out += a^T b on tcgen05, a (rows, M) and b (rows, N) bf16 row-major (16-byte aligned), out fp32 — (M, N) row-major,
+ * or (N, M) when transpose_out — ADDED TO with atomics: the caller zero-initialises it.  M % 64 == 0, N % 64 == 0;
+ * anything else returns AGA_ERR_UNSUPPORTED.  Replaces cuBLAS's split-K kernel + reduce pass. */
+AGA_API int aga_wgrad_bf16(const void* a, const void* b, int64_t rows, int M, int N, float* out, int transpose_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Optimizer update of the trainable (adapter) parameters on FLAT buffers.
  * Replaces the tail of Trainer.train_one_epoch's inner step (espnet2/train/trainer.py:649-716): clip_grad_norm_ over all

@@ -75,3 +75,28 @@ def test_mlp_residual_node_matches_reference_expression():
     torch.testing.assert_close(out.float(), ref.float(), rtol=2e-2, atol=2e-2 * float(ref.detach().float().abs().max()))
     torch.testing.assert_close(xa.grad.float(), xb.grad.float(), rtol=2e-2, atol=2e-2 * float(xb.grad.float().abs().max()))
     assert torch.equal(ra.grad, rb.grad)
+
+
+@pytest.mark.parametrize("rows,M,N", [(24000, 768, 192), (1024, 768, 192), (5000, 1024, 256), (3000, 1280, 320), (513, 128, 64)])
+@pytest.mark.parametrize("transpose_out", [False, True])
+def test_adapter_wgrad_kernel_vs_fp32_matmul(rows, M, N, transpose_out):
+    """csrc/wgrad_tc.cu (a^T b over rows = batch x frames, MN-major tcgen05 operands, K splits combined with atomics)
+    against the fp32 product of the same bf16 operands, in both output layouts; row counts that are not a multiple of
+    the 64-row stage, N = 320 (two MMAs per step: 256 + 64 columns), and accumulation into a non-zero output."""
+    from aga_b200 import ops, _lib
+    g = torch.Generator().manual_seed(rows + M + N)
+    a = torch.randn(rows, M, generator=g).bfloat16().cuda()
+    b = torch.randn(rows, N, generator=g).bfloat16().cuda()
+    ref = a.float().t() @ b.float()
+    ref = ref.t().contiguous() if transpose_out else ref
+    got = ops.adapter_wgrad(a, b, torch.float32, transpose_out=transpose_out)  # (rows < 8192: one cuBLAS GEMM instead)
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4 * scale)
+    got = torch.zeros_like(ref).contiguous()
+    _lib.torch_ops().wgrad(a, b, got.view(-1), transpose_out)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4 * scale)
+    # the C ABI adds into what is there
+    out = torch.full_like(ref, 3.0).contiguous()
+    _lib.torch_ops().wgrad(a, b, out.view(-1), transpose_out)
+    torch.testing.assert_close(out, ref + 3.0, rtol=1e-4, atol=1e-4 * scale)

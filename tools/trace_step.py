@@ -16,7 +16,8 @@ torch.manual_seed(2022)
 model = bench.build_model("small", dev, specaug=True)
 params = [p for p in model.parameters() if p.requires_grad]
 bucket = FlatGradBucket(params, shadow_dtype=torch.bfloat16, n_chunks=1, overlap=False)
-opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01, fused=True, capturable=True)
+from aga_b200.optim import FlatAdamW
+opt = FlatAdamW(bucket, lr=1e-3, betas=(0.9, 0.99), eps=1e-6, weight_decay=0.01)
 resident = tuple(t.to(dev) for t in bench.synthetic_batch(16, 64, seed=2022))
 model.static_shapes = True
 step = GraphedTrainStep(model, opt, bucket, resident, max_grad_norm=1.0, warmup=3)
@@ -46,7 +47,11 @@ def short(name):
 g = collections.OrderedDict()
 prev_end = t0
 gap_total = 0.0
+gaps = []
+prev_name = "(start)"
 for e in one:
+    gaps.append((max(0.0, e.time_range.start - prev_end), prev_name, short(e.name)))
+    prev_name = short(e.name)
     c = g.setdefault(short(e.name), [0, 0.0, 0.0])
     c[0] += 1
     c[1] += e.time_range.end - e.time_range.start
@@ -54,7 +59,7 @@ for e in one:
     c[2] += gap
     gap_total += gap
     prev_end = max(prev_end, e.time_range.end)
-print(f"idle gaps: {gap_total / 1e3:.2f} ms")
+print(f"idle gaps: {gap_total / 1e3:.2f} ms; the largest: " + "; ".join(f"{g_:.1f} us {a} -> {b}" for g_, a, b in sorted(gaps, reverse=True)[:8]))
 print("| kernel | launches | in-graph ms | idle before (ms) |\n|---|---:|---:|---:|")
 for k, v in sorted(g.items(), key=lambda kv: -(kv[1][1]))[:45]:
     print(f"| `{k}` | {v[0]} | {v[1] / 1e3:.3f} | {v[2] / 1e3:.3f} |")
