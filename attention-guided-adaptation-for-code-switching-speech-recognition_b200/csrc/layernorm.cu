@@ -110,11 +110,13 @@ template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { 
 
 // residual != nullptr: normalises s = T(x + residual) (the sum is rounded to the row dtype first, as the reference's
 // `x + self.model(x)` is) and, when sum_out != nullptr, also writes s — the tensor the backward needs.
-template <typename T, int V, int NC>
+template <typename T, int V, int NC, bool kPair>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, int64_t rows, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, T* __restrict__ y, T* __restrict__ sum_out,
-                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ gamma2,
+                     const float* __restrict__ beta2, float eps2, T* __restrict__ y2, float* __restrict__ mean2_out,
+                     float* __restrict__ rstd2_out) {
   constexpr int D = NC * 32 * V;
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
@@ -158,10 +160,46 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, in
 #pragma unroll
     for (int e = 0; e < V; ++e) o[e] = fmaf((v[c][e] - mean) * rstd, g[e], b[e]);
     Vec<T, V>::store(yr + c * 32 * V + lane * V, o);
+    if (kPair) {  // keep the row as it was STORED (rounded to T): that is what a LayerNorm launched next would read
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[c][e] = round_to<T>(o[e]);
+    }
   }
   if (lane == 0) {
     mean_out[row] = mean;
     rstd_out[row] = rstd;
+  }
+  if (!kPair) return;
+  // ---- the pre-LayerNorm of the NEXT residual branch on the row just produced (whisper/model.py:231-246: the adapter's
+  //      post-LN output is at once the residual stream and the input of the next `*_ln`): no second pass over HBM
+  float sum2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int e = 0; e < V; ++e) sum2 += v[c][e];
+  const float m2 = warp_sum(sum2) * (1.0f / D);
+  float sq2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float d = v[c][e] - m2;
+      sq2 = fmaf(d, d, sq2);
+    }
+  const float r2 = rsqrtf(warp_sum(sq2) * (1.0f / D) + eps2);
+  T* y2r = y2 + row * D;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float g[V], b[V], o[V];
+    load_f32<V>(gamma2 + c * 32 * V + lane * V, g);
+    load_f32<V>(beta2 + c * 32 * V + lane * V, b);
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = fmaf((v[c][e] - m2) * r2, g[e], b[e]);
+    Vec<T, V>::store(y2r + c * 32 * V + lane * V, o);
+  }
+  if (lane == 0) {
+    mean2_out[row] = m2;
+    rstd2_out[row] = r2;
   }
 }
 
@@ -387,11 +425,17 @@ layernorm_bwd_ring_kernel(const T* __restrict__ dy, const T* __restrict__ x, int
 
 template <typename T, int V, int NC>
 int launch_fwd(const void* x, const void* residual, int64_t rows, const float* gamma, const float* beta, float eps, void* y,
-               void* sum_out, float* mean, float* rstd, cudaStream_t s) {
+               void* sum_out, float* mean, float* rstd, const float* gamma2, const float* beta2, float eps2, void* y2,
+               float* mean2, float* rstd2, cudaStream_t s) {
   const unsigned grid = unsigned((rows + kLnWarps - 1) / kLnWarps);
-  layernorm_fwd_kernel<T, V, NC><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(residual), rows,
-                                                                 gamma, beta, eps, static_cast<T*>(y), static_cast<T*>(sum_out),
-                                                                 mean, rstd);
+  if (y2)
+    layernorm_fwd_kernel<T, V, NC, true><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(residual), rows,
+                                                                         gamma, beta, eps, static_cast<T*>(y), static_cast<T*>(sum_out),
+                                                                         mean, rstd, gamma2, beta2, eps2, static_cast<T*>(y2), mean2, rstd2);
+  else
+    layernorm_fwd_kernel<T, V, NC, false><<<grid, kLnWarps * 32, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(residual), rows,
+                                                                          gamma, beta, eps, static_cast<T*>(y), static_cast<T*>(sum_out),
+                                                                          mean, rstd, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr);
   AGA_AFTER_LAUNCH();
   return AGA_OK;
 }
@@ -487,7 +531,23 @@ extern "C" int aga_layernorm_fwd(const void* x, const void* residual, int dtype,
   if ((reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(sum_out)) & 15) return AGA_ERR_UNSUPPORTED;
   const bool bf16 = dtype == AGA_BF16;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  AGA_LN_DISPATCH(launch_fwd, x, residual, rows, gamma, beta, eps, y, sum_out, mean, rstd, s)
+  AGA_LN_DISPATCH(launch_fwd, x, residual, rows, gamma, beta, eps, y, sum_out, mean, rstd, nullptr, nullptr, 0.f, nullptr, nullptr,
+                  nullptr, s)
+}
+
+extern "C" int aga_layernorm_pair_fwd(const void* x, const void* residual, int dtype, int64_t rows, int D, const float* gamma,
+                                      const float* beta, float eps, void* y, void* sum_out, float* mean, float* rstd,
+                                      const float* gamma2, const float* beta2, float eps2, void* y2, float* mean2, float* rstd2,
+                                      void* stream) {
+  int st = check(x, y, dtype, rows, D);
+  if (st != AGA_OK) return st;
+  if (!gamma || !beta || !mean || !rstd || (sum_out && !residual) || !gamma2 || !beta2 || !y2 || !mean2 || !rstd2)
+    return AGA_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(sum_out) | reinterpret_cast<uintptr_t>(y2)) & 15)
+    return AGA_ERR_UNSUPPORTED;
+  const bool bf16 = dtype == AGA_BF16;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  AGA_LN_DISPATCH(launch_fwd, x, residual, rows, gamma, beta, eps, y, sum_out, mean, rstd, gamma2, beta2, eps2, y2, mean2, rstd2, s)
 }
 
 namespace {

@@ -157,6 +157,25 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> layernorm_fwd(const Tensor& x2, const
   return {y, s.defined() ? s : x2, mean, rstd};
 }
 
+std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> layernorm_pair_fwd(
+    const Tensor& x2, const optional<Tensor>& residual2, const Tensor& gamma, const Tensor& beta, double eps, bool want_sum,
+    const Tensor& gamma2, const Tensor& beta2, double eps2) {
+  need_cuda(x2, "x");
+  c10::cuda::CUDAGuard guard(x2.device());
+  const int64_t rows = x2.size(0), D = x2.size(1);
+  Tensor y = at::empty_like(x2), y2 = at::empty_like(x2);
+  const bool has_res = residual2.has_value() && residual2->defined();
+  Tensor s = (has_res && want_sum) ? at::empty_like(x2) : Tensor();
+  auto fopt = x2.options().dtype(at::kFloat);
+  Tensor mean = at::empty({rows}, fopt), rstd = at::empty({rows}, fopt), mean2 = at::empty({rows}, fopt), rstd2 = at::empty({rows}, fopt);
+  check(aga_layernorm_pair_fwd(x2.data_ptr(), ptr(residual2), dtype_of(x2), rows, int(D), gamma.data_ptr<float>(),
+                               beta.data_ptr<float>(), float(eps), y.data_ptr(), s.defined() ? s.data_ptr() : nullptr,
+                               mean.data_ptr<float>(), rstd.data_ptr<float>(), gamma2.data_ptr<float>(), beta2.data_ptr<float>(),
+                               float(eps2), y2.data_ptr(), mean2.data_ptr<float>(), rstd2.data_ptr<float>(), stream_of(x2)),
+        "aga_layernorm_pair_fwd");
+  return {y, s.defined() ? s : x2, mean, rstd, y2, mean2, rstd2};
+}
+
 std::tuple<Tensor, Tensor> layernorm_bwd(const Tensor& dy2, const Tensor& s2, const Tensor& gamma, const Tensor& mean,
                                          const Tensor& rstd, bool need_params, bool need_dxsum, const optional<Tensor>& dres2,
                                          const optional<Tensor>& pg_zeroed) {
@@ -351,6 +370,8 @@ TORCH_LIBRARY(aga, m) {
         "Tensor(b!) dk, Tensor(c!) dv, int n_head, bool causal, int kind, int lo, int hi, Tensor? head_sel, int impl, Tensor? kv_len, "
         "Tensor? guided_pattern, Tensor? d_part, bool guided_early) -> ()");
   m.def("layernorm_fwd(Tensor x, Tensor? residual, Tensor gamma, Tensor beta, float eps, bool want_sum) -> (Tensor, Tensor, Tensor, Tensor)");
+  m.def("layernorm_pair_fwd(Tensor x, Tensor? residual, Tensor gamma, Tensor beta, float eps, bool want_sum, Tensor gamma2, "
+        "Tensor beta2, float eps2) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)");
   m.def("layernorm_bwd(Tensor dy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool need_params, bool need_dxsum, Tensor? dres, "
         "Tensor? pg_zeroed) -> (Tensor, Tensor)");
   m.def("gelu_bwd_colsum(Tensor dg, Tensor h, Tensor? colsum_zeroed) -> (Tensor, Tensor)");
@@ -374,6 +395,7 @@ TORCH_LIBRARY_IMPL(aga, CUDA, m) {
   m.impl("attn_fwd", attn_fwd);
   m.impl("attn_bwd", attn_bwd);
   m.impl("layernorm_fwd", layernorm_fwd);
+  m.impl("layernorm_pair_fwd", layernorm_pair_fwd);
   m.impl("layernorm_bwd", layernorm_bwd);
   m.impl("gelu_bwd_colsum", gelu_bwd_colsum);
   m.impl("wgrad", wgrad);

@@ -86,12 +86,8 @@ class OpenAIWhisperEncoder(torch.nn.Module):
         else:  # audio > 30 s: truncated to the positional table (:163-165)
             x = x[:, :max_pos, :] + enc.positional_embedding
         x = self.dropout(x)
-        last = len(enc.blocks) - 1
-        for layer, block in enumerate(enc.blocks):
-            x, _ = block(x, kv_len=kv_len)
-            if layer < last:
-                x = self.dropout(x)
-        x = enc.ln_post(x)
+        x = W.run_blocks(enc.blocks, x, enc.ln_post, between=self.dropout,
+                         between_changes_x=self.training and self.dropout.p > 0, kv_len=kv_len)
         if ilens is not None:
             olens = 1 + (ilens - enc.conv2.kernel_size[0] + 2 * enc.conv2.padding[0]) // enc.conv2.stride[0]
             olens = torch.clamp(olens, max=max_pos)
@@ -345,14 +341,11 @@ class OpenAIWhisperDecoder(torch.nn.Module):
             mode = "fused" if usable else "compact"
         self._set_export(self.whisper_cs, mode, self.guided_pattern)
         attention_scores: List[torch.Tensor] = []
-        last = len(dec.blocks) - 1
-        for layer, block in enumerate(dec.blocks):
-            x, attention_map = block(x, hs_pad, mask=dec.mask, xa_len=memory_len)
-            if layer < last:
-                x = self.dropout(x)
+        def collect(layer, attention_map):
             if self.whisper_cs and layer >= self.src_layer:
                 attention_scores.append(attention_map)
-        x = dec.ln(x)
+        x = W.run_blocks(dec.blocks, x, dec.ln, between=self.dropout, between_changes_x=self.training and self.dropout.p > 0,
+                         on_block=collect, xa=hs_pad, mask=dec.mask, xa_len=memory_len)
         logits = dec.vocab_logits(x, lazy=self.fused_loss)
         if self.whisper_cs:
             if mode == "fused":

@@ -618,13 +618,68 @@ class _AdapterLayerNormFn(torch.autograd.Function):
         rows, D = x2.shape
         dts = ctx.param_dtypes
         dz2 = _rows(dz.to(x2.dtype), D)
-        ds, dgamma, dbeta, db2 = _ln_bwd(dz2, s, g32, mean, rstd, True, need_dxsum=True)
-        dg = ds @ w2c                                  # (rows, bottleneck)
-        dw2 = adapter_wgrad(ds, g, dts[2])                          # ds^T g: (D, bottleneck)
-        dh1, db1 = gelu_bwd_colsum(dg, h1)
-        dw1 = adapter_wgrad(x2, dh1, dts[0], transpose_out=True)   # (x^T dh1)^T = dh1^T x: (bottleneck, D)
-        dx = _linear_residual_raw(dh1, w1c, None, ds, w_kn=True)  # ds + dh1 @ W1: the residual branch's gradient rides the GEMM
-        return (dx.view(ctx.shape), dw1, db1.to(dts[1]), dw2, db2.to(dts[3]), dgamma.to(dts[4]), dbeta.to(dts[5]), None)
+        return _adapter_ln_backward(ctx, x2, h1, g, s, mean, rstd, w1c, w2c, g32, dz2)
+
+
+class _AdapterLayerNormPairFn(torch.autograd.Function):
+    """(z, y2) = (LN_a(x + adapter(x)), LN_b(z)): the adapter's post-LayerNorm, whose output replaces the residual stream,
+    together with the FROZEN pre-LayerNorm of the residual branch that follows (whisper/model.py:234-246; across blocks:
+    the next block's ``attn_ln`` / the encoder's ``ln_post``).  Forward: both normalisations in ONE kernel (the row is
+    read once); backward: LN_b's backward with the residual-path gradient of z added in the same pass, then the adapter /
+    LN_a backward of ``_AdapterLayerNormFn``.  Same values as the two nodes it replaces."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, eps, gamma2, beta2, eps2):
+        _require_cuda(x, "x")
+        if x.dtype not in _DTYPES:
+            raise L.AgaError(f"adapter_layer_norm supports fp32 and bf16 rows, got {x.dtype}")
+        D = x.shape[-1]
+        x2 = _rows(x, D)
+        dt = x2.dtype
+        w1c, w2c = cast_trainable(w1, dt), cast_trainable(w2, dt)
+        h1 = torch.addmm(cast_trainable(b1, dt), x2, w1c.t())
+        g = torch.nn.functional.gelu(h1)
+        y = torch.addmm(cast_trainable(b2, dt), g, w2c.t())
+        g32 = gamma.detach().float().contiguous()
+        be32 = beta.detach().float().contiguous()
+        g2_32 = gamma2.detach().float().contiguous()
+        be2_32 = beta2.detach().float().contiguous()
+        tm = _Timed("layernorm_fwd", 5.0 * x2.numel() * x2.element_size(), x2.device)
+        z, s, mean, rstd, y2, mean2, rstd2 = L.torch_ops().layernorm_pair_fwd(x2, y, g32, be32, float(eps), True, g2_32, be2_32,
+                                                                            float(eps2))
+        tm.done(x2.device)
+        ctx.save_for_backward(x2, h1, g, s, mean, rstd, w1c, w2c, g32, z, g2_32, mean2, rstd2)
+        ctx.shape = x.shape
+        ctx.param_dtypes = tuple(t.dtype for t in (w1, b1, w2, b2, gamma, beta))
+        return z.view(x.shape), y2.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dz, dy2):
+        x2, h1, g, s, mean, rstd, w1c, w2c, g32, z, g2_32, mean2, rstd2 = ctx.saved_tensors
+        rows, D = x2.shape
+        if dy2 is not None:  # d z = LN_b'(dy2) + (gradient that reached z through the residual connection)
+            dres = None if dz is None else _rows(dz.to(x2.dtype), D)
+            dz2, _, _, _ = _ln_bwd(_rows(dy2.to(x2.dtype), D), z, g2_32, mean2, rstd2, False, dres2=dres)
+        else:
+            dz2 = _rows(dz.to(x2.dtype), D)
+        return _adapter_ln_backward(ctx, x2, h1, g, s, mean, rstd, w1c, w2c, g32, dz2) + (None, None, None)
+
+
+def _adapter_ln_backward(ctx, x2, h1, g, s, mean, rstd, w1c, w2c, g32, dz2):
+    dts = ctx.param_dtypes
+    ds, dgamma, dbeta, db2 = _ln_bwd(dz2, s, g32, mean, rstd, True, need_dxsum=True)
+    dg = ds @ w2c                                  # (rows, bottleneck)
+    dw2 = adapter_wgrad(ds, g, dts[2])                          # ds^T g: (D, bottleneck)
+    dh1, db1 = gelu_bwd_colsum(dg, h1)
+    dw1 = adapter_wgrad(x2, dh1, dts[0], transpose_out=True)   # (x^T dh1)^T = dh1^T x: (bottleneck, D)
+    dx = _linear_residual_raw(dh1, w1c, None, ds, w_kn=True)  # ds + dh1 @ W1: the residual branch's gradient rides the GEMM
+    return (dx.view(ctx.shape), dw1, db1.to(dts[1]), dw2, db2.to(dts[3]), dgamma.to(dts[4]), dbeta.to(dts[5]), None)
+
+
+def adapter_layer_norm_pair(x, w1, b1, w2, b2, gamma, beta, eps, gamma2, beta2, eps2):
+    """``z = ln_a(x + adapter(x))`` and ``ln_b(z)`` (ln_b frozen) as one node: see ``_AdapterLayerNormPairFn``.  Returns
+    (z, ln_b(z)); use z as the residual stream and the second value as the next branch's input."""
+    return _AdapterLayerNormPairFn.apply(x, w1, b1, w2, b2, gamma, beta, float(eps), gamma2, beta2, float(eps2))
 
 
 def adapter_layer_norm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,

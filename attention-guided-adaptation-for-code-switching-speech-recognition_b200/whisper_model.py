@@ -294,18 +294,38 @@ class ResidualAttentionBlock(nn.Module):
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
                 kv_cache: Optional[dict] = None, kv_len: Optional[Tensor] = None, xa_len: Optional[Tensor] = None):
         """``kv_len`` / ``xa_len``: true lengths of x / xa when they are zero-padded to static shapes (device scalars)."""
-        y, x = self.attn_ln.with_residual(x)
-        x, second = self.attn(y, mask=mask, kv_cache=kv_cache, residual=x, kv_len=kv_len)  # x + attn(...)
-        if self.adapter_flag:
-            x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)  # post-LN replaces x (:234-236)
-        if self.cross_attn is not None:
-            y, x = self.cross_attn_ln.with_residual(x)
-            x = self.cross_attn(y, xa, kv_cache=kv_cache, residual=x, kv_len=xa_len)[0]
-        y, x = self.mlp_ln.with_residual(x)
-        x = self._mlp_residual(y, x)  # x + mlp(...)
-        if self.adapter_flag:
-            x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
+        x, second, _ = self.forward_chain(x, xa, mask, kv_cache, kv_len, xa_len)
         return x, second
+
+    def forward_chain(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                      kv_cache: Optional[dict] = None, kv_len: Optional[Tensor] = None, xa_len: Optional[Tensor] = None,
+                      pre: Optional[Tensor] = None, next_ln: Optional["LayerNorm"] = None):
+        """``forward`` for a chain of blocks.  ``pre``: ``self.attn_ln(x)`` already computed by the previous block's last
+        kernel; ``next_ln``: the LayerNorm the caller applies to this block's output next (the next block's ``attn_ln``,
+        ``ln_post`` / ``ln`` after the last one) — with adapters its result comes out of the adapter post-LN kernel and
+        is returned as the third value (else None).  Every adapter post-LN is followed by a pre-LN of the same tensor
+        (whisper/model.py:231-246): each such pair is one kernel and one read of the row."""
+        if pre is None:
+            y, x = self.attn_ln.with_residual(x)
+        else:
+            y = pre
+        x, second = self.attn(y, mask=mask, kv_cache=kv_cache, residual=x, kv_len=kv_len)  # x + attn(...)
+        y = None
+        if self.adapter_flag:  # post-LN replaces x (:234-236)
+            x, y = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x,
+                                    next_ln=self.cross_attn_ln if self.cross_attn is not None else self.mlp_ln)
+        if self.cross_attn is not None:
+            if y is None:
+                y, x = self.cross_attn_ln.with_residual(x)
+            x = self.cross_attn(y, xa, kv_cache=kv_cache, residual=x, kv_len=xa_len)[0]
+            y = None
+        if y is None:
+            y, x = self.mlp_ln.with_residual(x)
+        x = self._mlp_residual(y, x)  # x + mlp(...)
+        y = None
+        if self.adapter_flag:
+            x, y = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x, next_ln=next_ln)
+        return x, second, y
 
     def step(self, x: Tensor, xa: Tensor, cache: Optional[Tuple[Tensor, Tensor, Tensor, Tensor]] = None):
         """``forward`` for the new tokens only.  ``cache`` = (self K, self V, cross K, cross V) of the prefix, or None on
@@ -313,7 +333,7 @@ class ResidualAttentionBlock(nn.Module):
         a, k, v = self.attn.step(self.attn_ln(x), *((cache[0], cache[1]) if cache is not None else (None, None)))
         x = x + a
         if self.adapter_flag:
-            x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)
+            x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)[0]
         if cache is not None:
             kc, vc = cache[2], cache[3]
         else:
@@ -322,7 +342,7 @@ class ResidualAttentionBlock(nn.Module):
         x = x + self.cross_attn.step(self.cross_attn_ln(x), cross_kv=(kc, vc))
         x = x + self.mlp(self.mlp_ln(x))
         if self.adapter_flag:
-            x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
+            x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)[0]
         return x, (k, v, kc, vc)
 
     def step_static(self, x: Tensor, kv_buf: Tensor, pos: Tensor, kv_len: Tensor, cross_kv: Tuple[Tensor, Tensor]):
@@ -330,11 +350,11 @@ class ResidualAttentionBlock(nn.Module):
         and every residual add rides a GEMM (17 launches per block instead of 27)."""
         x = self.attn.step_static(self.attn_ln(x), kv_buf, pos, kv_len, residual=x)
         if self.adapter_flag:
-            x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)
+            x = self._adapter_ln(self.adapter_attn, self.adapter_attn_ln, x)[0]
         x = self.cross_attn.step(self.cross_attn_ln(x), cross_kv=cross_kv, residual=x)
         x = self._mlp_residual(self.mlp_ln(x), x)
         if self.adapter_flag:
-            x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)
+            x = self._adapter_ln(self.adapter_mlp, self.adapter_mlp_ln, x)[0]
         return x
 
     def _mlp_residual(self, y: Tensor, x: Tensor) -> Tensor:
@@ -357,17 +377,40 @@ class ResidualAttentionBlock(nn.Module):
                                 w2, c[1], cast_param(l2, "_b_cast", l2.bias, dt), x.to(dt))
 
     @staticmethod
-    def _adapter_ln(adapter: "Adapter", ln: "LayerNorm", x: Tensor) -> Tensor:
-        """``ln(adapter(x))`` = LN(x + W2 gelu(W1 x)) as one fused autograd node."""
+    def _adapter_ln(adapter: "Adapter", ln: "LayerNorm", x: Tensor, next_ln: Optional["LayerNorm"] = None):
+        """``ln(adapter(x))`` = LN(x + W2 gelu(W1 x)) as one fused autograd node.  With ``next_ln`` (the FROZEN pre-LayerNorm of
+        the residual branch that consumes the result next) returns ``(z, next_ln(z))`` from one kernel
+        (ops.adapter_layer_norm_pair), else ``(z, None)``."""
         m = adapter.model
+        ps = (m[0].weight, m[0].bias, m[2].weight, m[2].bias)
         if not torch.is_grad_enabled() and x.dtype != m[0].weight.dtype:
             # inference / decoding: the low-precision copies of the adapter weights are made once, not per call
             # (8 cast kernels per decoder block and token otherwise)
-            return ops.adapter_layer_norm(x, *(cast_param(lin, slot, t, x.dtype) for lin, slot, t in
-                                               ((m[0], "_w_cast", m[0].weight), (m[0], "_b_cast", m[0].bias),
-                                                (m[2], "_w_cast", m[2].weight), (m[2], "_b_cast", m[2].bias))),
-                                          ln.weight, ln.bias, ln.eps)
-        return ops.adapter_layer_norm(x, m[0].weight, m[0].bias, m[2].weight, m[2].bias, ln.weight, ln.bias, ln.eps)
+            ps = tuple(cast_param(lin, slot, t, x.dtype) for lin, slot, t in
+                       ((m[0], "_w_cast", m[0].weight), (m[0], "_b_cast", m[0].bias),
+                        (m[2], "_w_cast", m[2].weight), (m[2], "_b_cast", m[2].bias)))
+        if next_ln is not None and _native(x) and _no_grad_needed(next_ln.weight, next_ln.bias):
+            return ops.adapter_layer_norm_pair(x, *ps, ln.weight, ln.bias, ln.eps, next_ln.weight, next_ln.bias, next_ln.eps)
+        return ops.adapter_layer_norm(x, *ps, ln.weight, ln.bias, ln.eps), None
+
+
+def run_blocks(blocks, x: Tensor, final_ln: "LayerNorm", between=None, between_changes_x: bool = True, on_block=None, **kw) -> Tensor:
+    """``for block in blocks: x, second = block(x, **kw)`` then ``final_ln(x)``, with each block's leading LayerNorm (and
+    the final one) taken from the previous block's last kernel when that block ends in an adapter post-LN
+    (ResidualAttentionBlock.forward_chain).  ``between(x)``: applied to x between blocks (ESPnet's dropout); unless the
+    caller states that it leaves x as it is (``between_changes_x=False``: p = 0, or eval mode) the chaining is off;
+    ``on_block(layer, second)``: receives every block's second output."""
+    chain = between is None or not between_changes_x
+    pre = None
+    n = len(blocks)
+    for layer, block in enumerate(blocks):
+        nxt = (blocks[layer + 1].attn_ln if layer + 1 < n else final_ln) if chain else None
+        x, second, pre = block.forward_chain(x, pre=pre, next_ln=nxt, **kw)
+        if on_block is not None:
+            on_block(layer, second)
+        if between is not None and layer + 1 < n:
+            x = between(x)
+    return pre if pre is not None else final_ln(x)
 
 
 class AudioEncoder(nn.Module):
@@ -430,9 +473,7 @@ class AudioEncoder(nn.Module):
         x = self.stem(x)
         assert x.shape[1:] == self.positional_embedding.shape, "incorrect audio shape"
         x = (x + self.positional_embedding).to(x.dtype)
-        for block in self.blocks:
-            x, _ = block(x)
-        return self.ln_post(x)
+        return run_blocks(self.blocks, x, self.ln_post)
 
 
 class TextDecoder(nn.Module):
@@ -456,9 +497,7 @@ class TextDecoder(nn.Module):
         offset = next(iter(kv_cache.values())).shape[1] if kv_cache else 0
         x = self.token_embedding(x) + self.positional_embedding[offset: offset + x.shape[-1]]
         x = x.to(xa.dtype)
-        for block in self.blocks:
-            x, _ = block(x, xa, mask=self.mask, kv_cache=kv_cache)
-        x = self.ln(x)
+        x = run_blocks(self.blocks, x, self.ln, xa=xa, mask=self.mask, kv_cache=kv_cache)
         return self.vocab_logits(x)
 
     def vocab_logits(self, x: Tensor, lazy: bool = False):

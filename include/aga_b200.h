@@ -205,6 +205,12 @@ AGA_API int aga_head_vote(const float* probs, int L, int B, int H, int T, uint8_
  * ------------------------------------------------------------------------------------------ */
 AGA_API int aga_layernorm_fwd(const void* x, const void* residual, int dtype, int64_t rows, int D, const float* gamma,
                       const float* beta, float eps, void* y, void* sum_out, float* mean, float* rstd, void* stream);
+/* aga_layernorm_fwd followed, on the row just produced (as stored: rounded to dtype), by a SECOND LayerNorm (gamma2, beta2,
+ * eps2 -> y2, mean2, rstd2): ResidualAttentionBlock.forward applies the adapter's post-LN and then the next branch's pre-LN to
+ * the same tensor (W/model.py:231-246); one kernel, one read of the row.  Same results as two aga_layernorm_fwd calls. */
+AGA_API int aga_layernorm_pair_fwd(const void* x, const void* residual, int dtype, int64_t rows, int D, const float* gamma,
+                      const float* beta, float eps, void* y, void* sum_out, float* mean, float* rstd, const float* gamma2,
+                      const float* beta2, float eps2, void* y2, float* mean2, float* rstd2, void* stream);
 AGA_API int aga_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int D, const float* gamma,
                       const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                       float* dxsum, void* stream);

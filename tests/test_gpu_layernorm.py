@@ -198,3 +198,37 @@ def test_layer_norm_residual_backward_adds_residual_gradient(A, dtype, tol, rows
     assert torch.equal(res[True][0], res[False][0])
     for a, r in zip(res[True][1:], res[False][1:]):
         torch.testing.assert_close(a.float(), r.float(), rtol=tol, atol=tol * float(r.float().abs().max()))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("shape,D", [((4, 300), 768), ((6, 1000), 768), ((2, 64), 1280)])
+def test_adapter_layer_norm_pair_equals_the_two_nodes(A, dtype, tol, shape, D):
+    """ops.adapter_layer_norm_pair — the adapter post-LN and the frozen pre-LN that follows it, one forward kernel — gives
+    the values and gradients of adapter_layer_norm followed by layer_norm_residual (z feeds both the next LN and the
+    residual stream, whisper/model.py:234-246): outputs bit-identical, gradients equal up to the order of the atomics."""
+    from aga_b200 import ops
+    g = torch.Generator().manual_seed(D + shape[1])
+    Bn = D // 4
+    x = torch.randn(*shape, D, generator=g).to(dtype).cuda()
+    params = [torch.randn(Bn, D, generator=g) / D ** 0.5, 0.02 * torch.randn(Bn, generator=g),
+              torch.randn(D, Bn, generator=g) / Bn ** 0.5, 0.02 * torch.randn(D, generator=g),
+              1.0 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)]
+    g2 = (1.0 + 0.1 * torch.randn(D, generator=g)).cuda()
+    b2 = (0.1 * torch.randn(D, generator=g)).cuda()
+    m = torch.randn(D, D, generator=g).to(dtype).cuda() / D ** 0.5
+    do = torch.randn(*shape, D, generator=g).to(dtype).cuda()
+    res = {}
+    for fused in (True, False):
+        xs = x.clone().requires_grad_()
+        ps = [p.cuda().requires_grad_() for p in params]
+        if fused:
+            z, y2 = ops.adapter_layer_norm_pair(xs, *ps, 1e-5, g2, b2, 1e-5)
+        else:
+            z = ops.adapter_layer_norm(xs, *ps, 1e-5)
+            y2, z = ops.layer_norm_residual(z, g2, b2, 1e-5)
+        out = z + torch.tanh(y2 @ m)  # z is used twice, as in `x = x + f(ln(x))`
+        grads = torch.autograd.grad(out, [xs] + ps, do)
+        res[fused] = (z.detach(), y2.detach(), grads)
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    for a, r in zip(res[True][2], res[False][2]):
+        torch.testing.assert_close(a.float(), r.float(), rtol=tol, atol=tol * float(r.float().abs().max()))
