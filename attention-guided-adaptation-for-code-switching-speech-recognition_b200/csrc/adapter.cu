@@ -7,6 +7,7 @@
 // rows with a grid stride keeping its columns' partial sums in registers, one smem reduction + one atomicAdd per
 // column per CTA at the end.  gelu' is the exact (erf) form in fp32, as at::gelu_backward computes it.
 #include "aga_common.cuh"
+#include "gelu_math.cuh"
 
 #include <algorithm>
 
@@ -18,6 +19,9 @@ constexpr int kThreads = 256;
 template <typename T> struct Pack;
 template <> struct Pack<float> {
   static constexpr int kVec = 4;
+  using Raw = float4;
+  static __device__ __forceinline__ Raw load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -28,6 +32,16 @@ template <> struct Pack<float> {
 };
 template <> struct Pack<__nv_bfloat16> {
   static constexpr int kVec = 8;
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(w[e] << 16);
+      v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     const uint4 t = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
@@ -62,19 +76,39 @@ gelu_bwd_colsum_kernel(const T* __restrict__ dg, const T* __restrict__ h, int64_
 #pragma unroll
   for (int e = 0; e < V; ++e) acc[e] = 0.f;
   if (active) {
-    for (int64_t r = int64_t(blockIdx.x) * rpb + ro; r < rows; r += int64_t(gridDim.x) * rpb) {
-      const int64_t off = r * cols + cg * V;
-      float x[V], g[V], o[V];
-      Pack<T>::load(h + off, x);
-      Pack<T>::load(dg + off, g);
+    // four rows per trip, their eight 16-byte loads issued before any arithmetic: with one row per trip the kernel ran
+    // at 2.6x its HBM time on load latency (240 threads x 32 bytes in flight per CTA)
+    constexpr int kU = 4;
+    const int64_t step = int64_t(gridDim.x) * rpb;
+    for (int64_t r0 = int64_t(blockIdx.x) * rpb + ro; r0 < rows; r0 += kU * step) {
+      typename Pack<T>::Raw xr[kU], gr[kU];
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const float cdf = 0.5f * (1.0f + erff(x[e] * 0.70710678118654752440f));
-        const float pdf = expf(-0.5f * x[e] * x[e]) * 0.39894228040143267794f;
-        o[e] = g[e] * fmaf(x[e], pdf, cdf);
-        acc[e] += to_f32<T>(from_f32<T>(o[e]));  // the bias gradient sums the ROUNDED dh, as dh.sum(0) would
+      for (int u = 0; u < kU; ++u) {
+        const int64_t r = r0 + u * step;
+        if (r < rows) {
+          xr[u] = Pack<T>::load_raw(h + r * cols + cg * V);
+          gr[u] = Pack<T>::load_raw(dg + r * cols + cg * V);
+        }
       }
-      Pack<T>::store(dh + off, o);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t r = r0 + u * step;
+        if (r >= rows) break;
+        float x[V], g[V], o[V];
+        Pack<T>::unpack(xr[u], x);
+        Pack<T>::unpack(gr[u], g);
+        // gelu'(x) = Phi(x) + x phi(x) on PAIRS (packed fp32x2 FMAs, erf by Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7:
+        // gelu_math.cuh)
+#pragma unroll
+        for (int e = 0; e < V; e += 2) {
+          const float2 d = dgelu_erf2(make_float2(x[e], x[e + 1]));
+          o[e] = g[e] * d.x;
+          o[e + 1] = g[e + 1] * d.y;
+          acc[e] += to_f32<T>(from_f32<T>(o[e]));  // the bias gradient sums the ROUNDED dh, as dh.sum(0) would
+          acc[e + 1] += to_f32<T>(from_f32<T>(o[e + 1]));
+        }
+        Pack<T>::store(dh + r * cols + cg * V, o);
+      }
     }
 #pragma unroll
     for (int e = 0; e < V; ++e) red[ro * cols + cg * V + e] = acc[e];
