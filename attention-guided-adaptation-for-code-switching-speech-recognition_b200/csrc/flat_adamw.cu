@@ -32,12 +32,22 @@ __global__ void __launch_bounds__(kThreads) flat_norm_kernel(const float* __rest
   float acc = 0.f;
   const int64_t n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += int64_t(gridDim.x) * kThreads) {
+  // four independent 16-byte loads per trip (one load per trip ran at 1.6 TB/s on load latency: ncu, profiles/r2_new_kernels.md)
+  const int64_t stride = int64_t(gridDim.x) * kThreads;
+  int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 v0 = __ldg(g4 + i), v1 = __ldg(g4 + i + stride), v2 = __ldg(g4 + i + 2 * stride), v3 = __ldg(g4 + i + 3 * stride);
+    acc = fmaf(v0.x, v0.x, acc); acc = fmaf(v0.y, v0.y, acc); acc = fmaf(v0.z, v0.z, acc); acc = fmaf(v0.w, v0.w, acc);
+    acc = fmaf(v1.x, v1.x, acc); acc = fmaf(v1.y, v1.y, acc); acc = fmaf(v1.z, v1.z, acc); acc = fmaf(v1.w, v1.w, acc);
+    acc = fmaf(v2.x, v2.x, acc); acc = fmaf(v2.y, v2.y, acc); acc = fmaf(v2.z, v2.z, acc); acc = fmaf(v2.w, v2.w, acc);
+    acc = fmaf(v3.x, v3.x, acc); acc = fmaf(v3.y, v3.y, acc); acc = fmaf(v3.z, v3.z, acc); acc = fmaf(v3.w, v3.w, acc);
+  }
+  for (; i < n4; i += stride) {
     const float4 v = __ldg(g4 + i);
     acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
   }
   if (blockIdx.x == 0)
-    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += kThreads) acc = fmaf(g[i], g[i], acc);
+    for (int64_t j = (n4 << 2) + threadIdx.x; j < n; j += kThreads) acc = fmaf(g[j], g[j], acc);
   __shared__ double red[kThreads / 32];
   __shared__ bool last;
   const double d = double(warp_sum(acc));
@@ -52,18 +62,27 @@ __global__ void __launch_bounds__(kThreads) flat_norm_kernel(const float* __rest
     last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {  // the whole last block: strided partial sums, then a fixed-shape tree — the same bits on every run
+    __shared__ double tree[kThreads];
     __threadfence();
     double t = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) t += *(volatile double*)&ws->partial[b];  // fixed order: the same bits on every run
-    const float norm = float(sqrt(t));
-    *norm_out = norm;
-    if (isfinite(norm)) {
-      if (step) *step += 1.0f;
-    } else if (skipped) {
-      *skipped += 1.0f;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) t += *(volatile double*)&ws->partial[b];
+    tree[threadIdx.x] = t;
+    __syncthreads();
+    for (int w = kThreads / 2; w > 0; w >>= 1) {
+      if (int(threadIdx.x) < w) tree[threadIdx.x] += tree[threadIdx.x + w];
+      __syncthreads();
     }
-    ws->ticket = 0;  // ready for the next launch
+    if (threadIdx.x == 0) {
+      const float norm = float(sqrt(tree[0]));
+      *norm_out = norm;
+      if (isfinite(norm)) {
+        if (step) *step += 1.0f;
+      } else if (skipped) {
+        *skipped += 1.0f;
+      }
+      ws->ticket = 0;  // ready for the next launch
+    }
   }
 }
 
