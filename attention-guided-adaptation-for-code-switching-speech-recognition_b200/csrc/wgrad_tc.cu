@@ -27,7 +27,8 @@ using namespace ptx;
 constexpr int kWK = 64;                  // contraction rows per stage
 constexpr int kWPanel = kWK * 128;       // one panel: 64 rows x 64 bf16 = 8 KiB
 constexpr int kWTmaWarp = 0, kWMmaWarp = 1, kWEpiWarp0 = 2;
-constexpr int kWThreads = 6 * 32;
+constexpr int kWEpiWarps = 8;           // two per TMEM lane quadrant, half of the tile's columns each
+constexpr int kWThreads = (2 + kWEpiWarps) * 32;
 
 struct WSmem {
   uint64_t full[4], empty[4], acc_full;
@@ -76,26 +77,31 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   const int n_ksteps = (min(a.k_chunk, a.rows - k_begin) + kWK - 1) / kWK;
   const uint32_t tmem_cols = a.mt == 1 ? 256u : 512u;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < a.n_stages; ++s) {
-      mbar_init(&sb->full[s], 1);
-      mbar_init(&sb->empty[s], 1);
+  // The producer warp initialises the barriers itself and starts fetching at once (a short kernel: the first loads'
+  // DRAM latency is a fifth of its life); everybody else meets it at a named barrier, after the TMEM allocation.
+  if (warp == kWTmaWarp) {
+    if (lane == 0) {
+      for (int s = 0; s < a.n_stages; ++s) {
+        mbar_init(&sb->full[s], 1);
+        mbar_init(&sb->empty[s], 1);
+      }
+      mbar_init(&sb->acc_full, 1);
+      fence_barrier_init();
+      prefetch_tensormap(&map_a);
+      prefetch_tensormap(&map_b);
     }
-    mbar_init(&sb->acc_full, 1);
-    fence_barrier_init();
+    __syncwarp();
+    named_bar_arrive(1, kWThreads);
+  } else {
+    if (warp == kWMmaWarp) {
+      tmem_alloc(&sb->tmem_base, tmem_cols);
+      tmem_relinquish();
+    }
+    tc_fence_before();
+    named_bar_sync(1, kWThreads);
+    tc_fence_after();
   }
-  if (warp == kWMmaWarp) {
-    tmem_alloc(&sb->tmem_base, tmem_cols);
-    tmem_relinquish();
-  }
-  if (warp == kWTmaWarp && lane == 0) {
-    prefetch_tensormap(&map_a);
-    prefetch_tensormap(&map_b);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sb->tmem_base;
+  const uint32_t tmem = warp == kWTmaWarp ? 0u : sb->tmem_base;
 
   if (warp == kWTmaWarp) {
     for (int it = 0; it < n_ksteps; ++it) {
@@ -137,14 +143,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     // TMEM lane = column of a = the CONTIGUOUS index of the output: for a fixed output row the 32 lanes of a warp add
     // 32 consecutive floats
     const int quad = warp & 3;  // TMEM lanes [32 quad, +32)
+    const int chalf = (warp - kWEpiWarp0) >> 2;  // which half of the tile's columns
     const uint32_t lane_base = uint32_t(quad * 32);
+    const int c_lo = chalf * (n_tile / 2), c_hi = c_lo + n_tile / 2;  // n_tile is a multiple of 64: halves of whole 32-column chunks
     mbar_wait(&sb->acc_full, 0);
     tc_fence_after();
     for (int t = 0; t < a.mt; ++t) {
       const int m = m0 + 128 * t + int(lane_base) + lane;
       if (m0 + 128 * t + int(lane_base) >= a.M) break;  // (warp-uniform: this quadrant is past the matrix)
       float* o = a.out + int64_t(n0) * a.M + m;
-      for (int c0 = 0; c0 < n_tile; c0 += 32) {
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + (lane_base << 16) + 256 * t + c0, v);
         tmem_wait_ld();
