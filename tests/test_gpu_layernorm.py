@@ -201,7 +201,7 @@ def test_layer_norm_residual_backward_adds_residual_gradient(A, dtype, tol, rows
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("shape,D", [((4, 300), 768), ((6, 1000), 768), ((2, 64), 1280), ((5, 1000), 1280)])
+@pytest.mark.parametrize("shape,D", [((4, 300), 768), ((6, 1000), 768), ((2, 64), 1280), ((5, 1000), 1280), ((16, 1500), 768)])  # last: the BASELINE size
 def test_adapter_layer_norm_pair_equals_the_two_nodes(A, dtype, tol, shape, D):
     """ops.adapter_layer_norm_pair — the adapter post-LN and the frozen pre-LN that follows it, one forward kernel — gives
     the values and gradients of adapter_layer_norm followed by layer_norm_residual (z feeds both the next LN and the
